@@ -1,0 +1,102 @@
+/* libsnnb200 -- C ABI of the B200-native spiking-detector hot path.
+ *
+ * The reference (Anannayjain/SNN_Object_DetectionDDP) is pure Python/PyTorch and has NO FFI; this
+ * header is the boundary a maintainer binds with ctypes from the reference's model.py/train.py
+ * (see INTEGRATION.md).  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; snn_last_error() returns a
+ *    thread-local message.  Nothing throws across the ABI.
+ *  - all pointers are DEVICE pointers owned by the caller (PyTorch allocates everything,
+ *    including workspaces); `stream` is a cudaStream_t passed as void*.
+ *  - activations are NHWC with the T*B batch folded into N ("NB"); element (n,h,w,c) of a view
+ *    lives at ptr[((n*H+h)*W+w)*ld + c]  (ld >= C lets a view be a channel slice).
+ *  - bf16 = raw uint16 storage; weights for the tensor-core convs are bf16 [rows][taps][K]
+ *    (fprop: rows = Cout, K = Cin;  dgrad: rows = Cin, K = Cout), taps = kh*kw in (kh,kw) order.
+ *  - compute dtype: bf16 operands, fp32 accumulate (tcgen05), fp32 everywhere else.
+ */
+#ifndef SNN_B200_H
+#define SNN_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* snn_last_error(void);
+int snn_version(void);
+/* test/debug knobs (stage caps, descriptor variants); key in [0,8) */
+void snn_debug_set(int key, int value);
+
+/* conv geometries on the path (reference model.py:13 k3 s1/s2 p1; model.py:119 k1; model.py:36 convT k2 s2) */
+enum { SNN_GEOM_3x3_S1 = 0, SNN_GEOM_3x3_S2 = 1, SNN_GEOM_1x1 = 2, SNN_GEOM_T2x2_S2 = 3 };
+enum { SNN_ACT_LIF = 0, SNN_ACT_SILU = 1 };
+
+/* ---- spike convolutions: replaces nn.Conv2d / nn.ConvTranspose2d forward+backward in
+ *      ConvBlock (model.py:13,18), UpBlock.up (model.py:36,42), ConvLSTM2d.conv (model.py:55,66),
+ *      out_p3/4/5 (model.py:119,146).  (H, W) are always the conv INPUT's spatial dims.
+ *      x1 != NULL convolves the channel concatenation cat([x0, x1]) (model.py:45,66,126,127)
+ *      without materialising it. ---- */
+int snn_conv_fprop(int geom, int NB, int H, int W,
+                   const void* x0, int C0, long long ld0, const void* x1, int C1, long long ld1,
+                   const void* w_bf16, int w_rows, int w_K, int w_coff, int Cout, int w_row_off,
+                   const float* bias, void* out, int out_is_f32, long long out_ld, int out_coff,
+                   int accumulate, void* stream);
+int snn_conv_dgrad(int geom, int NB, int H, int W,
+                   const void* dy, int Cout, long long ld_dy,
+                   const void* wt_bf16, int wt_rows, int ci_off, int Ci,
+                   void* dx, int dx_is_f32, long long dx_ld, int dx_coff, int accumulate, void* stream);
+/* dw (fp32 [Cout][taps][w_K]) += ... ; caller zeroes it once per step */
+int snn_conv_wgrad(int geom, int NB, int H, int W,
+                   const void* x, int Ci, long long ld_x, const void* dy, int Cout, long long ld_dy,
+                   float* dw, int w_K, int w_coff, void* stream);
+/* fp32 master [N][T][K] -> bf16 same layout (w_bf16, may be NULL) and bf16 [K][T][N] (wt_bf16, may be NULL) */
+int snn_weight_prep(const float* w, void* w_bf16, void* wt_bf16, int N, int T, int K, void* stream);
+
+/* ---- neuron layer: replaces `self.silu(self.bn(.))` of ConvBlock.forward (model.py:14-18)
+ *      y is the conv output, fp32 [T][P][C].  Train-mode BN statistics are per timestep
+ *      (the reference calls the module once per frame, train.py:64-66). ---- */
+int snn_bn_stats(const float* y, double* sums /*[T][2][C]*/, int T, int P, int C, void* stream);
+int snn_bn_finalize(const double* sums, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var,
+                    float* scale, float* shift, float* mean, float* invstd /* each [T][C] (train) or [C] (eval) */,
+                    int T, int C, int P, float eps, float momentum, int training, void* stream);
+/* fused BN affine + multi-step LIF (or SiLU): out bf16 [T][P][C]; mask = 1 bit/neuron [T][P*C/8] (LIF, may be NULL);
+ * v_init / v_final fp32 [P][C] may be NULL (zero initial membrane / state not needed). ss_stride_t = C (train) or 0 (eval). */
+int snn_bn_act_fwd(int act, const float* y, const float* scale, const float* shift, const float* v_init,
+                   void* out_bf16, uint8_t* mask, float* v_final, int T, long long n_per_t, int C,
+                   int ss_stride_t, float beta, float theta, void* stream);
+/* reverse-time surrogate-gradient scan. training!=0: writes gx fp32 [T][P][C] and red [T][2][C]
+ * (sum gx, sum gx*xhat); training==0: writes dy bf16 = gx*scale directly. */
+int snn_bn_act_bwd(int act, int training, const float* y, const float* scale, const float* shift,
+                   const float* mean, const float* invstd, const float* v_init,
+                   const void* gs_bf16, const float* gv_final,
+                   float* gx, void* dy_bf16, float* gv_init, float* red,
+                   int T, int P, int C, int ss_stride_t, float beta, float theta, float alpha, void* stream);
+/* BN input gradient from gx and the reductions; dgamma/dbeta (+=) */
+int snn_bn_bwd_dx(const float* red, const float* gamma, const float* gx, const float* y,
+                  const float* scale, const float* mean, const float* invstd, float* coef /*[T][2][C]*/,
+                  float* dgamma, float* dbeta, void* dy_bf16, int T, int P, int C, void* stream);
+
+/* ---- ConvLSTM gate math (model.py:67-69): gates fp32 [P][4*Ch] in i|f|g|o order ---- */
+int snn_lstm_gates_fwd(const float* gates, const float* c_prev, float* c_next, float* h_next,
+                       void* h_bf16, long long P, int Ch, void* stream);
+int snn_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_next,
+                       const float* dh, const float* dc_in, void* dgates_bf16, float* dc_prev,
+                       long long P, int Ch, void* stream);
+
+/* ---- layout conversion at the nn.Module boundary (reference tensors are NCHW fp32) ---- */
+int snn_nchw_to_nhwc(const float* in, void* out, int out_is_bf16, int NB, int C, int HW,
+                     long long out_ld, int out_coff, void* stream);
+int snn_nhwc_to_nchw(const void* in, int in_is_bf16, float* out, int NB, int C, int HW,
+                     long long in_ld, int in_coff, void* stream);
+
+/* ---- optimizer: replaces clip_grad_norm_(10) + AdamW.step (train.py:77-78) over one flat buffer.
+ *      hp (device, 8 floats) = {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, max_norm} ---- */
+int snn_grad_sumsq(const float* g, long long n, double* acc, int zero_first, void* stream);
+int snn_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
+                   const float* hp, const double* sumsq, float* gnorm_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,93 @@
+"""ctypes binding of libsnnb200.so (C ABI in include/snn_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsnnb200.so")
+
+GEOM_3x3_S1, GEOM_3x3_S2, GEOM_1x1, GEOM_T2x2_S2 = 0, 1, 2, 3
+ACT_LIF, ACT_SILU = 0, 1
+GEOM_TAPS = {GEOM_3x3_S1: 9, GEOM_3x3_S2: 9, GEOM_1x1: 1, GEOM_T2x2_S2: 4}
+
+_c = ctypes
+_P, _I, _L, _F = _c.c_void_p, _c.c_int, _c.c_longlong, _c.c_float
+
+_SIGNATURES = {
+    "snn_conv_fprop": [_I, _I, _I, _I, _P, _I, _L, _P, _I, _L, _P, _I, _I, _I, _I, _I, _P, _P, _I, _L, _I, _I, _P],
+    "snn_conv_dgrad": [_I, _I, _I, _I, _P, _I, _L, _P, _I, _I, _I, _P, _I, _L, _I, _I, _P],
+    "snn_conv_wgrad": [_I, _I, _I, _I, _P, _I, _L, _P, _I, _L, _P, _I, _I, _P],
+    "snn_weight_prep": [_P, _P, _P, _I, _I, _I, _P],
+    "snn_bn_stats": [_P, _P, _I, _I, _I, _P],
+    "snn_bn_finalize": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P],
+    "snn_bn_act_fwd": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _F, _P],
+    "snn_bn_act_bwd": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
+    "snn_bn_bwd_dx": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "snn_lstm_gates_fwd": [_P, _P, _P, _P, _P, _L, _I, _P],
+    "snn_lstm_gates_bwd": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
+    "snn_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _L, _I, _P],
+    "snn_nhwc_to_nchw": [_P, _I, _P, _I, _I, _I, _L, _I, _P],
+    "snn_grad_sumsq": [_P, _L, _P, _I, _P],
+    "snn_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P],
+}
+
+_lib = None
+launch_count = 0  # number of libsnnb200 kernel-launching calls made (bench.py reports it)
+
+
+class SnnKernelError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    return sorted(list(_SIGNATURES) + ["snn_last_error", "snn_version", "snn_debug_set"])
+
+
+def lib():
+    """Load libsnnb200.so (once). Raises if it was not built: the product has no CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise SnnKernelError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no fallback path.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, args in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = _I
+        L.snn_last_error.restype = ctypes.c_char_p
+        L.snn_version.restype = _I
+        L.snn_debug_set.argtypes = [_I, _I]
+        L.snn_debug_set.restype = None
+        _lib = L
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    global launch_count
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise SnnKernelError(f"{name} failed (rc={rc}): {lib().snn_last_error().decode()}")
+    launch_count += 1
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise SnnKernelError("snn_object_detectionddp_b200 kernels run on CUDA tensors only (no CPU fallback)")

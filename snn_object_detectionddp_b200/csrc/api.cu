@@ -1,0 +1,137 @@
+// extern "C" boundary of libsnnb200.so (declared in include/snn_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/snn_b200.h"
+#include "common.cuh"
+
+namespace snn {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return 1;
+}
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+// launchers defined in the other translation units
+void debug_set(int k, int v);
+int conv_fprop(int, int, int, int, const void*, int, long long, const void*, int, long long, const void*, int, int, int, int,
+               int, const float*, void*, int, long long, int, int, cudaStream_t);
+int conv_dgrad(int, int, int, int, const void*, int, long long, const void*, int, int, int, void*, int, long long, int, int,
+               cudaStream_t);
+int conv_wgrad(int, int, int, int, const void*, int, long long, const void*, int, long long, float*, int, int, cudaStream_t);
+int launch_weight_prep(const float*, __nv_bfloat16*, __nv_bfloat16*, int, int, int, cudaStream_t);
+int launch_bn_stats(const float*, double*, int, int, int, cudaStream_t);
+int launch_bn_finalize(const double*, const float*, const float*, float*, float*, float*, float*, float*, float*, int, int, int,
+                       float, float, int, cudaStream_t);
+int launch_bn_act_fwd(int, const float*, const float*, const float*, const float*, __nv_bfloat16*, uint8_t*, float*, int,
+                      long long, int, int, float, float, cudaStream_t);
+int launch_bn_act_bwd(int, int, const float*, const float*, const float*, const float*, const float*, const float*,
+                      const __nv_bfloat16*, const float*, float*, __nv_bfloat16*, float*, float*, int, int, int, int, float,
+                      float, float, cudaStream_t);
+int launch_bn_bwd_dx(const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*,
+                     float*, float*, __nv_bfloat16*, int, int, int, cudaStream_t);
+int launch_lstm_gates_fwd(const float*, const float*, float*, float*, __nv_bfloat16*, long long, int, cudaStream_t);
+int launch_lstm_gates_bwd(const float*, const float*, const float*, const float*, const float*, __nv_bfloat16*, float*,
+                          long long, int, cudaStream_t);
+int launch_nchw_to_nhwc(const float*, void*, int, int, int, int, long long, int, cudaStream_t);
+int launch_nhwc_to_nchw(const void*, int, float*, int, int, int, long long, int, cudaStream_t);
+int launch_sumsq(const float*, long long, double*, int, cudaStream_t);
+int launch_adamw(float*, const float*, float*, float*, __nv_bfloat16*, long long, const float*, const double*, float*,
+                 cudaStream_t);
+
+}  // namespace snn
+
+using namespace snn;
+#define ST ((cudaStream_t)stream)
+
+extern "C" {
+
+const char* snn_last_error(void) { return g_err; }
+int snn_version(void) { return 100; }
+void snn_debug_set(int key, int value) { debug_set(key, value); }
+
+int snn_conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long long ld0, const void* x1, int C1,
+                   long long ld1, const void* w, int w_rows, int w_K, int w_coff, int Cout, int w_row_off,
+                   const float* bias, void* out, int out_is_f32, long long out_ld, int out_coff, int accumulate,
+                   void* stream) {
+    return conv_fprop(geom, NB, H, W, x0, C0, ld0, x1, C1, ld1, w, w_rows, w_K, w_coff, Cout, w_row_off, bias, out,
+                      out_is_f32, out_ld, out_coff, accumulate, ST);
+}
+int snn_conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long long ld_dy, const void* wt, int wt_rows,
+                   int ci_off, int Ci, void* dx, int dx_is_f32, long long dx_ld, int dx_coff, int accumulate, void* stream) {
+    return conv_dgrad(geom, NB, H, W, dy, Cout, ld_dy, wt, wt_rows, ci_off, Ci, dx, dx_is_f32, dx_ld, dx_coff, accumulate, ST);
+}
+int snn_conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long ld_x, const void* dy, int Cout,
+                   long long ld_dy, float* dw, int w_K, int w_coff, void* stream) {
+    return conv_wgrad(geom, NB, H, W, x, Ci, ld_x, dy, Cout, ld_dy, dw, w_K, w_coff, ST);
+}
+int snn_weight_prep(const float* w, void* wf, void* wt, int N, int T, int K, void* stream) {
+    return launch_weight_prep(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wt, N, T, K, ST);
+}
+int snn_bn_stats(const float* y, double* sums, int T, int P, int C, void* stream) { return launch_bn_stats(y, sums, T, P, C, ST); }
+int snn_bn_finalize(const double* sums, const float* gamma, const float* beta, float* rm, float* rv, float* scale,
+                    float* shift, float* mean, float* invstd, int T, int C, int P, float eps, float momentum, int training,
+                    void* stream) {
+    return launch_bn_finalize(sums, gamma, beta, rm, rv, scale, shift, mean, invstd, T, C, P, eps, momentum, training, ST);
+}
+int snn_bn_act_fwd(int act, const float* y, const float* scale, const float* shift, const float* v_init, void* out,
+                   uint8_t* mask, float* v_final, int T, long long n_per_t, int C, int ss_stride_t, float beta, float theta,
+                   void* stream) {
+    return launch_bn_act_fwd(act, y, scale, shift, v_init, (__nv_bfloat16*)out, mask, v_final, T, n_per_t, C, ss_stride_t,
+                             beta, theta, ST);
+}
+int snn_bn_act_bwd(int act, int training, const float* y, const float* scale, const float* shift, const float* mean,
+                   const float* invstd, const float* v_init, const void* gs, const float* gv_final, float* gx, void* dy,
+                   float* gv_init, float* red, int T, int P, int C, int ss_stride_t, float beta, float theta, float alpha,
+                   void* stream) {
+    return launch_bn_act_bwd(act, training, y, scale, shift, mean, invstd, v_init, (const __nv_bfloat16*)gs, gv_final, gx,
+                             (__nv_bfloat16*)dy, gv_init, red, T, P, C, ss_stride_t, beta, theta, alpha, ST);
+}
+int snn_bn_bwd_dx(const float* red, const float* gamma, const float* gx, const float* y, const float* scale,
+                  const float* mean, const float* invstd, float* coef, float* dgamma, float* dbeta, void* dy, int T, int P,
+                  int C, void* stream) {
+    return launch_bn_bwd_dx(red, gamma, gx, y, scale, mean, invstd, coef, dgamma, dbeta, (__nv_bfloat16*)dy, T, P, C, ST);
+}
+int snn_lstm_gates_fwd(const float* gates, const float* c_prev, float* c_next, float* h_next, void* h_bf16, long long P,
+                       int Ch, void* stream) {
+    return launch_lstm_gates_fwd(gates, c_prev, c_next, h_next, (__nv_bfloat16*)h_bf16, P, Ch, ST);
+}
+int snn_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_next, const float* dh, const float* dc_in,
+                       void* dgates, float* dc_prev, long long P, int Ch, void* stream) {
+    return launch_lstm_gates_bwd(gates, c_prev, c_next, dh, dc_in, (__nv_bfloat16*)dgates, dc_prev, P, Ch, ST);
+}
+int snn_nchw_to_nhwc(const float* in, void* out, int out_is_bf16, int NB, int C, int HW, long long out_ld, int out_coff,
+                     void* stream) {
+    return launch_nchw_to_nhwc(in, out, out_is_bf16, NB, C, HW, out_ld, out_coff, ST);
+}
+int snn_nhwc_to_nchw(const void* in, int in_is_bf16, float* out, int NB, int C, int HW, long long in_ld, int in_coff,
+                     void* stream) {
+    return launch_nhwc_to_nchw(in, in_is_bf16, out, NB, C, HW, in_ld, in_coff, ST);
+}
+int snn_grad_sumsq(const float* g, long long n, double* acc, int zero_first, void* stream) {
+    return launch_sumsq(g, n, acc, zero_first, ST);
+}
+int snn_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, long long n, const float* hp,
+                   const double* sumsq, float* gnorm_out, void* stream) {
+    return launch_adamw(p, g, m, v, (__nv_bfloat16*)shadow, n, hp, sumsq, gnorm_out, ST);
+}
+
+}  // extern "C"

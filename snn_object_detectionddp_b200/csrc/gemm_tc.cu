@@ -1,0 +1,657 @@
+// Spike-convolution kernels: implicit-GEMM on the 5th-gen tensor cores (tcgen05.mma, fp32
+// accumulators in TMEM), operands staged by TMA into 128B-swizzled shared memory, bf16 x bf16.
+//
+// Replaces the cuDNN fp32 convolutions behind the reference's ConvBlock / UpBlock / ConvLSTM2d /
+// output 1x1 convs (reference model.py:13, 36, 55, 119) and their autograd backward.
+//
+// Activations are NHWC bf16 with the T*B batch folded into N.  A convolution is a sum over "taps"
+// (kh,kw); every tap is a *shifted TMA box* of the activation tensor, so im2col never exists in
+// memory: padding is the TMA out-of-bounds zero fill, stride 2 / transposed conv are handled by a
+// 5-D "phase view" (N, H/2, 2, W/2, 2*C) of the same memory, channel concatenation
+// (torch.cat in model.py:45,66,126,127) by walking two tensor maps in the K loop.
+//
+//   conv_gemm_kernel  : D[pixel, cout] = sum_taps A_tap[pixel, c] * W[cout, tap, c]   (A, W K-major)
+//                       used for fprop, dgrad (with [cin][tap][cout] weights), 1x1, convT (4 phases)
+//   wgrad_gemm_kernel : dW[cout, tap, cin] += sum_pixels dY[pixel, cout] * X_tap[pixel, cin]
+//                       (both operands MN-major straight from the NHWC tensors, split-K + fp32 red)
+//
+// Warp roles (192 threads): warp0 = TMA producer + TMEM owner, warp1 = MMA issuer, warps2-5 =
+// epilogue (one TMEM lane quarter each).
+#include <mutex>
+
+#include "common.cuh"
+
+namespace snn {
+
+// ------------------------------------------------------------------------------------------
+// parameter blocks (passed __grid_constant__)
+// ------------------------------------------------------------------------------------------
+struct Seg {  // one K-segment: a tap of one source tensor
+    int src, dc, dw, dhp, dh;  // source 0/1 and coordinate offsets (channel, w, row-phase, h)
+    int wtap, wc0, nchunk;     // weight tap index, weight channel base, number of 64-wide K chunks
+};
+struct Phase {
+    int nseg, oph, opw, pad;
+    Seg seg[18];
+};
+struct ConvGemmParams {
+    int NB, Hd, Wd;                   // tile domain (pixels enumerated by the CTA grid)
+    int bn, bh, bw;                   // pixel box (bn*bh*bw == 128)
+    int tiles_w, tiles_h, tiles_n;
+    int BN;                           // UMMA N
+    int n_store;                      // valid output channels
+    int wn_off;                       // first weight row (N coordinate) of this launch
+    int stages, stage_bytes;
+    void* out;
+    const float* bias;
+    int out_f32, accumulate;
+    int Ho, Wo, os;                   // output spatial dims and pixel stride (1 or 2)
+    long long out_ld;                 // elements between consecutive output pixels
+    int out_coff;
+    int nphase;
+    Phase phase[4];
+};
+
+struct WTap {
+    int g_dc, g_dw, g_dhp, g_dh;
+    int x_dc, x_dw, x_dhp, x_dh;
+    int wtap, pad0, pad1, pad2;
+};
+struct WgradParams {
+    int NB, Hd, Wd;
+    int bn, bh, bw;                   // pixel box (product == 64)
+    int tiles_w, tiles_h, tiles_n, total_tiles;
+    int ksplit, tiles_per_split;
+    int NT;                           // cin per CTA (multiple of 64, <= 256)
+    int n_ci_tiles;
+    int Cout, Ci;
+    float* dw;
+    long long dw_ld;                  // elements between consecutive cout rows (= taps*wK)
+    int wK, w_coff;
+    int stages, stage_bytes;
+    int lbo_bytes, sbo_bytes;         // MN-major descriptor strides
+    int ntaps;
+    WTap taps[9];
+};
+
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 256;
+
+// ------------------------------------------------------------------------------------------
+// fprop-type kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int stages = p.stages;
+    const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+
+    // tile coordinates
+    const int mt = blockIdx.x;
+    const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+    const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+    const int ncol0 = blockIdx.y * p.BN;
+    const Phase& ph = p.phase[blockIdx.z];
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA0);
+            tma_prefetch_desc(&tmA1);
+            tma_prefetch_desc(&tmB);
+        }
+        tmem_alloc<kTmemCols>(smem_u32(&tmem_base_s));
+    } else if (warp == 1 && lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&tmem_full_bar), 1);
+        mbar_fence_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    int total = 0;
+    for (int s = 0; s < ph.nseg; ++s) total += ph.seg[s].nchunk;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int sg = 0; sg < ph.nseg; ++sg) {
+                const Seg g = ph.seg[sg];
+                const CUtensorMap* tmA = g.src ? &tmA1 : &tmA0;
+                for (int kc = 0; kc < g.nchunk; ++kc, ++it) {
+                    const int s = it % stages;
+                    const uint32_t par = (uint32_t)((it / stages) & 1);
+                    mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    mbar_expect_tx(fb, stage_bytes);
+                    const uint32_t a_s = sbase + (uint32_t)s * stage_bytes;
+                    tma_load_5d(a_s, tmA, fb, g.dc + kc * 64, w0 + g.dw, g.dhp, h0 + g.dh, n0);
+                    tma_load_3d(a_s + 16384u, &tmB, fb, g.wc0 + kc * 64, g.wtap, p.wn_off + ncol0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
+            for (int it = 0; it < total; ++it) {
+                const int s = it % stages;
+                const uint32_t par = (uint32_t)((it / stages) & 1);
+                mbar_wait(smem_u32(&full_bar[s]), par);
+                tc_fence_after();
+                const uint32_t a_s = sbase + (uint32_t)s * stage_bytes;
+                const uint32_t b_s = a_s + 16384u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    umma_bf16(tmem_base, umma_desc_sw128(a_s + k * 32, 16, 1024), umma_desc_sw128(b_s + k * 32, 16, 1024),
+                              idesc, (uint32_t)((it | k) != 0));
+                }
+                umma_commit(smem_u32(&empty_bar[s]));
+            }
+            umma_commit(smem_u32(&tmem_full_bar));
+        }
+    } else {
+        // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int wl = row % p.bw, hl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
+        const int n = n0 + nl, hd = h0 + hl, wd = w0 + wl;
+        const bool valid = (n < p.NB) && (hd < p.Hd) && (wd < p.Wd);
+        const long long pix = ((long long)n * p.Ho + (hd * p.os + ph.oph)) * p.Wo + (wd * p.os + ph.opw);
+        mbar_wait(smem_u32(&tmem_full_bar), 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int nchunks = p.BN >> 4;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t r[16];
+            tmem_ld16(trow + (uint32_t)(ch * 16), r);
+            tmem_ld_wait();
+            const int col = ncol0 + ch * 16;
+            if (!valid || col >= p.n_store) continue;
+            const int nv = min(16, p.n_store - col);  // 8 or 16 (n_store % 8 == 0)
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < nv) v[j] += __ldg(p.bias + col + j);
+            }
+            if (p.out_f32) {
+                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_ld + p.out_coff + col);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j * 4 < nv) {
+                        float4 t = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        if (p.accumulate) {
+                            const float4 old = o[j];
+                            t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+                        }
+                        o[j] = t;
+                    }
+                }
+            } else {
+                __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + p.out_coff + col;
+                uint4* o = reinterpret_cast<uint4*>(ob);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j * 8 < nv) {
+                        if (p.accumulate) {
+                            const uint4 old = o[j];
+                            v[8 * j + 0] += bf16_lo(old.x); v[8 * j + 1] += bf16_hi(old.x);
+                            v[8 * j + 2] += bf16_lo(old.y); v[8 * j + 3] += bf16_hi(old.y);
+                            v[8 * j + 4] += bf16_lo(old.z); v[8 * j + 5] += bf16_hi(old.z);
+                            v[8 * j + 6] += bf16_lo(old.w); v[8 * j + 7] += bf16_hi(old.w);
+                        }
+                        uint4 t;
+                        t.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); t.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                        t.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); t.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                        o[j] = t;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad kernel: dW[co, tap, ci] += sum_{pixels} dY[pix, co] * X[pix + tap, ci]
+// A = dY tile (M = 128 couts, K = 64 pixels), B = X tile (N = NT cins, K = 64 pixels), both MN-major.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
+                  const __grid_constant__ WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int stages = p.stages;
+    const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+    constexpr uint32_t kBox = 64 * 128;  // one [64 pixels x 64 channels] bf16 box
+
+    const int co0 = blockIdx.x * 128;
+    const int tap_i = blockIdx.y / p.n_ci_tiles;
+    const int ci0 = (blockIdx.y % p.n_ci_tiles) * p.NT;
+    const WTap tp = p.taps[tap_i];
+    const int t_begin = blockIdx.z * p.tiles_per_split;
+    const int t_end = min(p.total_tiles, t_begin + p.tiles_per_split);
+    const int nxb = p.NT >> 6;  // X boxes per stage
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmG);
+            tma_prefetch_desc(&tmX);
+        }
+        tmem_alloc<kTmemCols>(smem_u32(&tmem_base_s));
+    } else if (warp == 1 && lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&tmem_full_bar), 1);
+        mbar_fence_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const int total = max(0, t_end - t_begin);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < total; ++it) {
+                const int tile = t_begin + it;
+                const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tn = tile / (p.tiles_w * p.tiles_h);
+                const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+                const int s = it % stages;
+                const uint32_t par = (uint32_t)((it / stages) & 1);
+                mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
+                const uint32_t fb = smem_u32(&full_bar[s]);
+                mbar_expect_tx(fb, stage_bytes);
+                const uint32_t g_s = sbase + (uint32_t)s * stage_bytes;
+                tma_load_5d(g_s, &tmG, fb, tp.g_dc + co0, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
+                tma_load_5d(g_s + kBox, &tmG, fb, tp.g_dc + co0 + 64, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
+                const uint32_t x_s = g_s + 2 * kBox;
+                for (int b = 0; b < nxb; ++b)
+                    tma_load_5d(x_s + b * kBox, &tmX, fb, tp.x_dc + ci0 + b * 64, w0 + tp.x_dw, tp.x_dhp, h0 + tp.x_dh, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, p.NT, 1, 1);
+            for (int it = 0; it < total; ++it) {
+                const int s = it % stages;
+                const uint32_t par = (uint32_t)((it / stages) & 1);
+                mbar_wait(smem_u32(&full_bar[s]), par);
+                tc_fence_after();
+                const uint32_t g_s = sbase + (uint32_t)s * stage_bytes;
+                const uint32_t x_s = g_s + 2 * kBox;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // 16 pixels (rows of 128 B) per MMA
+                    umma_bf16(tmem_base, umma_desc_sw128(g_s + k * 2048, p.lbo_bytes, p.sbo_bytes),
+                              umma_desc_sw128(x_s + k * 2048, p.lbo_bytes, p.sbo_bytes), idesc, (uint32_t)((it | k) != 0));
+                }
+                umma_commit(smem_u32(&empty_bar[s]));
+            }
+            umma_commit(smem_u32(&tmem_full_bar));
+        }
+    } else if (total > 0) {
+        const int q = warp & 3;
+        const int co = co0 + q * 32 + lane;
+        const bool valid = co < p.Cout;
+        mbar_wait(smem_u32(&tmem_full_bar), 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* drow = p.dw + (long long)co * p.dw_ld + (long long)tp.wtap * p.wK + p.w_coff;
+        const int nchunks = p.NT >> 4;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t r[16];
+            tmem_ld16(trow + (uint32_t)(ch * 16), r);
+            tmem_ld_wait();
+            const int ci = ci0 + ch * 16;
+            if (!valid || ci >= p.Ci) continue;
+            const int nv = min(16, p.Ci - ci);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j * 4 < nv) {
+                    float* d = drow + ci + j * 4;
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(__uint_as_float(r[4 * j])),
+                                 "f"(__uint_as_float(r[4 * j + 1])), "f"(__uint_as_float(r[4 * j + 2])),
+                                 "f"(__uint_as_float(r[4 * j + 3]))
+                                 : "memory");
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static int get_encode() {
+    std::call_once(g_encode_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) g_encode = (EncodeTiledFn)fn;
+    });
+    SNN_REQUIRE(g_encode != nullptr, "cuTensorMapEncodeTiled not available from the CUDA driver");
+    return 0;
+}
+
+// NHWC bf16 activation view -> 5-D map (c, w, row-phase, h, n).
+//   plain : tensor (NB, H, W, C) with pixel stride ld           -> dims (C, W, 1, H, NB)
+//   phase : same memory seen as (NB, H/2, 2, W/2, [2 pixels])   -> dims (ld + C, W/2, 2, H/2, NB)
+static int make_act_map(CUtensorMap* m, const void* ptr, int NB, int H, int W, int C, long long ld, int phase_view,
+                        int box_n, int box_h, int box_w) {
+    if (get_encode()) return 2;
+    SNN_REQUIRE(((uintptr_t)ptr & 15) == 0, "activation pointer must be 16-byte aligned");
+    SNN_REQUIRE(ld % 8 == 0 && C % 8 == 0, "activation channels/stride must be multiples of 8 (C=%d ld=%lld)", C, ld);
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5] = {64, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, (cuuint32_t)box_n}, es[5] = {1, 1, 1, 1, 1};
+    if (!phase_view) {
+        dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = NB;
+        strides[0] = ld * 2; strides[1] = (cuuint64_t)W * ld * 2; strides[2] = (cuuint64_t)W * ld * 2;
+        strides[3] = (cuuint64_t)H * W * ld * 2;
+    } else {
+        SNN_REQUIRE(H % 2 == 0 && W % 2 == 0, "stride-2 / transposed conv needs even H, W (got %dx%d)", H, W);
+        SNN_REQUIRE(C % 64 == 0, "stride-2 / transposed conv needs C %% 64 == 0 (got %d)", C);
+        dims[0] = ld + C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = NB;
+        strides[0] = 2 * ld * 2; strides[1] = (cuuint64_t)W * ld * 2; strides[2] = (cuuint64_t)2 * W * ld * 2;
+        strides[3] = (cuuint64_t)H * W * ld * 2;
+    }
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SNN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(act) failed: %d (NB=%d H=%d W=%d C=%d ld=%lld phase=%d box=%d,%d,%d)",
+                (int)r, NB, H, W, C, ld, phase_view, box_n, box_h, box_w);
+    return 0;
+}
+
+// weights bf16 [wN][wT][wK] -> 3-D map (k, tap, n), box (64, 1, box_n)
+static int make_w_map(CUtensorMap* m, const void* ptr, int wN, int wT, int wK, int box_n) {
+    if (get_encode()) return 2;
+    SNN_REQUIRE(((uintptr_t)ptr & 15) == 0, "weight pointer must be 16-byte aligned");
+    SNN_REQUIRE(wK % 8 == 0, "weight K extent must be a multiple of 8 (got %d)", wK);
+    cuuint64_t dims[3] = {(cuuint64_t)wK, (cuuint64_t)wT, (cuuint64_t)wN};
+    cuuint64_t strides[2] = {(cuuint64_t)wK * 2, (cuuint64_t)wT * wK * 2};
+    cuuint32_t box[3] = {64, 1, (cuuint32_t)box_n}, es[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SNN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: %d (N=%d T=%d K=%d box_n=%d)", (int)r, wN, wT, wK, box_n);
+    return 0;
+}
+
+static int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// choose a power-of-two pixel box (bn, bh, bw) with bn*bh*bw == npix that wastes the least
+static void pick_box(int NB, int H, int W, int npix, int* bn, int* bh, int* bw) {
+    double best = -1;
+    for (int w = npix; w >= 1; w >>= 1) {
+        if (w > 256) continue;
+        for (int h = npix / w; h >= 1; h >>= 1) {
+            const int n = npix / (w * h);
+            if (w > pow2_ceil(W) || h > pow2_ceil(H)) continue;
+            if (n > 256) continue;
+            const double ew = (double)W / (((W + w - 1) / w) * w), eh = (double)H / (((H + h - 1) / h) * h),
+                         en = (double)NB / (((NB + n - 1) / n) * n);
+            const double e = ew * eh * en + 1e-6 * w;  // tie -> wider rows
+            if (e > best) { best = e; *bn = n; *bh = h; *bw = w; }
+        }
+    }
+}
+
+enum { GEOM_3x3_S1 = 0, GEOM_3x3_S2 = 1, GEOM_1x1 = 2, GEOM_T2x2_S2 = 3 };
+
+static int g_debug_flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+void debug_set(int k, int v) { if (k >= 0 && k < 8) g_debug_flags[k] = v; }
+
+static int smem_budget() { return 220 * 1024; }
+
+static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, ConvGemmParams& p, cudaStream_t st) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    SNN_CUDA_OK(attr_err);
+    p.stage_bytes = 16384 + p.BN * 128;
+    int stages = smem_budget() / p.stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (g_debug_flags[1] > 0 && stages > g_debug_flags[1]) stages = g_debug_flags[1];
+    SNN_REQUIRE(stages >= 2, "conv_gemm: not enough shared memory for 2 stages");
+    p.stages = stages;
+    const size_t smem = (size_t)stages * p.stage_bytes + 1024;
+    dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, (p.n_store + p.BN - 1) / p.BN, p.nphase);
+    conv_gemm_kernel<<<grid, 192, smem, st>>>(a0, a1, b, p);
+    return check_cuda(cudaGetLastError(), "conv_gemm_kernel launch");
+}
+
+static int pick_bn(int n_store) {
+    // largest UMMA N (multiple of 16, <= 256) that tiles n_store with little padding
+    if (n_store <= 256) return ((n_store + 15) / 16) * 16;
+    int best = 256; double beste = -1;
+    for (int bn = 256; bn >= 64; bn -= 16) {
+        const int tiles = (n_store + bn - 1) / bn;
+        const double e = (double)n_store / (tiles * bn) + 1e-4 * bn / 256.0;
+        if (e > beste) { beste = e; best = bn; }
+    }
+    return best;
+}
+
+static void set_domain(ConvGemmParams& p, int NB, int Hd, int Wd) {
+    p.NB = NB; p.Hd = Hd; p.Wd = Wd;
+    pick_box(NB, Hd, Wd, 128, &p.bn, &p.bh, &p.bw);
+    p.tiles_w = (Wd + p.bw - 1) / p.bw; p.tiles_h = (Hd + p.bh - 1) / p.bh; p.tiles_n = (NB + p.bn - 1) / p.bn;
+}
+
+static Seg mkseg(int src, int dc, int dw, int dhp, int dh, int wtap, int wc0, int C) {
+    Seg s; s.src = src; s.dc = dc; s.dw = dw; s.dhp = dhp; s.dh = dh; s.wtap = wtap; s.wc0 = wc0; s.nchunk = (C + 63) / 64;
+    return s;
+}
+
+// stride-2 3x3 (pad 1) tap -> phase-view offsets: input row 2*o + k - 1
+static void s2_tap(int k, int* phase, int* d) {
+    if (k == 0) { *phase = 1; *d = -1; } else if (k == 1) { *phase = 0; *d = 0; } else { *phase = 1; *d = 0; }
+}
+
+// ------------------------------------------------------------------------------------------
+// fprop: out[NB,Ho,Wo,Cout] = conv(cat(x0,x1)) (+bias) ; geometry decides Ho, Wo
+// ------------------------------------------------------------------------------------------
+int conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long long ld0, const void* x1, int C1, long long ld1,
+               const void* w, int w_rows, int w_K, int w_coff, int Cout, int w_row_off, const float* bias, void* out,
+               int out_f32, long long out_ld, int out_coff, int accumulate, cudaStream_t st) {
+    SNN_REQUIRE(Cout % 8 == 0, "conv_fprop: Cout=%d must be a multiple of 8", Cout);
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    const int taps = geom == GEOM_3x3_S1 || geom == GEOM_3x3_S2 ? 9 : (geom == GEOM_1x1 ? 1 : 4);
+    const int phase_view = geom == GEOM_3x3_S2;
+    int Hd = H, Wd = W;
+    p.os = 1; p.Ho = H; p.Wo = W;
+    if (geom == GEOM_3x3_S2) { Hd = H / 2; Wd = W / 2; p.Ho = Hd; p.Wo = Wd; }
+    if (geom == GEOM_T2x2_S2) { p.os = 2; p.Ho = 2 * H; p.Wo = 2 * W; }
+    set_domain(p, NB, Hd, Wd);
+    p.BN = pick_bn(Cout);
+    p.n_store = Cout; p.wn_off = w_row_off;
+    p.out = out; p.bias = bias; p.out_f32 = out_f32; p.accumulate = accumulate; p.out_ld = out_ld; p.out_coff = out_coff;
+    CUtensorMap a0, a1, b;
+    if (make_act_map(&a0, x0, NB, H, W, C0, ld0, phase_view, p.bn, p.bh, p.bw)) return 2;
+    if (x1) { if (make_act_map(&a1, x1, NB, H, W, C1, ld1, phase_view, p.bn, p.bh, p.bw)) return 2; } else a1 = a0;
+    if (make_w_map(&b, w, w_rows, taps, w_K, p.BN)) return 2;
+    if (geom == GEOM_T2x2_S2) {
+        p.nphase = 4;
+        for (int a = 0; a < 2; ++a)
+            for (int bb = 0; bb < 2; ++bb) {
+                Phase& ph = p.phase[a * 2 + bb];
+                ph.oph = a; ph.opw = bb; ph.nseg = 0;
+                ph.seg[ph.nseg++] = mkseg(0, 0, 0, 0, 0, a * 2 + bb, w_coff, C0);
+                if (x1) ph.seg[ph.nseg++] = mkseg(1, 0, 0, 0, 0, a * 2 + bb, w_coff + C0, C1);
+            }
+    } else {
+        p.nphase = 1;
+        Phase& ph = p.phase[0];
+        ph.nseg = 0;
+        const int k = geom == GEOM_1x1 ? 1 : 3;
+        for (int kh = 0; kh < k; ++kh)
+            for (int kw = 0; kw < k; ++kw) {
+                int dcm = 0, dw = 0, dhp = 0, dh = 0;
+                if (geom == GEOM_3x3_S1) { dw = kw - 1; dh = kh - 1; }
+                if (geom == GEOM_3x3_S2) { int pc; s2_tap(kh, &dhp, &dh); s2_tap(kw, &pc, &dw); dcm = pc; }
+                ph.seg[ph.nseg++] = mkseg(0, (int)(dcm * ld0), dw, dhp, dh, kh * k + kw, w_coff, C0);
+                if (x1) ph.seg[ph.nseg++] = mkseg(1, (int)(dcm * ld1), dw, dhp, dh, kh * k + kw, w_coff + C0, C1);
+            }
+    }
+    return launch_conv_gemm(a0, a1, b, p, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// dgrad: dx[NB,H,W,Ci] = conv^T(dy) using weights laid out [Cin_tot][tap][Cout] (K-major in Cout)
+// (H, W) are the conv's INPUT spatial dims; dy has the geometry's output dims.
+// ------------------------------------------------------------------------------------------
+int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long long ld_dy, const void* wt, int wt_rows,
+               int ci_off, int Ci, void* dx, int dx_f32, long long dx_ld, int dx_coff, int accumulate, cudaStream_t st) {
+    SNN_REQUIRE(Ci % 8 == 0, "conv_dgrad: Ci=%d must be a multiple of 8", Ci);
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    const int taps = geom == GEOM_3x3_S1 || geom == GEOM_3x3_S2 ? 9 : (geom == GEOM_1x1 ? 1 : 4);
+    int Hd = H, Wd = W, Hy = H, Wy = W, phase_view = 0;
+    p.os = 1; p.Ho = H; p.Wo = W;
+    if (geom == GEOM_3x3_S2) { Hd = H / 2; Wd = W / 2; Hy = Hd; Wy = Wd; p.os = 2; }
+    if (geom == GEOM_T2x2_S2) { Hy = 2 * H; Wy = 2 * W; phase_view = 1; }
+    set_domain(p, NB, Hd, Wd);
+    p.BN = pick_bn(Ci);
+    p.n_store = Ci; p.wn_off = ci_off;
+    p.out = dx; p.bias = nullptr; p.out_f32 = dx_f32; p.accumulate = accumulate; p.out_ld = dx_ld; p.out_coff = dx_coff;
+    CUtensorMap a0, b;
+    if (make_act_map(&a0, dy, NB, Hy, Wy, Cout, ld_dy, phase_view, p.bn, p.bh, p.bw)) return 2;
+    if (make_w_map(&b, wt, wt_rows, taps, Cout, p.BN)) return 2;
+    if (geom == GEOM_3x3_S1 || geom == GEOM_1x1) {
+        p.nphase = 1;
+        Phase& ph = p.phase[0];
+        const int k = geom == GEOM_1x1 ? 1 : 3;
+        for (int kh = 0; kh < k; ++kh)
+            for (int kw = 0; kw < k; ++kw)
+                ph.seg[ph.nseg++] = mkseg(0, 0, k == 3 ? 1 - kw : 0, 0, k == 3 ? 1 - kh : 0, kh * k + kw, 0, Cout);
+    } else if (geom == GEOM_3x3_S2) {
+        // input pixel (2a+pr, 2b+pc): pr==0 -> kh=1 (dh 0); pr==1 -> kh=0 (dh +1), kh=2 (dh 0)
+        p.nphase = 4;
+        for (int pr = 0; pr < 2; ++pr)
+            for (int pc = 0; pc < 2; ++pc) {
+                Phase& ph = p.phase[pr * 2 + pc];
+                ph.oph = pr; ph.opw = pc; ph.nseg = 0;
+                for (int kh = 0; kh < 3; ++kh) {
+                    if ((kh == 1) != (pr == 0)) continue;
+                    const int dh = kh == 0 ? 1 : 0;
+                    for (int kw = 0; kw < 3; ++kw) {
+                        if ((kw == 1) != (pc == 0)) continue;
+                        const int dw = kw == 0 ? 1 : 0;
+                        ph.seg[ph.nseg++] = mkseg(0, 0, dw, 0, dh, kh * 3 + kw, 0, Cout);
+                    }
+                }
+            }
+    } else {  // transposed conv: dx[h,w] = sum_{a,b} dy[2h+a, 2w+b] * W[:, :, a, b]
+        p.nphase = 1;
+        Phase& ph = p.phase[0];
+        for (int a = 0; a < 2; ++a)
+            for (int bb = 0; bb < 2; ++bb) ph.seg[ph.nseg++] = mkseg(0, (int)(bb * ld_dy), 0, a, 0, a * 2 + bb, 0, Cout);
+    }
+    return launch_conv_gemm(a0, a0, b, p, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad: dw[Cout][taps][w_K] (fp32, +=) at channel offset w_coff, from x (conv input) and dy
+// ------------------------------------------------------------------------------------------
+int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long ld_x, const void* dy, int Cout,
+               long long ld_dy, float* dw, int w_K, int w_coff, cudaStream_t st) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    SNN_CUDA_OK(attr_err);
+    SNN_REQUIRE(Ci % 8 == 0 && Cout % 8 == 0 && w_K % 4 == 0 && w_coff % 4 == 0, "conv_wgrad: channel counts must be multiples of 8");
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    const int taps = geom == GEOM_3x3_S1 || geom == GEOM_3x3_S2 ? 9 : (geom == GEOM_1x1 ? 1 : 4);
+    int Hd = H, Wd = W, Hy = H, Wy = W, x_phase = 0, g_phase = 0;
+    if (geom == GEOM_3x3_S2) { Hd = H / 2; Wd = W / 2; Hy = Hd; Wy = Wd; x_phase = 1; }
+    if (geom == GEOM_T2x2_S2) { Hy = 2 * H; Wy = 2 * W; g_phase = 1; }
+    p.NB = NB; p.Hd = Hd; p.Wd = Wd;
+    pick_box(NB, Hd, Wd, 64, &p.bn, &p.bh, &p.bw);
+    p.tiles_w = (Wd + p.bw - 1) / p.bw; p.tiles_h = (Hd + p.bh - 1) / p.bh; p.tiles_n = (NB + p.bn - 1) / p.bn;
+    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    // cin per CTA: multiple of 64 up to 256 with little padding
+    {
+        const int c64 = (Ci + 63) / 64;
+        int nt = c64 >= 4 ? 4 : c64;
+        if (c64 > 4) { // prefer an exact tiling
+            for (int cand = 4; cand >= 2; --cand) if (c64 % cand == 0) { nt = cand; break; }
+        }
+        p.NT = nt * 64;
+        p.n_ci_tiles = (Ci + p.NT - 1) / p.NT;
+    }
+    p.Cout = Cout; p.Ci = Ci; p.dw = dw; p.dw_ld = (long long)taps * w_K; p.wK = w_K; p.w_coff = w_coff;
+    p.stage_bytes = (2 + p.NT / 64) * 8192;
+    int stages = smem_budget() / p.stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    p.stages = stages;
+    p.lbo_bytes = g_debug_flags[2] ? g_debug_flags[2] : 8192;
+    p.sbo_bytes = g_debug_flags[3] ? g_debug_flags[3] : 1024;
+    p.ntaps = taps;
+    const int k = geom == GEOM_1x1 ? 1 : (geom == GEOM_T2x2_S2 ? 2 : 3);
+    for (int kh = 0; kh < k; ++kh)
+        for (int kw = 0; kw < k; ++kw) {
+            WTap& t = p.taps[kh * k + kw];
+            memset(&t, 0, sizeof(t));
+            t.wtap = kh * k + kw;
+            if (geom == GEOM_3x3_S1) { t.x_dw = kw - 1; t.x_dh = kh - 1; }
+            if (geom == GEOM_3x3_S2) { int pc; s2_tap(kh, &t.x_dhp, &t.x_dh); s2_tap(kw, &pc, &t.x_dw); t.x_dc = (int)(pc * ld_x); }
+            if (geom == GEOM_T2x2_S2) { t.g_dhp = kh; t.g_dc = (int)(kw * ld_dy); }
+        }
+    const int m_tiles = (Cout + 127) / 128;
+    const int base_ctas = m_tiles * p.n_ci_tiles * taps;
+    int ksplit = (num_sms() * 2 + base_ctas - 1) / base_ctas;
+    const int max_split = (p.total_tiles + 3) / 4;  // >= 4 pixel tiles per CTA
+    if (ksplit > max_split) ksplit = max_split;
+    if (ksplit < 1) ksplit = 1;
+    if (g_debug_flags[4] > 0) ksplit = g_debug_flags[4];
+    p.tiles_per_split = (p.total_tiles + ksplit - 1) / ksplit;
+    p.ksplit = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    CUtensorMap mg, mx;
+    if (make_act_map(&mg, dy, NB, Hy, Wy, Cout, ld_dy, g_phase, p.bn, p.bh, p.bw)) return 2;
+    if (make_act_map(&mx, x, NB, H, W, Ci, ld_x, x_phase, p.bn, p.bh, p.bw)) return 2;
+    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+    dim3 grid(m_tiles, p.n_ci_tiles * taps, p.ksplit);
+    wgrad_gemm_kernel<<<grid, 192, smem, st>>>(mg, mx, p);
+    return check_cuda(cudaGetLastError(), "wgrad_gemm_kernel launch");
+}
+
+}  // namespace snn

@@ -1,0 +1,278 @@
+// Small HBM-bound helpers around the tensor-core convs: weight casts/transposes, layout
+// conversion at the module boundary, ConvLSTM gate math, fused grad-clip + AdamW.
+#include "common.cuh"
+
+namespace snn {
+
+// ------------------------------------------------------------------------------------------
+// weight prep: fp32 master [N][T][K] -> bf16 copy (fprop operand) and bf16 [K][T][N] (dgrad operand)
+// ------------------------------------------------------------------------------------------
+__global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                   __nv_bfloat16* __restrict__ wt, int N, int T, int K) {
+    __shared__ float tile[32][33];
+    const int t = blockIdx.z;
+    const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int n = n0 + j, k = k0 + tx;
+        float v = 0.f;
+        if (n < N && k < K) {
+            const size_t idx = ((size_t)n * T + t) * K + k;
+            v = w[idx];
+            if (wf) wf[idx] = __float2bfloat16_rn(v);
+        }
+        tile[j][tx] = v;
+    }
+    __syncthreads();
+    if (wt) {
+        for (int j = ty; j < 32; j += 8) {
+            const int k = k0 + j, n = n0 + tx;
+            if (n < N && k < K) wt[((size_t)k * T + t) * N + n] = __float2bfloat16_rn(tile[tx][j]);
+        }
+    }
+}
+
+int launch_weight_prep(const float* w, __nv_bfloat16* wf, __nv_bfloat16* wt, int N, int T, int K, cudaStream_t st) {
+    dim3 grid((K + 31) / 32, (N + 31) / 32, T), block(32, 8);
+    weight_prep_kernel<<<grid, block, 0, st>>>(w, wf, wt, N, T, K);
+    return check_cuda(cudaGetLastError(), "weight_prep_kernel");
+}
+
+// ------------------------------------------------------------------------------------------
+// NCHW fp32 <-> NHWC (bf16 | fp32) at the module boundary
+// ------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, TOut* __restrict__ out, int C, int HW, long long out_ld,
+                                    int out_coff) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, p = p0 + tx;
+        tile[j][tx] = (c < C && p < HW) ? in[((size_t)n * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int p = p0 + j, c = c0 + tx;
+        if (c < C && p < HW) out[((size_t)n * HW + p) * out_ld + out_coff + c] = (TOut)tile[tx][j];
+    }
+}
+
+template <typename TIn>
+__global__ void nhwc_to_nchw_kernel(const TIn* __restrict__ in, float* __restrict__ out, int C, int HW, long long in_ld,
+                                    int in_coff) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int j = ty; j < 32; j += 8) {
+        const int p = p0 + j, c = c0 + tx;
+        tile[j][tx] = (c < C && p < HW) ? (float)in[((size_t)n * HW + p) * in_ld + in_coff + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, p = p0 + tx;
+        if (c < C && p < HW) out[((size_t)n * C + c) * HW + p] = tile[tx][j];
+    }
+}
+
+int launch_nchw_to_nhwc(const float* in, void* out, int out_bf16, int NB, int C, int HW, long long out_ld, int out_coff,
+                        cudaStream_t st) {
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, NB), block(32, 8);
+    if (out_bf16)
+        nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(in, (__nv_bfloat16*)out, C, HW, out_ld, out_coff);
+    else
+        nchw_to_nhwc_kernel<float><<<grid, block, 0, st>>>(in, (float*)out, C, HW, out_ld, out_coff);
+    return check_cuda(cudaGetLastError(), "nchw_to_nhwc_kernel");
+}
+
+int launch_nhwc_to_nchw(const void* in, int in_bf16, float* out, int NB, int C, int HW, long long in_ld, int in_coff,
+                        cudaStream_t st) {
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, NB), block(32, 8);
+    if (in_bf16)
+        nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, out, C, HW, in_ld, in_coff);
+    else
+        nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>((const float*)in, out, C, HW, in_ld, in_coff);
+    return check_cuda(cudaGetLastError(), "nhwc_to_nchw_kernel");
+}
+
+// ------------------------------------------------------------------------------------------
+// ConvLSTM gate math (reference model.py:67-69), NHWC: gates fp32 [P][4*Ch] (i|f|g|o), state fp32 [P][Ch]
+// forward also emits h as bf16 (operand of the next recurrent conv / bottleneck conv)
+// ------------------------------------------------------------------------------------------
+SNN_DEVINL float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__global__ void __launch_bounds__(256)
+lstm_gates_fwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, float* __restrict__ c_next,
+                      float* __restrict__ h_next, __nv_bfloat16* __restrict__ h_bf16, long long n4, int Ch) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= n4) return;
+    const int ch4 = Ch >> 2;
+    const long long p = idx / ch4;
+    const int c = (int)(idx % ch4) * 4;
+    const float4* g = reinterpret_cast<const float4*>(gates + p * 4 * Ch + c);
+    const float4 gi = __ldg(g), gf = __ldg(g + ch4), gg = __ldg(g + 2 * ch4), go = __ldg(g + 3 * ch4);
+    float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c_prev) cp = __ldg(reinterpret_cast<const float4*>(c_prev) + idx);
+    const float iv[4] = {gi.x, gi.y, gi.z, gi.w}, fv[4] = {gf.x, gf.y, gf.z, gf.w}, gv[4] = {gg.x, gg.y, gg.z, gg.w},
+                ov[4] = {go.x, go.y, go.z, go.w}, cv[4] = {cp.x, cp.y, cp.z, cp.w};
+    float cn[4], hn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        cn[j] = sigmoidf_(fv[j]) * cv[j] + sigmoidf_(iv[j]) * tanhf(gv[j]);
+        hn[j] = sigmoidf_(ov[j]) * tanhf(cn[j]);
+    }
+    reinterpret_cast<float4*>(c_next)[idx] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+    reinterpret_cast<float4*>(h_next)[idx] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+    if (h_bf16) {
+        uint2 pk;
+        pk.x = pack_bf16x2(hn[0], hn[1]); pk.y = pack_bf16x2(hn[2], hn[3]);
+        reinterpret_cast<uint2*>(h_bf16)[idx] = pk;
+    }
+}
+
+// backward of one step: inputs dh (total grad wrt h_next), dc_in (grad wrt c_next from the future);
+// outputs dgates (bf16, operand of dgrad/wgrad) and dc_prev.
+__global__ void __launch_bounds__(256)
+lstm_gates_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_next,
+                      const float* __restrict__ dh, const float* __restrict__ dc_in, __nv_bfloat16* __restrict__ dgates,
+                      float* __restrict__ dc_prev, long long n4, int Ch) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= n4) return;
+    const int ch4 = Ch >> 2;
+    const long long p = idx / ch4;
+    const int c = (int)(idx % ch4) * 4;
+    const float4* g = reinterpret_cast<const float4*>(gates + p * 4 * Ch + c);
+    const float4 gi = __ldg(g), gf = __ldg(g + ch4), gg = __ldg(g + 2 * ch4), go = __ldg(g + 3 * ch4);
+    float4 cp = make_float4(0.f, 0.f, 0.f, 0.f), dci = cp;
+    if (c_prev) cp = __ldg(reinterpret_cast<const float4*>(c_prev) + idx);
+    if (dc_in) dci = __ldg(reinterpret_cast<const float4*>(dc_in) + idx);
+    const float4 cnx = __ldg(reinterpret_cast<const float4*>(c_next) + idx);
+    const float4 dhh = __ldg(reinterpret_cast<const float4*>(dh) + idx);
+    const float iv[4] = {gi.x, gi.y, gi.z, gi.w}, fv[4] = {gf.x, gf.y, gf.z, gf.w}, gv[4] = {gg.x, gg.y, gg.z, gg.w},
+                ov[4] = {go.x, go.y, go.z, go.w}, cv[4] = {cp.x, cp.y, cp.z, cp.w}, cn[4] = {cnx.x, cnx.y, cnx.z, cnx.w},
+                dhv[4] = {dhh.x, dhh.y, dhh.z, dhh.w}, dcv[4] = {dci.x, dci.y, dci.z, dci.w};
+    float di[4], df[4], dg[4], dov[4], dcp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float si = sigmoidf_(iv[j]), sf = sigmoidf_(fv[j]), so = sigmoidf_(ov[j]), tg = tanhf(gv[j]), tc = tanhf(cn[j]);
+        const float dc = dcv[j] + dhv[j] * so * (1.f - tc * tc);
+        dov[j] = dhv[j] * tc * so * (1.f - so);
+        di[j] = dc * tg * si * (1.f - si);
+        df[j] = dc * cv[j] * sf * (1.f - sf);
+        dg[j] = dc * si * (1.f - tg * tg);
+        dcp[j] = dc * sf;
+    }
+    uint2* o = reinterpret_cast<uint2*>(dgates + p * 4 * Ch + c);
+    uint2 pk;
+    pk.x = pack_bf16x2(di[0], di[1]); pk.y = pack_bf16x2(di[2], di[3]); o[0] = pk;
+    pk.x = pack_bf16x2(df[0], df[1]); pk.y = pack_bf16x2(df[2], df[3]); o[ch4] = pk;
+    pk.x = pack_bf16x2(dg[0], dg[1]); pk.y = pack_bf16x2(dg[2], dg[3]); o[2 * ch4] = pk;
+    pk.x = pack_bf16x2(dov[0], dov[1]); pk.y = pack_bf16x2(dov[2], dov[3]); o[3 * ch4] = pk;
+    reinterpret_cast<float4*>(dc_prev)[idx] = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
+}
+
+int launch_lstm_gates_fwd(const float* gates, const float* c_prev, float* c_next, float* h_next, __nv_bfloat16* h_bf16,
+                          long long P, int Ch, cudaStream_t st) {
+    SNN_REQUIRE(Ch % 4 == 0, "lstm_gates: Ch must be a multiple of 4");
+    const long long n4 = P * Ch / 4;
+    lstm_gates_fwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(gates, c_prev, c_next, h_next, h_bf16, n4, Ch);
+    return check_cuda(cudaGetLastError(), "lstm_gates_fwd_kernel");
+}
+
+int launch_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_next, const float* dh, const float* dc_in,
+                          __nv_bfloat16* dgates, float* dc_prev, long long P, int Ch, cudaStream_t st) {
+    SNN_REQUIRE(Ch % 4 == 0, "lstm_gates: Ch must be a multiple of 4");
+    const long long n4 = P * Ch / 4;
+    lstm_gates_bwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(gates, c_prev, c_next, dh, dc_in, dgates, dc_prev, n4, Ch);
+    return check_cuda(cudaGetLastError(), "lstm_gates_bwd_kernel");
+}
+
+// ------------------------------------------------------------------------------------------
+// fused global grad-norm + clip + AdamW over ONE flat fp32 buffer (reference train.py:77-78)
+//   pass 1: sum of squares -> device scalar        (4 B/param)
+//   pass 2: clip coefficient from the scalar, AdamW update, bf16 shadow copy (28+2 B/param)
+// hyper-parameters (lr, beta1, step-dependent bias corrections) are read from a device array so the
+// OneCycle schedule never forces a host sync:  hp = {lr, beta1, beta2, eps, wd, bc1, bc2, max_norm}
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n4, double* __restrict__ acc) {
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+        s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ float ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < 8; ++i) t += ws[i];
+        atomicAdd(acc, t);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             __nv_bfloat16* __restrict__ shadow, long long n4, const float* __restrict__ hp, const double* __restrict__ sumsq,
+             float* __restrict__ gnorm_out) {
+    const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], bc1 = hp[5], bc2 = hp[6], max_norm = hp[7];
+    const float gn = (float)sqrt(*sumsq);
+    float clip = max_norm / (gn + 1e-6f);  // torch.nn.utils.clip_grad_norm_: coef clamped to 1
+    if (clip > 1.f) clip = 1.f;
+    if (max_norm <= 0.f) clip = 1.f;
+    if (gnorm_out && blockIdx.x == 0 && threadIdx.x == 0) *gnorm_out = gn;
+    const float step_size = lr / bc1;
+    const float rsq_bc2 = 1.f / sqrtf(bc2);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        float4 pp = reinterpret_cast<float4*>(p)[i];
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+        float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w}, ma[4] = {mm.x, mm.y, mm.z, mm.w},
+              va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gr = ga[j] * clip;
+            pa[j] *= (1.f - lr * wd);
+            ma[j] = b1 * ma[j] + (1.f - b1) * gr;
+            va[j] = b2 * va[j] + (1.f - b2) * gr * gr;
+            const float denom = sqrtf(va[j]) * rsq_bc2 + eps;
+            pa[j] -= step_size * (ma[j] / denom);
+        }
+        reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+        reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+        reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
+        if (shadow) {
+            uint2 pk;
+            pk.x = pack_bf16x2(pa[0], pa[1]); pk.y = pack_bf16x2(pa[2], pa[3]);
+            reinterpret_cast<uint2*>(shadow)[i] = pk;
+        }
+    }
+}
+
+int launch_sumsq(const float* g, long long n, double* acc, int zero_first, cudaStream_t st) {
+    SNN_REQUIRE(n % 4 == 0, "sumsq: length must be a multiple of 4");
+    if (zero_first) SNN_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double), st));
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    sumsq_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, n4, acc);
+    return check_cuda(cudaGetLastError(), "sumsq_kernel");
+}
+
+int launch_adamw(float* p, const float* g, float* m, float* v, __nv_bfloat16* shadow, long long n, const float* hp,
+                 const double* sumsq, float* gnorm_out, cudaStream_t st) {
+    SNN_REQUIRE(n % 4 == 0, "adamw: length must be a multiple of 4");
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, shadow, n4, hp, sumsq, gnorm_out);
+    return check_cuda(cudaGetLastError(), "adamw_kernel");
+}
+
+}  // namespace snn

@@ -1,0 +1,417 @@
+// Spiking-neuron layer kernels (HBM-bound): per-timestep BatchNorm statistics, fused
+// BN-affine + LIF scan over all T steps (forward), reverse-time surrogate-gradient scan (backward)
+// and the BatchNorm input-gradient pass.  Replaces the `bn -> silu` tail of the reference's
+// ConvBlock (reference model.py:14-18) with `bn -> LIF` (build-defined); the SiLU
+// variant is kept so the reference's own numerics can be reproduced through the same kernels.
+//
+// Data layout: conv outputs y are fp32 [T][P][C] (P = B*H*W pixels of one timestep, channels
+// innermost = NHWC with the T*B batch folded).  Each thread owns a few consecutive channels of one
+// pixel and walks the T steps with the membrane potential in registers; all global accesses are
+// 128-bit and coalesced along C.
+#include "common.cuh"
+
+namespace snn {
+
+enum { ACT_LIF = 0, ACT_SILU = 1 };
+
+// ------------------------------------------------------------------------------------------
+// per-(t, c) sum / sum-of-squares of y (train-mode BN batch statistics, one group per timestep)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, double* __restrict__ sums,
+                                                        int P, int C, int pix_per_block) {
+    extern __shared__ double sh[];  // [2][C]
+    const int t = blockIdx.y;
+    const int tpp = C >> 2;  // threads per pixel (float4 each)
+    const int rows = 256 / tpp;
+    const int cg = threadIdx.x % tpp, row = threadIdx.x / tpp;
+    for (int i = threadIdx.x; i < 2 * C; i += 256) sh[i] = 0.0;
+    __syncthreads();
+    if (row < rows) {
+        const int p0 = blockIdx.x * pix_per_block;
+        const int p1 = min(P, p0 + pix_per_block);
+        const float4* base = reinterpret_cast<const float4*>(y + (size_t)t * P * C) + cg;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+        for (int p = p0 + row; p < p1; p += rows) {
+            float4 v = __ldg(base + (size_t)p * tpp);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+        }
+        const int c = cg * 4;
+        atomicAdd(&sh[c + 0], (double)s.x); atomicAdd(&sh[c + 1], (double)s.y);
+        atomicAdd(&sh[c + 2], (double)s.z); atomicAdd(&sh[c + 3], (double)s.w);
+        atomicAdd(&sh[C + c + 0], (double)q.x); atomicAdd(&sh[C + c + 1], (double)q.y);
+        atomicAdd(&sh[C + c + 2], (double)q.z); atomicAdd(&sh[C + c + 3], (double)q.w);
+    }
+    __syncthreads();
+    double* out = sums + (size_t)t * 2 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(&out[i], sh[i]);
+}
+
+// scale/shift per (t,c); running-stat update applied T times in order (the reference calls the
+// module once per timestep, model.py:14 via train.py:64-66).
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
+                                   float* __restrict__ invstd_o, int T, int C, int P, float eps, float momentum,
+                                   int training) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    if (!training) {
+        const float m = running_mean[c], inv = 1.0f / sqrtf(running_var[c] + eps);
+        const float sc = g * inv;
+        scale[c] = sc; shift[c] = b - m * sc; mean_o[c] = m; invstd_o[c] = inv;
+        return;
+    }
+    float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 1.f;
+    for (int t = 0; t < T; ++t) {
+        const double s = sums[(size_t)t * 2 * C + c], q = sums[(size_t)t * 2 * C + C + c];
+        const double md = s / P;
+        double vd = q / P - md * md;
+        if (vd < 0) vd = 0;
+        const float m = (float)md, var = (float)vd;
+        const float inv = 1.0f / sqrtf(var + eps);
+        const float sc = g * inv;
+        scale[t * C + c] = sc; shift[t * C + c] = b - m * sc;
+        mean_o[t * C + c] = m; invstd_o[t * C + c] = inv;
+        const float unb = (P > 1) ? (float)(vd * ((double)P / (double)(P - 1))) : var;
+        rm = (1.f - momentum) * rm + momentum * m;
+        rv = (1.f - momentum) * rv + momentum * unb;
+    }
+    if (running_mean) running_mean[c] = rm;
+    if (running_var) running_var[c] = rv;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward: x = y*scale + shift ; LIF scan over T (or SiLU) ; 8 channels / thread
+// ------------------------------------------------------------------------------------------
+template <int ACT>
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, const float* __restrict__ v_init,
+                                                          __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ mask,
+                                                          float* __restrict__ v_final, int T, long long n8, int C,
+                                                          int ss_stride_t, float beta, float theta) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= n8) return;
+    const int c0 = (int)((idx * 8) % C);
+    const size_t nt = (size_t)n8 * 8;
+    float v[8];
+    if (ACT == ACT_LIF && v_init) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(v_init) + idx * 2);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(v_init) + idx * 2 + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+#pragma unroll 4
+    for (int t = 0; t < T; ++t) {
+        const float4* yp = reinterpret_cast<const float4*>(y + (size_t)t * nt) + idx * 2;
+        const float4 ya = __ldcs(yp), yb = __ldcs(yp + 1);
+        const float4* sp = reinterpret_cast<const float4*>(scale + (size_t)t * ss_stride_t + c0);
+        const float4* hp = reinterpret_cast<const float4*>(shift + (size_t)t * ss_stride_t + c0);
+        const float4 sa = __ldg(sp), sb = __ldg(sp + 1), ha = __ldg(hp), hb = __ldg(hp + 1);
+        float x[8];
+        x[0] = __fadd_rn(__fmul_rn(ya.x, sa.x), ha.x); x[1] = __fadd_rn(__fmul_rn(ya.y, sa.y), ha.y);
+        x[2] = __fadd_rn(__fmul_rn(ya.z, sa.z), ha.z); x[3] = __fadd_rn(__fmul_rn(ya.w, sa.w), ha.w);
+        x[4] = __fadd_rn(__fmul_rn(yb.x, sb.x), hb.x); x[5] = __fadd_rn(__fmul_rn(yb.y, sb.y), hb.y);
+        x[6] = __fadd_rn(__fmul_rn(yb.z, sb.z), hb.z); x[7] = __fadd_rn(__fmul_rn(yb.w, sb.w), hb.w);
+        float o[8];
+        uint32_t bits = 0;
+        if (ACT == ACT_LIF) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float u = __fadd_rn(__fmul_rn(beta, v[i]), x[i]);
+                const bool s = u >= theta;
+                v[i] = s ? 0.f : u;
+                o[i] = s ? 1.f : 0.f;
+                bits |= (s ? 1u : 0u) << i;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = x[i] / (1.f + __expf(-x[i]));
+        }
+        uint4 pk;
+        pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+        pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+        *(reinterpret_cast<uint4*>(out + (size_t)t * nt) + idx) = pk;
+        if (ACT == ACT_LIF && mask) mask[(size_t)t * n8 + idx] = (uint8_t)bits;
+    }
+    if (ACT == ACT_LIF && v_final) {
+        float4* vp = reinterpret_cast<float4*>(v_final) + idx * 2;
+        vp[0] = make_float4(v[0], v[1], v[2], v[3]);
+        vp[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: recompute u[t] forward in registers, then one reverse-time scan.
+//   gu[t] = gs[t]*g(u[t]) + gv[t]*((1-s[t]) - u[t]*g(u[t])),  g(u) = (a/2)/(1+(pi*a/2*(u-th))^2)
+//   gx[t] = gu[t] ; gv[t-1] = beta*gu[t]
+// TRAIN: writes gx (fp32) and accumulates per-(t,c) sum(gx), sum(gx*xhat) for the BN backward.
+// EVAL : BN statistics are constants -> writes dy = gx*scale directly as bf16.
+// 4 channels / thread; a block covers `rows` pixels per iteration and loops `iters` times.
+// ------------------------------------------------------------------------------------------
+template <int ACT, int TMAX, bool TRAIN>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ v_init,
+                  const __nv_bfloat16* __restrict__ gs, const float* __restrict__ gv_final, float* __restrict__ gx_out,
+                  __nv_bfloat16* __restrict__ dy_out, float* __restrict__ gv_init, float* __restrict__ red /*[T][2][C]*/,
+                  int T, int P, int C, int ss_stride_t, int pix_per_block, float beta, float theta, float alpha) {
+    extern __shared__ float shf[];  // TRAIN: [T][2][C]
+    const int tpp = C >> 2;
+    const int rows = 256 / tpp;
+    const int cg = threadIdx.x % tpp, row = threadIdx.x / tpp;
+    const int c0 = cg * 4;
+    const size_t nt4 = (size_t)P * tpp;  // float4 per timestep
+    if (TRAIN) {
+        for (int i = threadIdx.x; i < T * 2 * C; i += 256) shf[i] = 0.f;
+        __syncthreads();
+    }
+    float acc_s[TMAX][4], acc_d[TMAX][4];
+    if (TRAIN) {
+#pragma unroll
+        for (int t = 0; t < TMAX; ++t)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc_s[t][i] = acc_d[t][i] = 0.f;
+    }
+    const float ka = 0.5f * alpha, kz = 1.5707963267948966f * alpha;
+    if (row < rows) {
+        const int p0 = blockIdx.x * pix_per_block, p1 = min(P, p0 + pix_per_block);
+        for (int p = p0 + row; p < p1; p += rows) {
+            const size_t e4 = (size_t)p * tpp + cg;
+            float u[TMAX][4], xh[TMAX][4];
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ACT == ACT_LIF && v_init) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(v_init) + e4);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            }
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t) {
+                if (t < T) {
+                    const float4 yy = __ldcs(reinterpret_cast<const float4*>(y) + (size_t)t * nt4 + e4);
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + (size_t)t * ss_stride_t + c0));
+                    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + (size_t)t * ss_stride_t + c0));
+                    const float yv[4] = {yy.x, yy.y, yy.z, yy.w};
+                    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                    float mv[4] = {0, 0, 0, 0}, iv[4] = {0, 0, 0, 0};
+                    if (TRAIN) {
+                        const float4 m = __ldg(reinterpret_cast<const float4*>(mean + (size_t)t * ss_stride_t + c0));
+                        const float4 is = __ldg(reinterpret_cast<const float4*>(invstd + (size_t)t * ss_stride_t + c0));
+                        mv[0] = m.x; mv[1] = m.y; mv[2] = m.z; mv[3] = m.w;
+                        iv[0] = is.x; iv[1] = is.y; iv[2] = is.z; iv[3] = is.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float x = __fadd_rn(__fmul_rn(yv[i], scv[i]), shv[i]);
+                        if (TRAIN) xh[t][i] = (yv[i] - mv[i]) * iv[i];
+                        if (ACT == ACT_LIF) {
+                            const float uu = __fadd_rn(__fmul_rn(beta, v[i]), x);
+                            u[t][i] = uu;
+                            v[i] = (uu >= theta) ? 0.f : uu;
+                        } else {
+                            u[t][i] = x;
+                        }
+                    }
+                }
+            }
+            float gv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ACT == ACT_LIF && gv_final) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(gv_final) + e4);
+                gv[0] = a.x; gv[1] = a.y; gv[2] = a.z; gv[3] = a.w;
+            }
+#pragma unroll
+            for (int t = TMAX - 1; t >= 0; --t) {
+                if (t < T) {
+                    const uint2 graw = __ldcs(reinterpret_cast<const uint2*>(gs) + (size_t)t * nt4 + e4);
+                    const float g4[4] = {bf16_lo(graw.x), bf16_hi(graw.x), bf16_lo(graw.y), bf16_hi(graw.y)};
+                    float gx[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float uu = u[t][i];
+                        if (ACT == ACT_LIF) {
+                            const float z = kz * (uu - theta);
+                            const float sg = ka / (1.f + z * z);
+                            const float keep = (uu >= theta) ? 0.f : 1.f;
+                            const float gu = g4[i] * sg + gv[i] * (keep - uu * sg);
+                            gx[i] = gu;
+                            gv[i] = beta * gu;
+                        } else {
+                            const float sgm = 1.f / (1.f + __expf(-uu));
+                            gx[i] = g4[i] * (sgm * (1.f + uu * (1.f - sgm)));
+                        }
+                    }
+                    if (TRAIN) {
+                        *(reinterpret_cast<float4*>(gx_out) + (size_t)t * nt4 + e4) = make_float4(gx[0], gx[1], gx[2], gx[3]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            acc_s[t][i] += gx[i];
+                            acc_d[t][i] += gx[i] * xh[t][i];
+                        }
+                    } else {
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + (size_t)t * ss_stride_t + c0));
+                        uint2 pk;
+                        pk.x = pack_bf16x2(gx[0] * sc.x, gx[1] * sc.y);
+                        pk.y = pack_bf16x2(gx[2] * sc.z, gx[3] * sc.w);
+                        *(reinterpret_cast<uint2*>(dy_out) + (size_t)t * nt4 + e4) = pk;
+                    }
+                }
+            }
+            if (ACT == ACT_LIF && gv_init)
+                *(reinterpret_cast<float4*>(gv_init) + e4) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        }
+        if (TRAIN) {
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t) {
+                if (t < T) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        atomicAdd(&shf[(t * 2 + 0) * C + c0 + i], acc_s[t][i]);
+                        atomicAdd(&shf[(t * 2 + 1) * C + c0 + i], acc_d[t][i]);
+                    }
+                }
+            }
+        }
+    }
+    if (TRAIN) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < T * 2 * C; i += 256) atomicAdd(&red[i], shf[i]);
+    }
+}
+
+// dgamma/dbeta (+=) and the two per-(t,c) coefficients of the BN input gradient
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ red, const float* __restrict__ scale,
+                                       float* __restrict__ coef /*[T][2][C]*/, float* dgamma, float* dbeta,
+                                       const float* __restrict__ gamma, int T, int C, int P) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float dg = 0.f, db = 0.f;
+    const float invP = 1.f / (float)P;
+    for (int t = 0; t < T; ++t) {
+        const float s = red[(t * 2 + 0) * C + c], d = red[(t * 2 + 1) * C + c];
+        coef[(t * 2 + 0) * C + c] = s * invP;
+        coef[(t * 2 + 1) * C + c] = d * invP;
+        db += s; dg += d;
+    }
+    if (dgamma) dgamma[c] += dg;
+    if (dbeta) dbeta[c] += db;
+}
+
+// dy = scale * (gx - mean(gx) - xhat * mean(gx*xhat))  -> bf16 (operand of dgrad / wgrad)
+__global__ void __launch_bounds__(256)
+bn_bwd_dx_kernel(const float* __restrict__ gx, const float* __restrict__ y, const float* __restrict__ scale,
+                 const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ coef,
+                 __nv_bfloat16* __restrict__ dy, int T, long long n4, int C) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= n4) return;
+    const int t = blockIdx.y;
+    const int c0 = (int)((idx * 4) % C);
+    const size_t e = (size_t)t * n4 + idx;
+    const float4 g = __ldcs(reinterpret_cast<const float4*>(gx) + e);
+    const float4 yy = __ldcs(reinterpret_cast<const float4*>(y) + e);
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + t * C + c0));
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mean + t * C + c0));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd + t * C + c0));
+    const float4 k1 = __ldg(reinterpret_cast<const float4*>(coef + (t * 2 + 0) * C + c0));
+    const float4 k2 = __ldg(reinterpret_cast<const float4*>(coef + (t * 2 + 1) * C + c0));
+    uint2 pk;
+    pk.x = pack_bf16x2(sc.x * (g.x - k1.x - (yy.x - m.x) * is.x * k2.x), sc.y * (g.y - k1.y - (yy.y - m.y) * is.y * k2.y));
+    pk.y = pack_bf16x2(sc.z * (g.z - k1.z - (yy.z - m.z) * is.z * k2.z), sc.w * (g.w - k1.w - (yy.w - m.w) * is.w * k2.w));
+    *(reinterpret_cast<uint2*>(dy) + e) = pk;
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------
+static int pick_ppb(int P, int rows, int T) {
+    // enough blocks to fill 148 SMs a few times, but >= 8 pixels per row-thread to amortise the reduce
+    long long want_blocks = (long long)num_sms() * 8 / (T > 0 ? T : 1);
+    if (want_blocks < 1) want_blocks = 1;
+    int ppb = (int)((P + want_blocks - 1) / want_blocks);
+    int min_ppb = rows * 8;
+    if (ppb < min_ppb) ppb = min_ppb;
+    ppb = ((ppb + rows - 1) / rows) * rows;
+    return ppb;
+}
+
+int launch_bn_stats(const float* y, double* sums, int T, int P, int C, cudaStream_t st) {
+    SNN_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "bn_stats: C=%d must be a multiple of 4 in [4,1024]", C);
+    SNN_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * T * C, st));
+    const int rows = 256 / (C / 4);
+    const int ppb = pick_ppb(P, rows, T);
+    dim3 grid((P + ppb - 1) / ppb, T);
+    bn_stats_kernel<<<grid, 256, sizeof(double) * 2 * C, st>>>(y, sums, P, C, ppb);
+    return check_cuda(cudaGetLastError(), "bn_stats_kernel");
+}
+
+int launch_bn_finalize(const double* sums, const float* gamma, const float* beta, float* rm, float* rv, float* scale,
+                       float* shift, float* mean, float* invstd, int T, int C, int P, float eps, float momentum,
+                       int training, cudaStream_t st) {
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, gamma, beta, rm, rv, scale, shift, mean, invstd, T, C, P,
+                                                        eps, momentum, training);
+    return check_cuda(cudaGetLastError(), "bn_finalize_kernel");
+}
+
+int launch_bn_act_fwd(int act, const float* y, const float* scale, const float* shift, const float* v_init,
+                      __nv_bfloat16* out, uint8_t* mask, float* v_final, int T, long long n_per_t, int C,
+                      int ss_stride_t, float beta, float theta, cudaStream_t st) {
+    SNN_REQUIRE(C % 8 == 0, "bn_act_fwd: C=%d must be a multiple of 8", C);
+    SNN_REQUIRE(n_per_t % C == 0, "bn_act_fwd: n_per_t not a multiple of C");
+    const long long n8 = n_per_t / 8;
+    const unsigned blocks = (unsigned)((n8 + 255) / 256);
+    if (act == ACT_LIF)
+        bn_act_fwd_kernel<ACT_LIF><<<blocks, 256, 0, st>>>(y, scale, shift, v_init, out, mask, v_final, T, n8, C,
+                                                           ss_stride_t, beta, theta);
+    else
+        bn_act_fwd_kernel<ACT_SILU><<<blocks, 256, 0, st>>>(y, scale, shift, v_init, out, mask, v_final, T, n8, C,
+                                                            ss_stride_t, beta, theta);
+    return check_cuda(cudaGetLastError(), "bn_act_fwd_kernel");
+}
+
+template <int ACT, int TMAX, bool TRAIN>
+static int launch_bwd_t(const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
+                        const float* v_init, const __nv_bfloat16* gs, const float* gv_final, float* gx,
+                        __nv_bfloat16* dy, float* gv_init, float* red, int T, int P, int C, int ss, float beta,
+                        float theta, float alpha, cudaStream_t st) {
+    const int rows = 256 / (C / 4);
+    const int ppb = pick_ppb(P, rows, 1);
+    const size_t smem = TRAIN ? sizeof(float) * T * 2 * C : 0;
+    auto kern = bn_act_bwd_kernel<ACT, TMAX, TRAIN>;
+    if (smem > 48 * 1024) SNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(P + ppb - 1) / ppb, 256, smem, st>>>(y, scale, shift, mean, invstd, v_init, gs, gv_final, gx, dy, gv_init,
+                                                 red, T, P, C, ss, ppb, beta, theta, alpha);
+    return check_cuda(cudaGetLastError(), "bn_act_bwd_kernel");
+}
+
+int launch_bn_act_bwd(int act, int training, const float* y, const float* scale, const float* shift, const float* mean,
+                      const float* invstd, const float* v_init, const __nv_bfloat16* gs, const float* gv_final,
+                      float* gx, __nv_bfloat16* dy, float* gv_init, float* red, int T, int P, int C, int ss_stride_t,
+                      float beta, float theta, float alpha, cudaStream_t st) {
+    SNN_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "bn_act_bwd: C=%d must be a multiple of 4 in [4,1024]", C);
+    SNN_REQUIRE(T >= 1 && T <= 16, "bn_act_bwd: T=%d must be in [1,16]", T);
+    if (training) SNN_CUDA_OK(cudaMemsetAsync(red, 0, sizeof(float) * 2 * T * C, st));
+#define SNN_BWD(ACT, TM, TR) \
+    return launch_bwd_t<ACT, TM, TR>(y, scale, shift, mean, invstd, v_init, gs, gv_final, gx, dy, gv_init, red, T, P, C, ss_stride_t, beta, theta, alpha, st)
+    if (act == ACT_LIF) {
+        if (training) { if (T <= 4) SNN_BWD(ACT_LIF, 4, true); else if (T <= 8) SNN_BWD(ACT_LIF, 8, true); else SNN_BWD(ACT_LIF, 16, true); }
+        else          { if (T <= 4) SNN_BWD(ACT_LIF, 4, false); else if (T <= 8) SNN_BWD(ACT_LIF, 8, false); else SNN_BWD(ACT_LIF, 16, false); }
+    } else {
+        if (training) { if (T <= 4) SNN_BWD(ACT_SILU, 4, true); else if (T <= 8) SNN_BWD(ACT_SILU, 8, true); else SNN_BWD(ACT_SILU, 16, true); }
+        else          { if (T <= 4) SNN_BWD(ACT_SILU, 4, false); else if (T <= 8) SNN_BWD(ACT_SILU, 8, false); else SNN_BWD(ACT_SILU, 16, false); }
+    }
+#undef SNN_BWD
+}
+
+int launch_bn_bwd_dx(const float* red, const float* gamma, const float* gx, const float* y, const float* scale,
+                     const float* mean, const float* invstd, float* coef, float* dgamma, float* dbeta,
+                     __nv_bfloat16* dy, int T, int P, int C, cudaStream_t st) {
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, scale, coef, dgamma, dbeta, gamma, T, C, P);
+    SNN_CUDA_OK(cudaGetLastError());
+    const long long n4 = (long long)P * C / 4;
+    dim3 grid((unsigned)((n4 + 255) / 256), T);
+    bn_bwd_dx_kernel<<<grid, 256, 0, st>>>(gx, y, scale, mean, invstd, coef, dy, T, n4, C);
+    return check_cuda(cudaGetLastError(), "bn_bwd_dx_kernel");
+}
+
+}  // namespace snn

@@ -1,0 +1,214 @@
+"""Functional (non-autograd) wrappers: torch tensors in, libsnnb200 kernels launched on the current stream.
+
+Activations are NHWC tensors ``[NB, H, W, C]`` (NB = T*B folded); a tensor may be a channel slice of
+a wider buffer (``stride(2) = ld >= C``).  See include/snn_b200.h for the ABI.
+"""
+import torch
+
+from . import _lib
+from ._lib import (ACT_LIF, ACT_SILU, GEOM_1x1, GEOM_3x3_S1, GEOM_3x3_S2, GEOM_T2x2_S2, GEOM_TAPS, call, ptr,
+                   require_cuda, stream_ptr)
+
+
+def _nhwc_ld(x):
+    """Validate an NHWC (channel-slice) view and return its pixel stride."""
+    nb, h, w, c = x.shape
+    ld = x.stride(2) if w > 1 else (x.stride(1) if h > 1 else (x.stride(0) if nb > 1 else c))
+    if x.stride(3) != 1 and c > 1:
+        raise ValueError("NHWC view must be channel-contiguous")
+    if (w > 1 and x.stride(2) != ld) or (h > 1 and x.stride(1) != w * ld) or (nb > 1 and x.stride(0) != h * w * ld):
+        raise ValueError(f"not a dense NHWC pixel grid: shape {tuple(x.shape)} strides {x.stride()}")
+    return ld
+
+
+def out_hw(geom, h, w):
+    if geom == GEOM_3x3_S2:
+        return h // 2, w // 2
+    if geom == GEOM_T2x2_S2:
+        return 2 * h, 2 * w
+    return h, w
+
+
+def conv_fprop(geom, x0, w_bf16, cout, x1=None, bias=None, out=None, out_dtype=torch.float32, w_coff=0, w_row_off=0,
+               accumulate=False):
+    """out[NB,Ho,Wo,cout] = conv(cat([x0,x1],C), W[w_row_off:w_row_off+cout, :, w_coff:...]) (+bias)."""
+    require_cuda(x0, x1, w_bf16, bias, out)
+    nb, h, w, c0 = x0.shape
+    ho, wo = out_hw(geom, h, w)
+    if out is None:
+        out = torch.empty((nb, ho, wo, cout), device=x0.device, dtype=out_dtype)
+    assert x0.dtype == torch.bfloat16 and w_bf16.dtype == torch.bfloat16 and w_bf16.is_contiguous()
+    assert tuple(out.shape) == (nb, ho, wo, cout)
+    rows, taps, wk = w_bf16.shape
+    assert taps == GEOM_TAPS[geom]
+    c1 = 0 if x1 is None else x1.shape[3]
+    if x1 is not None:
+        assert x1.dtype == torch.bfloat16 and tuple(x1.shape[:3]) == (nb, h, w)
+    assert w_coff + c0 + c1 <= wk and w_row_off + cout <= rows
+    call("snn_conv_fprop", geom, nb, h, w, ptr(x0), c0, _nhwc_ld(x0), ptr(x1), c1, 0 if x1 is None else _nhwc_ld(x1),
+         ptr(w_bf16), rows, wk, w_coff, cout, w_row_off, ptr(bias), ptr(out), int(out.dtype == torch.float32),
+         _nhwc_ld(out), 0, int(accumulate), stream_ptr())
+    return out
+
+
+def conv_dgrad(geom, dy, wt_bf16, in_hw, ci, ci_off=0, out=None, out_dtype=torch.bfloat16, accumulate=False):
+    """dx[NB,H,W,ci] for the conv-input channel range [ci_off, ci_off+ci); wt_bf16 = [Cin_tot][taps][Cout]."""
+    require_cuda(dy, wt_bf16, out)
+    nb, hy, wy, cout = dy.shape
+    h, w = in_hw
+    assert out_hw(geom, h, w) == (hy, wy), (geom, in_hw, dy.shape)
+    rows, taps, wk = wt_bf16.shape
+    assert taps == GEOM_TAPS[geom] and wk == cout and ci_off + ci <= rows
+    assert dy.dtype == torch.bfloat16 and wt_bf16.dtype == torch.bfloat16 and wt_bf16.is_contiguous()
+    if out is None:
+        out = torch.empty((nb, h, w, ci), device=dy.device, dtype=out_dtype)
+    call("snn_conv_dgrad", geom, nb, h, w, ptr(dy), cout, _nhwc_ld(dy), ptr(wt_bf16), rows, ci_off, ci, ptr(out),
+         int(out.dtype == torch.float32), _nhwc_ld(out), 0, int(accumulate), stream_ptr())
+    return out
+
+
+def conv_wgrad(geom, x, dy, dw, w_coff=0):
+    """dw[Cout][taps][wK] (fp32) += wgrad; x is the conv input NHWC bf16, dy the output gradient NHWC bf16."""
+    require_cuda(x, dy, dw)
+    nb, h, w, ci = x.shape
+    cout = dy.shape[3]
+    assert tuple(dy.shape[:3]) == (nb,) + out_hw(geom, h, w)
+    rows, taps, wk = dw.shape
+    assert rows == cout and taps == GEOM_TAPS[geom] and w_coff + ci <= wk
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16
+    call("snn_conv_wgrad", geom, nb, h, w, ptr(x), ci, _nhwc_ld(x), ptr(dy), cout, _nhwc_ld(dy), ptr(dw), wk, w_coff,
+         stream_ptr())
+    return dw
+
+
+def weight_prep(w_master, want_fprop=True, want_dgrad=True, wf=None, wt=None):
+    """fp32 [N][T][K] -> (bf16 [N][T][K], bf16 [K][T][N])."""
+    require_cuda(w_master)
+    n, t, k = w_master.shape
+    assert w_master.is_contiguous() and w_master.dtype == torch.float32
+    if want_fprop and wf is None:
+        wf = torch.empty((n, t, k), device=w_master.device, dtype=torch.bfloat16)
+    if want_dgrad and wt is None:
+        wt = torch.empty((k, t, n), device=w_master.device, dtype=torch.bfloat16)
+    call("snn_weight_prep", ptr(w_master), ptr(wf), ptr(wt), n, t, k, stream_ptr())
+    return wf, wt
+
+
+# ---------------------------------------------------------------------------------------------
+# neuron layer
+# ---------------------------------------------------------------------------------------------
+def bn_stats(y, T):
+    """y fp32 [T*B, H, W, C] -> sums fp64 [T][2][C]."""
+    require_cuda(y)
+    c = y.shape[-1]
+    p = y.numel() // (T * c)
+    sums = torch.empty((T, 2, c), device=y.device, dtype=torch.float64)
+    call("snn_bn_stats", ptr(y), ptr(sums), T, p, c, stream_ptr())
+    return sums
+
+
+def bn_finalize(sums, gamma, beta, running_mean, running_var, T, C, P, eps, momentum, training):
+    dev = gamma.device
+    n = T if training else 1
+    scale, shift, mean, invstd = (torch.empty((n, C), device=dev, dtype=torch.float32) for _ in range(4))
+    call("snn_bn_finalize", ptr(sums), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(scale), ptr(shift),
+         ptr(mean), ptr(invstd), T, C, P, float(eps), float(momentum), int(training), stream_ptr())
+    return scale, shift, mean, invstd
+
+
+def bn_act_fwd(act, y, scale, shift, T, v_init=None, want_mask=True, want_v_final=False, beta=0.5, theta=1.0):
+    """Fused BN affine + LIF scan over T (or SiLU).  y fp32 [T*B,H,W,C] -> bf16 same shape (+mask, +v_final)."""
+    require_cuda(y, scale, shift, v_init)
+    c = y.shape[-1]
+    n_per_t = y.numel() // T
+    out = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
+    mask = torch.empty((T, n_per_t // 8), device=y.device, dtype=torch.uint8) if (want_mask and act == ACT_LIF) else None
+    v_final = torch.empty((n_per_t,), device=y.device, dtype=torch.float32) if want_v_final else None
+    ss = c if scale.shape[0] == T and scale.dim() == 2 and scale.shape[0] > 1 else 0
+    if scale.dim() == 2 and scale.shape[0] == 1:
+        ss = 0
+    if T == 1:
+        ss = 0
+    call("snn_bn_act_fwd", act, ptr(y), ptr(scale), ptr(shift), ptr(v_init), ptr(out), ptr(mask), ptr(v_final), T, n_per_t,
+         c, ss, float(beta), float(theta), stream_ptr())
+    return out, mask, v_final
+
+
+def bn_act_bwd(act, training, y, scale, shift, mean, invstd, gs, T, v_init=None, gv_final=None, want_gv_init=False,
+               beta=0.5, theta=1.0, alpha=2.0):
+    """Returns (gx fp32 | None, dy bf16 | None, gv_init | None, red [T][2][C] | None)."""
+    require_cuda(y, gs)
+    c = y.shape[-1]
+    p = y.numel() // (T * c)
+    dev = y.device
+    gx = torch.empty(y.shape, device=dev, dtype=torch.float32) if training else None
+    dy = None if training else torch.empty(y.shape, device=dev, dtype=torch.bfloat16)
+    red = torch.empty((T, 2, c), device=dev, dtype=torch.float32) if training else None
+    gv_init = torch.empty((p * c,), device=dev, dtype=torch.float32) if want_gv_init else None
+    ss = 0 if (T == 1 or scale.shape[0] == 1) else c
+    assert gs.dtype == torch.bfloat16 and gs.is_contiguous()
+    call("snn_bn_act_bwd", act, int(training), ptr(y), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(v_init), ptr(gs),
+         ptr(gv_final), ptr(gx), ptr(dy), ptr(gv_init), ptr(red), T, p, c, ss, float(beta), float(theta), float(alpha),
+         stream_ptr())
+    return gx, dy, gv_init, red
+
+
+def bn_bwd_dx(red, gamma, gx, y, scale, mean, invstd, dgamma, dbeta, T):
+    c = y.shape[-1]
+    p = y.numel() // (T * c)
+    coef = torch.empty((T, 2, c), device=y.device, dtype=torch.float32)
+    dy = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
+    call("snn_bn_bwd_dx", ptr(red), ptr(gamma), ptr(gx), ptr(y), ptr(scale), ptr(mean), ptr(invstd), ptr(coef), ptr(dgamma),
+         ptr(dbeta), ptr(dy), T, p, c, stream_ptr())
+    return dy
+
+
+# ---------------------------------------------------------------------------------------------
+# ConvLSTM gates, layout conversion, optimizer
+# ---------------------------------------------------------------------------------------------
+def lstm_gates_fwd(gates, c_prev, ch):
+    p = gates.numel() // (4 * ch)
+    shape = gates.shape[:-1] + (ch,)
+    c_next = torch.empty(shape, device=gates.device, dtype=torch.float32)
+    h_next = torch.empty(shape, device=gates.device, dtype=torch.float32)
+    h_bf16 = torch.empty(shape, device=gates.device, dtype=torch.bfloat16)
+    call("snn_lstm_gates_fwd", ptr(gates), ptr(c_prev), ptr(c_next), ptr(h_next), ptr(h_bf16), p, ch, stream_ptr())
+    return h_next, c_next, h_bf16
+
+
+def lstm_gates_bwd(gates, c_prev, c_next, dh, dc_in, ch):
+    p = gates.numel() // (4 * ch)
+    dgates = torch.empty(gates.shape, device=gates.device, dtype=torch.bfloat16)
+    dc_prev = torch.empty(c_next.shape, device=gates.device, dtype=torch.float32)
+    call("snn_lstm_gates_bwd", ptr(gates), ptr(c_prev), ptr(c_next), ptr(dh), ptr(dc_in), ptr(dgates), ptr(dc_prev), p, ch,
+         stream_ptr())
+    return dgates, dc_prev
+
+
+def nchw_to_nhwc(x, dtype=torch.bfloat16, out=None):
+    """fp32 NCHW contiguous -> NHWC tensor (bf16 or fp32)."""
+    require_cuda(x)
+    nb, c, h, w = x.shape
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty((nb, h, w, c), device=x.device, dtype=dtype)
+    call("snn_nchw_to_nhwc", ptr(x), ptr(out), int(out.dtype == torch.bfloat16), nb, c, h * w, _nhwc_ld(out), 0, stream_ptr())
+    return out
+
+
+def nhwc_to_nchw(x):
+    """NHWC (bf16|fp32, may be a channel slice) -> fp32 NCHW contiguous."""
+    require_cuda(x)
+    nb, h, w, c = x.shape
+    out = torch.empty((nb, c, h, w), device=x.device, dtype=torch.float32)
+    call("snn_nhwc_to_nchw", ptr(x), int(x.dtype == torch.bfloat16), ptr(out), nb, c, h * w, _nhwc_ld(x), 0, stream_ptr())
+    return out
+
+
+def grad_sumsq(g, acc, zero_first=True):
+    call("snn_grad_sumsq", ptr(g), g.numel(), ptr(acc), int(zero_first), stream_ptr())
+
+
+def adamw_step(p, g, m, v, shadow, hp, sumsq, gnorm_out=None):
+    call("snn_adamw_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), p.numel(), ptr(hp), ptr(sumsq), ptr(gnorm_out),
+         stream_ptr())
