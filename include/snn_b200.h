@@ -90,6 +90,9 @@ int snn_nchw_to_nhwc(const float* in, void* out, int out_is_bf16, int NB, int C,
 int snn_nhwc_to_nchw(const void* in, int in_is_bf16, float* out, int NB, int C, int HW,
                      long long in_ld, int in_coff, void* stream);
 
+/* ---- bias gradient of the biased convs (ConvLSTM2d.conv, UpBlock.up, out_p*): acc[c] += sum_p dy[p][c] ---- */
+int snn_colsum_bf16(const void* dy_bf16, float* acc, long long P, int C, void* stream);
+
 /* ---- optimizer: replaces clip_grad_norm_(10) + AdamW.step (train.py:77-78) over one flat buffer.
  *      hp (device, 8 floats) = {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, max_norm} ---- */
 int snn_grad_sumsq(const float* g, long long n, double* acc, int zero_first, void* stream);

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "snn_lstm_gates_bwd": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
     "snn_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _L, _I, _P],
     "snn_nhwc_to_nchw": [_P, _I, _P, _I, _I, _I, _L, _I, _P],
+    "snn_colsum_bf16": [_P, _P, _L, _I, _P],
     "snn_grad_sumsq": [_P, _L, _P, _I, _P],
     "snn_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P],
 }

@@ -54,6 +54,7 @@ int launch_lstm_gates_bwd(const float*, const float*, const float*, const float*
 int launch_nchw_to_nhwc(const float*, void*, int, int, int, int, long long, int, cudaStream_t);
 int launch_nhwc_to_nchw(const void*, int, float*, int, int, int, long long, int, cudaStream_t);
 int launch_sumsq(const float*, long long, double*, int, cudaStream_t);
+int launch_colsum_bf16(const __nv_bfloat16*, float*, long long, int, cudaStream_t);
 int launch_adamw(float*, const float*, float*, float*, __nv_bfloat16*, long long, const float*, const double*, float*,
                  cudaStream_t);
 
@@ -125,6 +126,9 @@ int snn_nchw_to_nhwc(const float* in, void* out, int out_is_bf16, int NB, int C,
 int snn_nhwc_to_nchw(const void* in, int in_is_bf16, float* out, int NB, int C, int HW, long long in_ld, int in_coff,
                      void* stream) {
     return launch_nhwc_to_nchw(in, in_is_bf16, out, NB, C, HW, in_ld, in_coff, ST);
+}
+int snn_colsum_bf16(const void* dy, float* acc, long long P, int C, void* stream) {
+    return launch_colsum_bf16((const __nv_bfloat16*)dy, acc, P, C, ST);
 }
 int snn_grad_sumsq(const float* g, long long n, double* acc, int zero_first, void* stream) {
     return launch_sumsq(g, n, acc, zero_first, ST);

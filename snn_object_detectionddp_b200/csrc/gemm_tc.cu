@@ -440,7 +440,7 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     });
     SNN_CUDA_OK(attr_err);
     p.stage_bytes = 16384 + p.BN * 128;
@@ -594,7 +594,7 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     });
     SNN_CUDA_OK(attr_err);
     SNN_REQUIRE(Ci % 8 == 0 && Cout % 8 == 0 && w_K % 4 == 0 && w_coff % 4 == 0, "conv_wgrad: channel counts must be multiples of 8");

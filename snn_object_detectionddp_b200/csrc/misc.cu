@@ -190,6 +190,49 @@ int launch_lstm_gates_bwd(const float* gates, const float* c_prev, const float* 
 }
 
 // ------------------------------------------------------------------------------------------
+// bias gradient: acc[c] += sum_p dy[p][c]  (dy bf16 [P][C]); grid.y walks column blocks of <= 1024
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ acc, long long P, int C, int cblk,
+                   int pix_per_block) {
+    extern __shared__ float shc[];  // [cblk]
+    const int c_base = blockIdx.y * cblk;
+    const int cw = min(cblk, C - c_base);
+    const int tpp = cw >> 2;  // threads per pixel, 4 channels each
+    const int rows = 256 / tpp;
+    const int cg = threadIdx.x % tpp, row = threadIdx.x / tpp;
+    for (int i = threadIdx.x; i < cw; i += 256) shc[i] = 0.f;
+    __syncthreads();
+    if (row < rows) {
+        const long long p0 = (long long)blockIdx.x * pix_per_block;
+        const long long p1 = min(P, p0 + (long long)pix_per_block);
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (long long p = p0 + row; p < p1; p += rows) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(dy + p * C + c_base) + cg);
+            s[0] += bf16_lo(v.x); s[1] += bf16_hi(v.x); s[2] += bf16_lo(v.y); s[3] += bf16_hi(v.y);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) atomicAdd(&shc[cg * 4 + i], s[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cw; i += 256) atomicAdd(&acc[c_base + i], shc[i]);
+}
+
+int launch_colsum_bf16(const __nv_bfloat16* dy, float* acc, long long P, int C, cudaStream_t st) {
+    SNN_REQUIRE(C % 4 == 0, "colsum: C=%d must be a multiple of 4", C);
+    const int cblk = C < 1024 ? C : 1024;
+    SNN_REQUIRE(C % cblk == 0 || C < 1024, "colsum: C=%d must be < 1024 or a multiple of 1024", C);
+    const int rows = 256 / (cblk / 4);
+    long long want = (long long)num_sms() * 4;
+    long long ppb = (P + want - 1) / want;
+    if (ppb < rows * 4) ppb = rows * 4;
+    ppb = (ppb + rows - 1) / rows * rows;
+    dim3 grid((unsigned)((P + ppb - 1) / ppb), (C + cblk - 1) / cblk);
+    colsum_bf16_kernel<<<grid, 256, sizeof(float) * cblk, st>>>(dy, acc, P, C, cblk, (int)ppb);
+    return check_cuda(cudaGetLastError(), "colsum_bf16_kernel");
+}
+
+// ------------------------------------------------------------------------------------------
 // fused global grad-norm + clip + AdamW over ONE flat fp32 buffer (reference train.py:77-78)
 //   pass 1: sum of squares -> device scalar        (4 B/param)
 //   pass 2: clip coefficient from the scalar, AdamW update, bf16 shadow copy (28+2 B/param)

@@ -166,19 +166,21 @@ def bn_bwd_dx(red, gamma, gx, y, scale, mean, invstd, dgamma, dbeta, T):
 # ---------------------------------------------------------------------------------------------
 # ConvLSTM gates, layout conversion, optimizer
 # ---------------------------------------------------------------------------------------------
-def lstm_gates_fwd(gates, c_prev, ch):
+def lstm_gates_fwd(gates, c_prev, ch, h_bf16_out=None, c_out=None):
     p = gates.numel() // (4 * ch)
     shape = gates.shape[:-1] + (ch,)
-    c_next = torch.empty(shape, device=gates.device, dtype=torch.float32)
+    c_next = torch.empty(shape, device=gates.device, dtype=torch.float32) if c_out is None else c_out
     h_next = torch.empty(shape, device=gates.device, dtype=torch.float32)
-    h_bf16 = torch.empty(shape, device=gates.device, dtype=torch.bfloat16)
+    h_bf16 = torch.empty(shape, device=gates.device, dtype=torch.bfloat16) if h_bf16_out is None else h_bf16_out
+    assert gates.is_contiguous() and c_next.is_contiguous() and h_bf16.is_contiguous()
     call("snn_lstm_gates_fwd", ptr(gates), ptr(c_prev), ptr(c_next), ptr(h_next), ptr(h_bf16), p, ch, stream_ptr())
     return h_next, c_next, h_bf16
 
 
-def lstm_gates_bwd(gates, c_prev, c_next, dh, dc_in, ch):
+def lstm_gates_bwd(gates, c_prev, c_next, dh, dc_in, ch, dgates_out=None):
     p = gates.numel() // (4 * ch)
-    dgates = torch.empty(gates.shape, device=gates.device, dtype=torch.bfloat16)
+    dgates = torch.empty(gates.shape, device=gates.device, dtype=torch.bfloat16) if dgates_out is None else dgates_out
+    assert gates.is_contiguous() and dgates.is_contiguous() and dh.is_contiguous() and dh.dtype == torch.float32
     dc_prev = torch.empty(c_next.shape, device=gates.device, dtype=torch.float32)
     call("snn_lstm_gates_bwd", ptr(gates), ptr(c_prev), ptr(c_next), ptr(dh), ptr(dc_in), ptr(dgates), ptr(dc_prev), p, ch,
          stream_ptr())
@@ -203,6 +205,13 @@ def nhwc_to_nchw(x):
     out = torch.empty((nb, c, h, w), device=x.device, dtype=torch.float32)
     call("snn_nhwc_to_nchw", ptr(x), int(x.dtype == torch.bfloat16), ptr(out), nb, c, h * w, _nhwc_ld(x), 0, stream_ptr())
     return out
+
+
+def colsum_accumulate(dy, acc):
+    """acc[c] (fp32) += sum over all pixels of dy[..., c] (bf16)."""
+    c = dy.shape[-1]
+    assert dy.is_contiguous() and dy.dtype == torch.bfloat16 and acc.numel() == c and acc.is_contiguous()
+    call("snn_colsum_bf16", ptr(dy), ptr(acc), dy.numel() // c, c, stream_ptr())
 
 
 def grad_sumsq(g, acc, zero_first=True):

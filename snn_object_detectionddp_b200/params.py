@@ -1,0 +1,182 @@
+"""Flat parameter store: one fp32 master buffer, one fp32 gradient buffer, Adam moments and bf16
+tensor-core operand copies for every trainable tensor of a model.
+
+Why: (a) the optimizer (reference train.py:77-78: clip_grad_norm_ + AdamW.step) becomes two passes
+over ONE contiguous buffer; (b) DDP buckets are contiguous ranges of the gradient buffer (no
+flatten/unflatten copies); (c) conv weights are kept physically in the [Cout][kh*kw][Cin] order the TMA
+tensor maps want, while ``nn.Parameter`` objects keep the reference's logical shapes and names
+(``state_dict`` / checkpoints interchange with the reference).
+"""
+import weakref
+
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+
+_PAD = 8  # elements; keeps bf16 slices 16-byte aligned
+_STORE_OF_PARAM = weakref.WeakValueDictionary()
+
+
+def _kind_of(module, pname):
+    if isinstance(module, nn.ConvTranspose2d) and pname == "weight":
+        return "convT"
+    if isinstance(module, nn.Conv2d) and pname == "weight":
+        return "dw" if module.groups > 1 else "conv"
+    return "vec"
+
+
+class Entry:
+    __slots__ = ("name", "param", "kind", "offset", "numel", "shape3", "ready_epoch")
+
+    def __init__(self, name, param, kind, offset):
+        self.name, self.param, self.kind, self.offset = name, param, kind, offset
+        self.numel = param.numel()
+        s = tuple(param.shape)
+        if kind == "conv":      # logical [Cout, Cin, kh, kw] -> [N=Cout][T=kh*kw][K=Cin]
+            self.shape3 = (s[0], s[2] * s[3], s[1])
+        elif kind == "convT":   # logical [Cin, Cout, 2, 2]  -> [N=Cout][T=4][K=Cin]
+            self.shape3 = (s[1], s[2] * s[3], s[0])
+        elif kind == "dw":      # logical [C, 1, kh, kw]     -> [T=kh*kw][C]
+            self.shape3 = (1, s[2] * s[3], s[0])
+        else:
+            self.shape3 = None
+        self.ready_epoch = -1
+
+    def logical_view(self, flat):
+        """View of flat[offset:offset+numel] with the parameter's logical shape (strided)."""
+        sl = flat[self.offset:self.offset + self.numel]
+        s = tuple(self.param.shape)
+        if self.kind == "conv":
+            return sl.view(s[0], s[2], s[3], s[1]).permute(0, 3, 1, 2)
+        if self.kind == "convT":
+            return sl.view(s[1], s[2], s[3], s[0]).permute(3, 0, 1, 2)
+        if self.kind == "dw":
+            return sl.view(s[2], s[3], s[1], s[0]).permute(3, 2, 0, 1)
+        return sl.view(s)
+
+    def view3(self, flat):
+        return flat[self.offset:self.offset + self.numel].view(self.shape3)
+
+
+class ParamStore:
+    def __init__(self, root):
+        self.root = weakref.ref(root)
+        self.entries = []
+        self.by_param = {}
+        off = 0
+        seen = set()
+        for mname, mod in root.named_modules():
+            for pname, p in mod.named_parameters(recurse=False):
+                if id(p) in seen or not p.requires_grad:
+                    continue
+                seen.add(id(p))
+                e = Entry((mname + "." if mname else "") + pname, p, _kind_of(mod, pname), off)
+                self.entries.append(e)
+                self.by_param[id(p)] = e
+                off += (e.numel + _PAD - 1) // _PAD * _PAD
+        self.total = off
+        self.flat_p = self.flat_g = self.flat_m = self.flat_v = self.shadow = self.flat_wt = None
+        self.device = None
+        self._versions = None
+        self.opt_epoch = 0           # bumped by the fused optimizer (it rewrites master + shadow)
+        self._wt_epoch = -1
+        self.grad_epoch = 0          # bumped by zero_grad(); used by DDP bucket bookkeeping
+        self.grad_ready_hook = None  # callable(entry) fired right after an entry's gradient is complete
+        for e in self.entries:
+            _STORE_OF_PARAM[id(e.param)] = self
+
+    # -- construction / re-attachment ------------------------------------------------------
+    def _attached(self, e):
+        p = e.param
+        return (self.flat_p is not None and p.device == self.flat_p.device and p.dtype == torch.float32
+                and p.data_ptr() == self.flat_p.data_ptr() + 4 * e.offset
+                and p.stride() == e.logical_view(self.flat_p).stride())
+
+    def ensure(self, device):
+        """(Re)build the flat buffers on `device` and point every Parameter at its slice."""
+        device = torch.device(device)
+        if device.type != "cuda" and not getattr(K, "_EMULATED", False):
+            raise K._lib.SnnKernelError("parameters must live on a CUDA device (no CPU fallback)")
+        if self.flat_p is not None and self.device == device and all(self._attached(e) for e in self.entries):
+            return self
+        old_m, old_v = self.flat_m, self.flat_v
+        flat_p = torch.zeros(self.total, device=device, dtype=torch.float32)
+        for e in self.entries:
+            e.logical_view(flat_p).copy_(e.param.data.to(device=device, dtype=torch.float32))
+        self.flat_p = flat_p
+        self.flat_g = torch.zeros(self.total, device=device, dtype=torch.float32)
+        keep = old_m is not None and old_m.device == device
+        self.flat_m = old_m if keep else torch.zeros(self.total, device=device, dtype=torch.float32)
+        self.flat_v = old_v if keep else torch.zeros(self.total, device=device, dtype=torch.float32)
+        self.shadow = torch.zeros(self.total, device=device, dtype=torch.bfloat16)
+        self.flat_wt = torch.zeros(self.total, device=device, dtype=torch.bfloat16)
+        self.device = device
+        for e in self.entries:
+            e.param.data = e.logical_view(self.flat_p)
+            e.param.grad = None
+        self._versions = None
+        self._wt_epoch = -1
+        return self
+
+    # -- bf16 operand copies ---------------------------------------------------------------
+    def refresh_operands(self):
+        """Make shadow (bf16 [N][T][K]) and flat_wt (bf16 [K][T][N]) current."""
+        vers = tuple(e.param._version for e in self.entries)
+        stale_master = vers != self._versions
+        if not stale_master and self._wt_epoch == self.opt_epoch:
+            return
+        for e in self.entries:
+            if e.kind in ("conv", "convT"):
+                n, t, k = e.shape3
+                wf = self.shadow[e.offset:e.offset + e.numel].view(n, t, k) if stale_master else None
+                wt = self.flat_wt[e.offset:e.offset + e.numel].view(k, t, n)
+                K.weight_prep(e.view3(self.flat_p), want_fprop=stale_master, want_dgrad=True, wf=wf, wt=wt)
+        self._versions = vers
+        self._wt_epoch = self.opt_epoch
+
+    def w_fprop(self, p):
+        e = self.by_param[id(p)]
+        return e.view3(self.shadow)
+
+    def w_dgrad(self, p):
+        e = self.by_param[id(p)]
+        n, t, k = e.shape3
+        return self.flat_wt[e.offset:e.offset + e.numel].view(k, t, n)
+
+    # -- gradients -------------------------------------------------------------------------
+    def zero_grad(self):
+        self.flat_g.zero_()
+        self.grad_epoch += 1
+        for e in self.entries:
+            e.param.grad = e.logical_view(self.flat_g)
+
+    def grad_view(self, p, three_d=False):
+        """Gradient slice to accumulate into (PyTorch semantics: a `None` grad means start from zero)."""
+        e = self.by_param[id(p)]
+        g = p.grad
+        ours = e.logical_view(self.flat_g)
+        if g is None or g.data_ptr() != ours.data_ptr():
+            self.flat_g[e.offset:e.offset + e.numel].zero_()
+            if g is not None:
+                ours.add_(g)
+            p.grad = ours
+        return e.view3(self.flat_g) if three_d else ours
+
+    def grad_done(self, p):
+        if self.grad_ready_hook is not None:
+            self.grad_ready_hook(self.by_param[id(p)])
+
+
+def store_for(root, device):
+    """Store owning `root`'s parameters (shared with an enclosing model if one already claimed them)."""
+    st = getattr(root, "_snn_store", None)
+    if st is None:
+        params = [p for p in root.parameters() if p.requires_grad]
+        owner = _STORE_OF_PARAM.get(id(params[0])) if params else None
+        if owner is not None and all(_STORE_OF_PARAM.get(id(p)) is owner for p in params):
+            st = owner
+        else:
+            st = ParamStore(root)
+        object.__setattr__(root, "_snn_store", st)
+    return st.ensure(device)

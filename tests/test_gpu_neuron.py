@@ -35,8 +35,8 @@ def test_bn_stats_and_finalize(T, B, H, W, C):
     P = B * H * W
     sums = K.bn_stats(y, T)
     yt = y.reshape(T, P, C).double()
-    assert torch.allclose(sums[:, 0], yt.sum(1), rtol=1e-6, atol=1e-6)
-    assert torch.allclose(sums[:, 1], (yt * yt).sum(1), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(sums[:, 0], yt.sum(1), rtol=1e-5, atol=1e-4)  # fp32 partials of <=64 values, fp64 combine
+    assert torch.allclose(sums[:, 1], (yt * yt).sum(1), rtol=1e-5, atol=1e-4)
     rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
     scale, shift, mean, invstd = K.bn_finalize(sums, gamma, beta, rm, rv, T, C, P, 1e-5, 0.1, True)
     # torch BatchNorm2d called once per timestep (reference train.py:64-66 -> model.py:14)
