@@ -90,6 +90,16 @@ int snn_nchw_to_nhwc(const float* in, void* out, int out_is_bf16, int NB, int C,
 int snn_nhwc_to_nchw(const void* in, int in_is_bf16, float* out, int NB, int C, int HW,
                      long long in_ld, int in_coff, void* stream);
 
+/* ---- Detect-head depthwise 3x3 (ultralytics DWConv inside `Detect.cv3`, built at model.py:186):
+ *      x/dy bf16 NHWC, weights fp32 [9][C], y fp32 NHWC (feeds the BN+SiLU kernel), dw += ---- */
+int snn_dw3x3_fprop(const void* x_bf16, const float* w, float* y, int NB, int H, int W, int C, void* stream);
+int snn_dw3x3_dgrad(const void* dy_bf16, const float* w, void* dx_bf16, int NB, int H, int W, int C, void* stream);
+int snn_dw3x3_wgrad(const void* x_bf16, const void* dy_bf16, float* dw, int NB, int H, int W, int C, void* stream);
+
+/* ---- frame packer of the stand-in feature pyramid (the frozen YOLO11m of model.py:74-98 cannot exist
+ *      offline): fp32 frames [B][T][3][H][W] -> bf16 NHWC [T*B][H/8][W/8][192] ---- */
+int snn_space_to_depth8(const float* frames, void* out_bf16, int B, int T, int H, int W, void* stream);
+
 /* ---- bias gradient of the biased convs (ConvLSTM2d.conv, UpBlock.up, out_p*): acc[c] += sum_p dy[p][c] ---- */
 int snn_colsum_bf16(const void* dy_bf16, float* acc, long long P, int C, void* stream);
 

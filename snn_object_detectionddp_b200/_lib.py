@@ -32,6 +32,10 @@ _SIGNATURES = {
     "snn_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _L, _I, _P],
     "snn_nhwc_to_nchw": [_P, _I, _P, _I, _I, _I, _L, _I, _P],
     "snn_colsum_bf16": [_P, _P, _L, _I, _P],
+    "snn_dw3x3_fprop": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "snn_dw3x3_dgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "snn_dw3x3_wgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "snn_space_to_depth8": [_P, _P, _I, _I, _I, _I, _P],
     "snn_grad_sumsq": [_P, _L, _P, _I, _P],
     "snn_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P],
 }

@@ -55,6 +55,10 @@ int launch_nchw_to_nhwc(const float*, void*, int, int, int, int, long long, int,
 int launch_nhwc_to_nchw(const void*, int, float*, int, int, int, long long, int, cudaStream_t);
 int launch_sumsq(const float*, long long, double*, int, cudaStream_t);
 int launch_colsum_bf16(const __nv_bfloat16*, float*, long long, int, cudaStream_t);
+int launch_dw3x3_fwd(const __nv_bfloat16*, const float*, float*, int, int, int, int, cudaStream_t);
+int launch_dw3x3_dgrad(const __nv_bfloat16*, const float*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
+int launch_dw3x3_wgrad(const __nv_bfloat16*, const __nv_bfloat16*, float*, int, int, int, int, cudaStream_t);
+int launch_s2d8(const float*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 int launch_adamw(float*, const float*, float*, float*, __nv_bfloat16*, long long, const float*, const double*, float*,
                  cudaStream_t);
 
@@ -126,6 +130,18 @@ int snn_nchw_to_nhwc(const float* in, void* out, int out_is_bf16, int NB, int C,
 int snn_nhwc_to_nchw(const void* in, int in_is_bf16, float* out, int NB, int C, int HW, long long in_ld, int in_coff,
                      void* stream) {
     return launch_nhwc_to_nchw(in, in_is_bf16, out, NB, C, HW, in_ld, in_coff, ST);
+}
+int snn_dw3x3_fprop(const void* x, const float* w, float* y, int NB, int H, int W, int C, void* stream) {
+    return launch_dw3x3_fwd((const __nv_bfloat16*)x, w, y, NB, H, W, C, ST);
+}
+int snn_dw3x3_dgrad(const void* dy, const float* w, void* dx, int NB, int H, int W, int C, void* stream) {
+    return launch_dw3x3_dgrad((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, NB, H, W, C, ST);
+}
+int snn_dw3x3_wgrad(const void* x, const void* dy, float* dw, int NB, int H, int W, int C, void* stream) {
+    return launch_dw3x3_wgrad((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, NB, H, W, C, ST);
+}
+int snn_space_to_depth8(const float* frames, void* out, int B, int T, int H, int W, void* stream) {
+    return launch_s2d8(frames, (__nv_bfloat16*)out, B, T, H, W, ST);
 }
 int snn_colsum_bf16(const void* dy, float* acc, long long P, int C, void* stream) {
     return launch_colsum_bf16((const __nv_bfloat16*)dy, acc, P, C, ST);

@@ -221,3 +221,43 @@ def grad_sumsq(g, acc, zero_first=True):
 def adamw_step(p, g, m, v, shadow, hp, sumsq, gnorm_out=None):
     call("snn_adamw_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), p.numel(), ptr(hp), ptr(sumsq), ptr(gnorm_out),
          stream_ptr())
+
+
+# ---------------------------------------------------------------------------------------------
+# Detect-head depthwise conv, frame packer
+# ---------------------------------------------------------------------------------------------
+GEOM_DW3x3 = 4
+
+
+def dw3x3_fprop(x, w9c):
+    """x bf16 NHWC, w fp32 [9][C] -> y fp32 NHWC."""
+    require_cuda(x, w9c)
+    nb, h, w, c = x.shape
+    assert x.is_contiguous() and x.dtype == torch.bfloat16 and w9c.is_contiguous() and w9c.numel() == 9 * c
+    y = torch.empty((nb, h, w, c), device=x.device, dtype=torch.float32)
+    call("snn_dw3x3_fprop", ptr(x), ptr(w9c), ptr(y), nb, h, w, c, stream_ptr())
+    return y
+
+
+def dw3x3_dgrad(dy, w9c):
+    nb, h, w, c = dy.shape
+    assert dy.is_contiguous() and dy.dtype == torch.bfloat16
+    dx = torch.empty((nb, h, w, c), device=dy.device, dtype=torch.bfloat16)
+    call("snn_dw3x3_dgrad", ptr(dy), ptr(w9c), ptr(dx), nb, h, w, c, stream_ptr())
+    return dx
+
+
+def dw3x3_wgrad(x, dy, dw9c):
+    nb, h, w, c = x.shape
+    assert x.is_contiguous() and dy.is_contiguous() and dw9c.is_contiguous() and dw9c.dtype == torch.float32
+    call("snn_dw3x3_wgrad", ptr(x), ptr(dy), ptr(dw9c), nb, h, w, c, stream_ptr())
+
+
+def space_to_depth8(frames, B, T):
+    """fp32 frames [B,T,3,H,W] (contiguous) -> bf16 NHWC [T*B, H/8, W/8, 192] (timestep-major folded batch)."""
+    require_cuda(frames)
+    assert frames.is_contiguous() and frames.dtype == torch.float32
+    h, w = frames.shape[-2:]
+    out = torch.empty((T * B, h // 8, w // 8, 192), device=frames.device, dtype=torch.bfloat16)
+    call("snn_space_to_depth8", ptr(frames), ptr(out), B, T, h, w, stream_ptr())
+    return out

@@ -1,0 +1,343 @@
+"""Host-side mirror of the reference's model.py: same class names, constructor arguments, attribute /
+parameter names and forward signatures -- compute is the libsnnb200 CUDA kernels.
+
+    ConvBlock (ref model.py:9-18)      conv -> BN -> {LIF | SiLU}    one fused autograd op over all T steps
+    DownBlock (ref model.py:20-30), UpBlock (ref model.py:32-48), ConvLSTM2d (ref model.py:50-71)
+    TemporalUNet (ref model.py:100-146), YOLOFeatureExtractor (ref model.py:74-98), YOLOTemporalUNet
+    (ref model.py:148-211)
+
+Two entry styles:
+  * drop-in, per frame:   ``preds, hidden = model(frame[B,3,H,W], hidden)``  (train.py:64-66 loop works unchanged;
+    NCHW fp32 tensors in/out; LIF membranes travel inside the opaque ``hidden``)
+  * fused, per sequence:  ``model.forward_sequence(frames[B,T,3,H,W])`` runs layer-by-layer over the folded
+    T*B batch (valid because layer l at step t needs only layer l-1 at step t and its own state at t-1;
+    SURVEY.md 7.4-2); per-timestep BatchNorm statistics are kept so the numbers equal the per-frame loop.
+
+`neuron='lif'` is the BUILD-DEFINED spiking variant (the reference has no LIF);
+`neuron='silu'` reproduces the reference network itself.
+"""
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+from .ops import ConvBiasFn, ConvBNActFn, ConvLSTMSeqFn, NeuronCfg
+from .params import store_for
+from ._lib import GEOM_1x1, GEOM_3x3_S1, GEOM_3x3_S2, GEOM_T2x2_S2
+
+
+class RunCtx:
+    """Per-call context handed down the module tree."""
+
+    def __init__(self, store, T, want_state=False, want_mask=False, fp32_outputs=False):
+        self.store, self.T, self.want_state, self.want_mask, self.fp32_outputs = store, T, want_state, want_mask, fp32_outputs
+
+
+def _to_nhwc_bf16(x):
+    """NCHW fp32 (reference layout) -> NHWC bf16, differentiable (drop-in path only)."""
+    return x.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+
+
+def _to_nchw_f32(x):
+    return x.float().permute(0, 3, 1, 2)
+
+
+def make_neuron(neuron):
+    if isinstance(neuron, NeuronCfg):
+        return neuron
+    if neuron is None:
+        return NeuronCfg("lif")
+    if isinstance(neuron, str):
+        return NeuronCfg(neuron)
+    d = dict(neuron)
+    return NeuronCfg(d.get("type", "lif"), d.get("beta", 0.5), d.get("v_th", 1.0), d.get("alpha", 2.0))
+
+
+# ----------------------------------------------------------------------------------------------
+class ConvBlock(nn.Module):
+    """Conv2d(bias=False) -> BatchNorm2d -> neuron.  `conv` / `bn` are parameter containers (same state_dict keys
+    as the reference); they are never called."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, neuron=None, groups=1,
+                 bn_eps=1e-5, bn_momentum=0.1):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, groups=groups, bias=False)
+        self.bn = nn.BatchNorm2d(out_channels, eps=bn_eps, momentum=bn_momentum)
+        self.neuron = make_neuron(neuron)
+        if groups > 1:
+            assert groups == in_channels == out_channels and kernel_size == 3 and stride == 1 and padding == 1
+            self.geom = K.GEOM_DW3x3
+        elif kernel_size == 3 and padding == 1 and stride in (1, 2):
+            self.geom = GEOM_3x3_S1 if stride == 1 else GEOM_3x3_S2
+        elif kernel_size == 1 and padding == 0 and stride == 1:
+            self.geom = GEOM_1x1
+        else:
+            raise NotImplementedError("ConvBlock supports k3/p1/s{1,2}, k1/p0/s1 and depthwise k3 (the shapes on the path)")
+        self.last_mask = None
+
+    def forward_seq(self, rc, x0, x1=None, v_init=None):
+        cfg = dict(store=rc.store, geom=self.geom, T=rc.T, bn=self.bn, neuron=self.neuron, training=self.training,
+                   want_state=rc.want_state, want_mask=rc.want_mask)
+        out, v = ConvBNActFn.apply(x0, x1, v_init, self.conv.weight, self.bn.weight, self.bn.bias, cfg)
+        if rc.want_mask:
+            self.last_mask = cfg.get("last_mask")
+        return out, v
+
+    def forward(self, x):
+        """Drop-in single call on NCHW fp32 (zero initial membrane)."""
+        st = store_for(self, x.device)
+        st.refresh_operands()
+        out, _ = self.forward_seq(RunCtx(st, 1), _to_nhwc_bf16(x))
+        return _to_nchw_f32(out)
+
+
+class DownBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, neuron=None):
+        super().__init__()
+        self.conv1 = ConvBlock(in_channels, out_channels, stride=2, neuron=neuron)
+        self.conv2 = ConvBlock(out_channels, out_channels, neuron=neuron)
+
+    def forward_seq(self, rc, x, v=None):
+        v = v or (None, None)
+        x, v1 = self.conv1.forward_seq(rc, x, None, v[0])
+        x, v2 = self.conv2.forward_seq(rc, x, None, v[1])
+        return x, (v1, v2)
+
+    def forward(self, x):
+        st = store_for(self, x.device)
+        st.refresh_operands()
+        out, _ = self.forward_seq(RunCtx(st, 1), _to_nhwc_bf16(x))
+        return _to_nchw_f32(out)
+
+
+class UpBlock(nn.Module):
+    def __init__(self, in_channels, skip_channels, out_channels, neuron=None):
+        super().__init__()
+        self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
+        self.conv1 = ConvBlock(in_channels // 2 + skip_channels, out_channels, neuron=neuron)
+        self.conv2 = ConvBlock(out_channels, out_channels, neuron=neuron)
+
+    def forward_seq(self, rc, x, skip, v=None):
+        v = v or (None, None)
+        up = ConvBiasFn.apply(x, self.up.weight, self.up.bias, dict(store=rc.store, geom=GEOM_T2x2_S2))
+        if up.shape[1:3] != skip.shape[1:3]:
+            raise NotImplementedError(
+                "skip/upsample size mismatch (reference model.py:43-44 bilinear branch): input H, W must be multiples "
+                "of 64 for the B200 path")
+        x, v1 = self.conv1.forward_seq(rc, skip, up, v[0])      # cat([skip_x, x]) order of model.py:45
+        x, v2 = self.conv2.forward_seq(rc, x, None, v[1])
+        return x, (v1, v2)
+
+    def forward(self, x, skip_x):
+        st = store_for(self, x.device)
+        st.refresh_operands()
+        out, _ = self.forward_seq(RunCtx(st, 1), _to_nhwc_bf16(x), _to_nhwc_bf16(skip_x))
+        return _to_nchw_f32(out)
+
+
+class ConvLSTM2d(nn.Module):
+    def __init__(self, in_channels, hidden_channels, kernel_size=3):
+        super().__init__()
+        assert kernel_size == 3
+        self.hidden_channels = hidden_channels
+        self.conv = nn.Conv2d(in_channels + hidden_channels, 4 * hidden_channels, kernel_size,
+                              padding=kernel_size // 2, bias=True)
+
+    def forward_seq(self, rc, x, state=None):
+        """x bf16 [T*B,h,w,Cin]; state = (h, c) fp32 NHWC [B,h,w,Ch] or None. Returns h_all bf16, (h_T, c_T)."""
+        h0, c0 = state if state is not None else (None, None)
+        cfg = dict(store=rc.store, T=rc.T, bias=self.conv.bias)
+        h_all, h_last, c_last = ConvLSTMSeqFn.apply(x, h0, c0, self.conv.weight, self.conv.bias, cfg)
+        return h_all, (h_last, c_last)
+
+    def forward(self, x, hidden_state=None):
+        st = store_for(self, x.device)
+        st.refresh_operands()
+        state = None
+        if hidden_state is not None:
+            state = tuple(s.permute(0, 2, 3, 1).contiguous() for s in hidden_state)
+        h_all, (h, c) = self.forward_seq(RunCtx(st, 1), _to_nhwc_bf16(x), state)
+        h, c = h.permute(0, 3, 1, 2), c.permute(0, 3, 1, 2)
+        return h, (h, c)
+
+
+# ----------------------------------------------------------------------------------------------
+class TemporalUNet(nn.Module):
+    """U-Net with ConvLSTM bottleneck (reference model.py:100-146)."""
+
+    def __init__(self, feature_channels, use_conv_lstm=True, neuron=None, widths=(128, 256, 512, 1024)):
+        super().__init__()
+        if not use_conv_lstm:
+            raise NotImplementedError("use_conv_lstm=False (nn.LSTM bottleneck, model.py:114) is outside the B200 hot path")
+        ch_p3, ch_p4, ch_p5 = feature_channels
+        w1, w2, w3, w4 = widths
+        self.use_conv_lstm = use_conv_lstm
+        nr = make_neuron(neuron)
+        self.neuron = nr
+        self.enc1, self.down1 = ConvBlock(ch_p3, w1, neuron=nr), DownBlock(w1, w2, neuron=nr)
+        self.enc2, self.down2 = ConvBlock(w2 + ch_p4, w2, neuron=nr), DownBlock(w2, w3, neuron=nr)
+        self.enc3, self.down3 = ConvBlock(w3 + ch_p5, w3, neuron=nr), DownBlock(w3, w4, neuron=nr)
+        self.lstm = ConvLSTM2d(w4, w4)
+        self.bottleneck_conv = ConvBlock(w4, w4, neuron=nr)
+        self.up1, self.up2, self.up3 = UpBlock(w4, w3, w3, neuron=nr), UpBlock(w3, w2, w2, neuron=nr), UpBlock(w2, w1, w1, neuron=nr)
+        self.out_p5, self.out_p4, self.out_p3 = nn.Conv2d(w3, ch_p5, 1), nn.Conv2d(w2, ch_p4, 1), nn.Conv2d(w1, ch_p3, 1)
+
+    # state = (lstm_state | None, {block name: membrane(s)})
+    def forward_seq(self, rc, feats, state=None):
+        p3, p4, p5 = feats
+        lstm_state, m = state if state is not None else (None, {})
+        nm = {}
+        x1, nm["enc1"] = self.enc1.forward_seq(rc, p3, None, m.get("enc1"))
+        d, nm["down1"] = self.down1.forward_seq(rc, x1, m.get("down1"))
+        x2, nm["enc2"] = self.enc2.forward_seq(rc, d, p4, m.get("enc2"))          # cat([down1(x1), p4]) model.py:126
+        d, nm["down2"] = self.down2.forward_seq(rc, x2, m.get("down2"))
+        x3, nm["enc3"] = self.enc3.forward_seq(rc, d, p5, m.get("enc3"))          # model.py:127
+        x, nm["down3"] = self.down3.forward_seq(rc, x3, m.get("down3"))
+        h_all, new_lstm = self.lstm.forward_seq(rc, x, lstm_state)
+        x, nm["bottleneck_conv"] = self.bottleneck_conv.forward_seq(rc, h_all, None, m.get("bottleneck_conv"))
+        d1, nm["up1"] = self.up1.forward_seq(rc, x, x3, m.get("up1"))
+        d2, nm["up2"] = self.up2.forward_seq(rc, d1, x2, m.get("up2"))
+        d3, nm["up3"] = self.up3.forward_seq(rc, d2, x1, m.get("up3"))
+        od = torch.float32 if rc.fp32_outputs else torch.bfloat16
+        mk = lambda conv, x_: ConvBiasFn.apply(x_, conv.weight, conv.bias, dict(store=rc.store, geom=GEOM_1x1, out_dtype=od))
+        outs = (mk(self.out_p3, d3), mk(self.out_p4, d2), mk(self.out_p5, d1))
+        return outs, (new_lstm, nm)
+
+    def forward(self, features, hidden_state=None):
+        """Drop-in: features = 3 NCHW fp32 maps; hidden_state = None | (h, c) | (h, c, membranes)."""
+        p3 = features[0]
+        st = store_for(self, p3.device)
+        st.refresh_operands()
+        state = _unpack_hidden(hidden_state)
+        rc = RunCtx(st, 1, want_state=True, fp32_outputs=True)
+        outs, new_state = self.forward_seq(rc, tuple(_to_nhwc_bf16(f) for f in features), state)
+        return tuple(o.permute(0, 3, 1, 2) for o in outs), _pack_hidden(new_state, self.neuron.kind)
+
+
+def _unpack_hidden(hidden_state):
+    if hidden_state is None:
+        return None
+    h, c = hidden_state[0], hidden_state[1]
+    mem = hidden_state[2] if len(hidden_state) > 2 else {}
+    return (h.permute(0, 2, 3, 1).contiguous(), c.permute(0, 2, 3, 1).contiguous()), mem
+
+
+def _pack_hidden(state, kind):
+    (h, c), mem = state
+    h, c = h.permute(0, 3, 1, 2), c.permute(0, 3, 1, 2)   # NCHW-shaped views, as the reference returns
+    return (h, c) if kind == "silu" else (h, c, mem)
+
+
+# ----------------------------------------------------------------------------------------------
+class YOLOFeatureExtractor(nn.Module):
+    """Frozen multi-scale feature source (reference model.py:74-98).
+
+    The reference wraps a pretrained ultralytics YOLO11m and returns its three raw 144-channel head maps; neither
+    the package nor the weights can exist offline, and the frozen third-party net is out of scope as a kernel
+    target.  This is the documented STAND-IN: a deterministic, frozen, randomly initialised
+    stride-8/16/32 pyramid with the same interface, run with the same tensor-core kernels under no_grad:
+        pack 8x8 patches -> 1x1 conv 192->128 + SiLU -> [P3 = 1x1 ->144]
+        3x3 s2 128->128 + SiLU -> [P4 = 1x1 ->144];  3x3 s2 + SiLU -> [P5 = 1x1 ->144]
+    """
+    WIDTH = 128
+    OUT = 144
+
+    def __init__(self, model_name="yolo11m.pt", freeze=True, seed=1234):
+        super().__init__()
+        self.model_name = model_name
+        g = torch.Generator().manual_seed(seed)
+        w, o = self.WIDTH, self.OUT
+
+        def mk(rows, taps, k):
+            return (torch.randn(rows, taps, k, generator=g) * math.sqrt(2.0 / (taps * k))).to(torch.bfloat16)
+
+        for name, t in (("w_stem", mk(w, 1, 192)), ("w_d4", mk(w, 9, w)), ("w_d5", mk(w, 9, w)),
+                        ("w_p3", mk(o, 1, w)), ("w_p4", mk(o, 1, w)), ("w_p5", mk(o, 1, w))):
+            self.register_buffer(name, t, persistent=False)
+        self.register_buffer("_one", torch.ones(1, w), persistent=False)
+        self.register_buffer("_zero", torch.zeros(1, w), persistent=False)
+
+    def train(self, mode=True):          # stays in eval like the reference (model.py:84-86)
+        self.training = mode
+        return self
+
+    def get_feature_channels(self, dummy_input_shape=(1, 3, 640, 640)):
+        return [self.OUT] * 3
+
+    @torch.no_grad()
+    def forward_seq(self, frames, B, T):
+        """frames fp32 [B,T,3,H,W] (or [B,3,H,W] with T=1) contiguous -> (p3, p4, p5) bf16 NHWC [T*B, ...]."""
+        H, W = frames.shape[-2:]
+        if H % 64 or W % 64:
+            raise NotImplementedError("B200 path needs H, W multiples of 64 (see UpBlock)")
+        x = K.space_to_depth8(frames.contiguous(), B, T)
+        act = lambda y: K.bn_act_fwd(K.ACT_SILU, y, self._one, self._zero, 1)[0]
+        f3 = act(K.conv_fprop(GEOM_1x1, x, self.w_stem, self.WIDTH))
+        f4 = act(K.conv_fprop(GEOM_3x3_S2, f3, self.w_d4, self.WIDTH))
+        f5 = act(K.conv_fprop(GEOM_3x3_S2, f4, self.w_d5, self.WIDTH))
+        bf = torch.bfloat16
+        return (K.conv_fprop(GEOM_1x1, f3, self.w_p3, self.OUT, out_dtype=bf),
+                K.conv_fprop(GEOM_1x1, f4, self.w_p4, self.OUT, out_dtype=bf),
+                K.conv_fprop(GEOM_1x1, f5, self.w_p5, self.OUT, out_dtype=bf))
+
+    def forward(self, x):
+        feats = self.forward_seq(x, x.shape[0], 1)
+        return tuple(_to_nchw_f32(f) for f in feats)
+
+
+# ----------------------------------------------------------------------------------------------
+class YOLOTemporalUNet(nn.Module):
+    """Reference model.py:148-211: frozen extractor -> TemporalUNet -> Detect head.
+
+    Extra (additive) constructor arguments: `neuron` ('lif' default | 'silu' | dict with type/beta/v_th/alpha),
+    so `YOLOTemporalUNet(num_classes, yolo_model_name, use_conv_lstm, hyp)` from main.py:126-131 still works.
+    """
+
+    def __init__(self, num_classes=80, yolo_model_name="yolo11m.pt", use_conv_lstm=True,
+                 hyp: dict = {"box": 7.5, "cls": 0.5, "dfl": 1.5, "reg_max": 16}, neuron=None):
+        super().__init__()
+        from .head import Detect
+        self.args = SimpleNamespace(**hyp)
+        self.nc = num_classes
+        self.feature_extractor = YOLOFeatureExtractor(model_name=yolo_model_name, freeze=True)
+        feature_channels = self.feature_extractor.get_feature_channels()
+        self.temporal_unet = TemporalUNet(feature_channels=feature_channels, use_conv_lstm=use_conv_lstm, neuron=neuron)
+        self.detection_head = Detect(nc=num_classes, ch=feature_channels)
+        strides = torch.tensor([8.0, 16.0, 32.0])
+        self.detection_head.stride = strides
+        self.detection_head.reg_max = self.args.reg_max
+        self.register_buffer("strides", strides, persistent=False)
+        self.model = nn.ModuleList([self.detection_head])
+
+    # ---- fused sequence path -------------------------------------------------------------
+    def forward_sequence(self, frames, hidden_state=None, return_state=False, all_steps=False):
+        """frames [B,T,3,H,W] fp32 on the GPU.  Returns (HeadOut of the LAST step as in train.py:64-66, hidden);
+        `hidden` is None unless return_state (final LSTM state + LIF membranes, for streaming inference)."""
+        B, T = frames.shape[0], frames.shape[1]
+        st = store_for(self, frames.device)
+        st.refresh_operands()
+        feats = self.feature_extractor.forward_seq(frames, B, T)
+        rc = RunCtx(st, T, want_state=return_state)
+        outs, new_state = self.temporal_unet.forward_seq(rc, feats, _unpack_hidden(hidden_state))
+        det = self.detection_head.forward_seq(rc, outs, B, last_only=not all_steps)
+        hidden = _pack_hidden(new_state, self.temporal_unet.neuron.kind) if return_state else None
+        return det, hidden
+
+    # ---- drop-in per-frame path (train.py:66, visualize.py:71) ----------------------------
+    def forward(self, x, hidden_state=None):
+        B = x.shape[0]
+        st = store_for(self, x.device)
+        st.refresh_operands()
+        feats = self.feature_extractor.forward_seq(x, B, 1)
+        rc = RunCtx(st, 1, want_state=True)
+        outs, new_state = self.temporal_unet.forward_seq(rc, feats, _unpack_hidden(hidden_state))
+        det = self.detection_head.forward_seq(rc, outs, B, last_only=True)
+        return det.as_reference(self.detection_head), _pack_hidden(new_state, self.temporal_unet.neuron.kind)
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        """Reference checkpoints carry the frozen YOLO weights under `feature_extractor.model.*`; the stand-in
+        extractor has no persistent state, so those keys are dropped."""
+        sd = {k: v for k, v in state_dict.items() if not k.startswith("feature_extractor.")}
+        return super().load_state_dict(sd, strict=strict, assign=assign)

@@ -39,7 +39,10 @@ class ConvBNActFn(Function):
     def forward(ctx, x0, x1, v_init, weight, gamma, beta, cfg):
         st, geom, T, bn, neuron, training = cfg["store"], cfg["geom"], cfg["T"], cfg["bn"], cfg["neuron"], cfg["training"]
         cout = weight.shape[0]
-        y = K.conv_fprop(geom, x0, st.w_fprop(weight), cout, x1=x1)
+        if geom == K.GEOM_DW3x3:
+            y = K.dw3x3_fprop(x0, st.w_master3(weight).view(9, cout))
+        else:
+            y = K.conv_fprop(geom, x0, st.w_fprop(weight), cout, x1=x1)
         nb, ho, wo, _ = y.shape
         P = (nb // T) * ho * wo
         if training:
@@ -84,6 +87,12 @@ class ConvBNActFn(Function):
             st.grad_done(cfg["bn"].weight)
             st.grad_done(cfg["bn"].bias)
         gw3 = st.grad_view(weight, three_d=True)
+        if geom == K.GEOM_DW3x3:
+            c = weight.shape[0]
+            K.dw3x3_wgrad(x0, dy, gw3.view(9, c))
+            st.grad_done(weight)
+            gx0 = K.dw3x3_dgrad(dy, st.w_master3(weight).view(9, c)) if ctx.needs_input_grad[0] else None
+            return gx0, None, (None if gv0 is None else gv0.view(v_init.shape)), None, None, None, None
         K.conv_wgrad(geom, x0, dy, gw3, w_coff=0)
         if ctx.has_x1:
             K.conv_wgrad(geom, x1, dy, gw3, w_coff=x0.shape[3])

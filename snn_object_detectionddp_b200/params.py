@@ -139,6 +139,9 @@ class ParamStore:
         e = self.by_param[id(p)]
         return e.view3(self.shadow)
 
+    def w_master3(self, p):
+        return self.by_param[id(p)].view3(self.flat_p)
+
     def w_dgrad(self, p):
         e = self.by_param[id(p)]
         n, t, k = e.shape3
