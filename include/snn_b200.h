@@ -109,6 +109,25 @@ int snn_grad_sumsq(const float* g, long long n, double* acc, int zero_first, voi
 int snn_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
                    const float* hp, const double* sumsq, float* gnorm_out, void* stream);
 
+/* ---- Detect decode (ultralytics Detect._inference, reached through model.py:209 in eval mode, and
+ *      v8DetectionLoss.bbox_decode): boxes fp32 [N][4] in pixels (xywh != 0: cx,cy,w,h; else x1,y1,x2,y2) and
+ *      sigmoid class probabilities fp32 [N][nc] (probs may be NULL). ---- */
+int snn_detect_decode(const float* distri, const float* scores, const float* anchors, const float* stride,
+                      int B, int A, int nc, int reg_max, int xywh, float* boxes, float* probs, void* stream);
+
+/* ---- detection-loss tail: replaces the per-anchor part of ultralytics v8DetectionLoss called at train.py:74
+ *      (BCE class loss, CIoU box loss, DFL) given the assigner's targets.  N = B*A anchors (A = anchors per image,
+ *      scale-major), distri fp32 [N][4*reg_max], scores / tscores fp32 [N][nc], anchors fp32 [A][2] (grid units),
+ *      stride fp32 [A], tbox_px fp32 [N][4] (xyxy pixels), fg uint8 [N].
+ *      fwd: sums (double[3], zeroed here) = {sum (1-CIoU)*w, sum BCE, sum DFL*w}.
+ *      bwd: coef (device float[3]) = dL/d sums -> g_distri [N][4*reg_max], g_scores [N][nc] (overwritten). ---- */
+int snn_detect_loss_fwd(const float* distri, const float* scores, const float* anchors, const float* stride,
+                        const float* tbox_px, const float* tscores, const uint8_t* fg, int B, int A, int nc, int reg_max,
+                        double* sums, void* stream);
+int snn_detect_loss_bwd(const float* distri, const float* scores, const float* anchors, const float* stride,
+                        const float* tbox_px, const float* tscores, const uint8_t* fg, int B, int A, int nc, int reg_max,
+                        const float* coef, float* g_distri, float* g_scores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,7 +117,8 @@ class OracleConvBlock(nn.Module):
             return F.silu(z), None
         if v_prev is None:
             v_prev = torch.zeros_like(z)
-        s, v, _ = lif_step(z, v_prev, self.lif["beta"], self.lif["v_th"], self.lif["alpha"])
+        s, v, u = lif_step(z, v_prev, self.lif["beta"], self.lif["v_th"], self.lif["alpha"])
+        self.last_u = u.detach()      # pre-spike membrane, for the flip-rate protocol (|u - theta| < 1e-5)
         return s, v
 
 

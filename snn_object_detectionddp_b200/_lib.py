@@ -36,6 +36,9 @@ _SIGNATURES = {
     "snn_dw3x3_dgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
     "snn_dw3x3_wgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
     "snn_space_to_depth8": [_P, _P, _I, _I, _I, _I, _P],
+    "snn_detect_decode": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "snn_detect_loss_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "snn_detect_loss_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
     "snn_grad_sumsq": [_P, _L, _P, _I, _P],
     "snn_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P],
 }
@@ -84,12 +87,24 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name, *args):
+profile = None    # when set to a list, every call is bracketed by CUDA events: (name, work, ev_start, ev_end)
+
+
+def call(name, *args, work=None):
+    """Invoke one ABI entry point on the current stream.  `work` = ("flop" | "byte", amount) is the algorithmic
+    work of this launch (used by bench.py's live roofline accounting; ignored otherwise)."""
     global launch_count
+    if profile is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise SnnKernelError(f"{name} failed (rc={rc}): {lib().snn_last_error().decode()}")
     launch_count += 1
+    if profile is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        profile.append((name, work, e0, e1))
 
 
 def require_cuda(*tensors):

@@ -61,6 +61,12 @@ int launch_dw3x3_wgrad(const __nv_bfloat16*, const __nv_bfloat16*, float*, int, 
 int launch_s2d8(const float*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 int launch_adamw(float*, const float*, float*, float*, __nv_bfloat16*, long long, const float*, const double*, float*,
                  cudaStream_t);
+int launch_detect_decode(const float*, const float*, const float*, const float*, int, int, int, int, int, float*, float*,
+                         cudaStream_t);
+int launch_detect_loss_fwd(const float*, const float*, const float*, const float*, const float*, const float*, const uint8_t*,
+                           int, int, int, int, double*, cudaStream_t);
+int launch_detect_loss_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const uint8_t*,
+                           int, int, int, int, const float*, float*, float*, cudaStream_t);
 
 }  // namespace snn
 
@@ -152,6 +158,21 @@ int snn_grad_sumsq(const float* g, long long n, double* acc, int zero_first, voi
 int snn_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, long long n, const float* hp,
                    const double* sumsq, float* gnorm_out, void* stream) {
     return launch_adamw(p, g, m, v, (__nv_bfloat16*)shadow, n, hp, sumsq, gnorm_out, ST);
+}
+int snn_detect_decode(const float* distri, const float* scores, const float* anchors, const float* stride, int B, int A,
+                      int nc, int reg_max, int xywh, float* boxes, float* probs, void* stream) {
+    return launch_detect_decode(distri, scores, anchors, stride, B, A, nc, reg_max, xywh, boxes, probs, ST);
+}
+int snn_detect_loss_fwd(const float* distri, const float* scores, const float* anchors, const float* stride,
+                        const float* tbox_px, const float* tscores, const uint8_t* fg, int B, int A, int nc, int reg_max,
+                        double* sums, void* stream) {
+    return launch_detect_loss_fwd(distri, scores, anchors, stride, tbox_px, tscores, fg, B, A, nc, reg_max, sums, ST);
+}
+int snn_detect_loss_bwd(const float* distri, const float* scores, const float* anchors, const float* stride,
+                        const float* tbox_px, const float* tscores, const uint8_t* fg, int B, int A, int nc, int reg_max,
+                        const float* coef, float* g_distri, float* g_scores, void* stream) {
+    return launch_detect_loss_bwd(distri, scores, anchors, stride, tbox_px, tscores, fg, B, A, nc, reg_max, coef, g_distri,
+                                  g_scores, ST);
 }
 
 }  // extern "C"

@@ -1,0 +1,287 @@
+// Detection-loss tail as two fused kernels (forward sums, backward gradients).
+//
+// Replaces the per-anchor part of ultralytics' v8DetectionLoss called at reference train.py:74 (un-vendored third
+// party, restated from its published algorithm -- PARITY UNPINNED, see oracle/detect_oracle.py):
+//   cls : BCE-with-logits(pred_scores, target_scores) summed over [B, A, nc]
+//   box : sum over foreground anchors of (1 - CIoU(pred_box, target_box)) * weight
+//   dfl : sum over foreground anchors of mean_k[ CE(logits_k, tl)*wl + CE(logits_k, tr)*wr ] * weight
+// with pred_box = dist2bbox(softmax-expectation of the 4 x reg_max DFL logits) in grid units,
+// weight = sum_c target_scores.  The assigner that produces (fg, target boxes, target scores) runs before it.
+//
+// One thread per anchor for box/dfl (4*reg_max logits in registers, CIoU differentiated with 4-tangent dual
+// numbers), one thread per score element for BCE.  HBM-bound and tiny (B*A ~ 1e5 anchors): the point is launch
+// count -- 2 launches instead of the ~60 eager kernels of the torch formulation.
+#include "common.cuh"
+
+namespace snn {
+
+constexpr int kRegMax = 16;
+constexpr float kEps = 1e-7f;
+
+struct Dual {  // value + tangents w.r.t. pred (x1, y1, x2, y2)
+    float v, d[4];
+};
+SNN_DEVINL Dual dconst(float c) { return Dual{c, {0.f, 0.f, 0.f, 0.f}}; }
+SNN_DEVINL Dual dvar(float c, int i) { Dual r = dconst(c); r.d[i] = 1.f; return r; }
+SNN_DEVINL Dual operator+(Dual a, Dual b) { Dual r; r.v = a.v + b.v; for (int i = 0; i < 4; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
+SNN_DEVINL Dual operator-(Dual a, Dual b) { Dual r; r.v = a.v - b.v; for (int i = 0; i < 4; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
+SNN_DEVINL Dual operator*(Dual a, Dual b) { Dual r; r.v = a.v * b.v; for (int i = 0; i < 4; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+SNN_DEVINL Dual operator/(Dual a, Dual b) {
+    Dual r; r.v = a.v / b.v;
+    const float ib = 1.f / b.v;
+    for (int i = 0; i < 4; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
+    return r;
+}
+SNN_DEVINL Dual operator+(Dual a, float c) { a.v += c; return a; }
+SNN_DEVINL Dual operator*(Dual a, float c) { a.v *= c; for (int i = 0; i < 4; ++i) a.d[i] *= c; return a; }
+// min/max against a constant; torch.minimum/maximum backward splits the gradient evenly on ties
+SNN_DEVINL Dual dmin(Dual a, float c) {
+    if (a.v < c) return a;
+    if (a.v > c) return dconst(c);
+    Dual r = a * 0.5f; r.v = c; return r;
+}
+SNN_DEVINL Dual dmax(Dual a, float c) {
+    if (a.v > c) return a;
+    if (a.v < c) return dconst(c);
+    Dual r = a * 0.5f; r.v = c; return r;
+}
+SNN_DEVINL Dual dclamp0(Dual a) { return a.v >= 0.f ? a : dconst(0.f); }  // clamp_(0): gradient passes at x >= 0
+SNN_DEVINL Dual datan(Dual a) {
+    Dual r; r.v = atanf(a.v);
+    const float g = 1.f / (1.f + a.v * a.v);
+    for (int i = 0; i < 4; ++i) r.d[i] = a.d[i] * g;
+    return r;
+}
+
+// CIoU(box1 = pred (dual), box2 = target), ultralytics utils/metrics.py bbox_iou(xywh=False, CIoU=True)
+SNN_DEVINL Dual ciou(const Dual b1[4], const float b2[4]) {
+    const Dual w1 = b1[2] - b1[0], h1 = (b1[3] - b1[1]) + kEps;
+    const float w2 = b2[2] - b2[0], h2 = b2[3] - b2[1] + kEps;
+    const Dual iw = dclamp0(dmin(b1[2], b2[2]) - dmax(b1[0], b2[0]));
+    const Dual ih = dclamp0(dmin(b1[3], b2[3]) - dmax(b1[1], b2[1]));
+    const Dual inter = iw * ih;
+    const Dual uni = (w1 * h1 + dconst(w2 * h2)) - inter + kEps;
+    const Dual iou = inter / uni;
+    const Dual cw = dmax(b1[2], b2[2]) - dmin(b1[0], b2[0]);
+    const Dual ch = dmax(b1[3], b2[3]) - dmin(b1[1], b2[1]);
+    const Dual c2 = cw * cw + ch * ch + kEps;
+    const Dual dx = dconst(b2[0] + b2[2]) - b1[0] - b1[2];
+    const Dual dy = dconst(b2[1] + b2[3]) - b1[1] - b1[3];
+    const Dual rho2 = (dx * dx + dy * dy) * 0.25f;
+    const Dual da = dconst(atanf(w2 / h2)) - datan(w1 / h1);
+    const Dual v = (da * da) * 0.40528473456935109f;  // 4 / pi^2
+    const float alpha = v.v / (v.v - iou.v + (1.f + kEps));  // torch.no_grad()
+    return iou - (rho2 / c2 + v * alpha);
+}
+
+struct AnchorTerms {
+    float box, dfl;           // (1 - ciou) * weight ; dfl * weight
+    float gdist_box[4];       // d box / d dist_k
+    float p[4][kRegMax];      // softmax of each side
+    float dist[4];
+    float wl[4];
+    int tl[4];
+    float weight;
+};
+
+// returns false for background anchors
+SNN_DEVINL bool anchor_terms(const float* __restrict__ distri, const float* __restrict__ tscores,
+                             const float* __restrict__ tbox_px, const float* __restrict__ anchors,
+                             const float* __restrict__ stride, const uint8_t* __restrict__ fg, long long n, int a, int nc,
+                             AnchorTerms& o) {
+    if (!fg[n]) return false;
+    float wsum = 0.f;
+    for (int c = 0; c < nc; ++c) wsum += tscores[n * nc + c];
+    o.weight = wsum;
+    const float ax = anchors[2 * a], ay = anchors[2 * a + 1], inv_s = 1.f / stride[a];
+    float tb[4];
+    for (int k = 0; k < 4; ++k) tb[k] = tbox_px[n * 4 + k] * inv_s;  // target_bboxes /= stride_tensor
+    float lse[4];
+    for (int k = 0; k < 4; ++k) {
+        const float4* lp = reinterpret_cast<const float4*>(distri + n * (4 * kRegMax) + k * kRegMax);
+        float l[kRegMax];
+#pragma unroll
+        for (int j = 0; j < kRegMax / 4; ++j) {
+            const float4 t = __ldg(lp + j);
+            l[4 * j] = t.x; l[4 * j + 1] = t.y; l[4 * j + 2] = t.z; l[4 * j + 3] = t.w;
+        }
+        float m = l[0];
+#pragma unroll
+        for (int j = 1; j < kRegMax; ++j) m = fmaxf(m, l[j]);
+        float s = 0.f, e = 0.f;
+#pragma unroll
+        for (int j = 0; j < kRegMax; ++j) { o.p[k][j] = expf(l[j] - m); s += o.p[k][j]; }
+        const float is = 1.f / s;
+#pragma unroll
+        for (int j = 0; j < kRegMax; ++j) { o.p[k][j] *= is; e += o.p[k][j] * (float)j; }
+        o.dist[k] = e;
+        lse[k] = m + logf(s);
+        // DFL target for this side (bbox2dist + DFLoss clamp to reg_max - 1 - 0.01)
+        float t = k == 0 ? ax - tb[0] : (k == 1 ? ay - tb[1] : (k == 2 ? tb[2] - ax : tb[3] - ay));
+        t = fminf(fmaxf(t, 0.f), (float)(kRegMax - 1) - 0.01f);
+        const int tl = (int)t;
+        o.tl[k] = tl;
+        o.wl[k] = (float)(tl + 1) - t;
+        // CE(logits, j) = lse - l[j]
+        float ll = 0.f, lr = 0.f;
+#pragma unroll
+        for (int j = 0; j < kRegMax; ++j) { if (j == tl) ll = l[j]; if (j == tl + 1) lr = l[j]; }
+        lse[k] = (lse[k] - ll) * o.wl[k] + (lse[k] - lr) * (1.f - o.wl[k]);
+    }
+    o.dfl = 0.25f * (lse[0] + lse[1] + lse[2] + lse[3]) * wsum;
+    Dual b1[4] = {dvar(ax - o.dist[0], 0), dvar(ay - o.dist[1], 1), dvar(ax + o.dist[2], 2), dvar(ay + o.dist[3], 3)};
+    const Dual c = ciou(b1, tb);
+    o.box = (1.f - c.v) * wsum;
+    // d box / d dist_k : x1 = ax - d0, y1 = ay - d1, x2 = ax + d2, y2 = ay + d3
+    o.gdist_box[0] = c.d[0] * wsum; o.gdist_box[1] = c.d[1] * wsum;
+    o.gdist_box[2] = -c.d[2] * wsum; o.gdist_box[3] = -c.d[3] * wsum;
+    return true;
+}
+
+SNN_DEVINL float block_sum(float v, float* sh) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[w] = v;
+    __syncthreads();
+    float t = 0.f;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    return t;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(128)
+detect_loss_fwd_kernel(const float* __restrict__ distri, const float* __restrict__ scores, const float* __restrict__ anchors,
+                       const float* __restrict__ stride, const float* __restrict__ tbox_px, const float* __restrict__ tscores,
+                       const uint8_t* __restrict__ fg, long long N, int A, int nc, double* __restrict__ sums) {
+    __shared__ float sh[4];
+    const long long n = (long long)blockIdx.x * 128 + threadIdx.x;
+    float box = 0.f, dfl = 0.f, cls = 0.f;
+    if (n < N) {
+        for (int c = 0; c < nc; ++c) {
+            const float x = scores[n * nc + c], t = tscores[n * nc + c];
+            cls += fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+        }
+        AnchorTerms at;
+        if (anchor_terms(distri, tscores, tbox_px, anchors, stride, fg, n, (int)(n % A), nc, at)) { box = at.box; dfl = at.dfl; }
+    }
+    box = block_sum(box, sh);
+    cls = block_sum(cls, sh);
+    dfl = block_sum(dfl, sh);
+    if (threadIdx.x == 0) {
+        atomicAdd(&sums[0], (double)box);
+        atomicAdd(&sums[1], (double)cls);
+        atomicAdd(&sums[2], (double)dfl);
+    }
+}
+
+// coef[3] (device) = dL/d(sum_box), dL/d(sum_cls), dL/d(sum_dfl)
+__global__ void __launch_bounds__(128)
+detect_loss_bwd_kernel(const float* __restrict__ distri, const float* __restrict__ scores, const float* __restrict__ anchors,
+                       const float* __restrict__ stride, const float* __restrict__ tbox_px, const float* __restrict__ tscores,
+                       const uint8_t* __restrict__ fg, long long N, int A, int nc, const float* __restrict__ coef,
+                       float* __restrict__ g_distri, float* __restrict__ g_scores) {
+    const long long n = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (n >= N) return;
+    const float kb = coef[0], kc = coef[1], kd = coef[2];
+    for (int c = 0; c < nc; ++c) {
+        const float x = scores[n * nc + c], t = tscores[n * nc + c];
+        g_scores[n * nc + c] = kc * (1.f / (1.f + expf(-x)) - t);
+    }
+    float4* gp = reinterpret_cast<float4*>(g_distri + n * (4 * kRegMax));
+    AnchorTerms at;
+    if (!anchor_terms(distri, tscores, tbox_px, anchors, stride, fg, n, (int)(n % A), nc, at)) {
+#pragma unroll
+        for (int j = 0; j < kRegMax; ++j) gp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float g[kRegMax];
+        const float gb = kb * at.gdist_box[k];      // d[(1 - ciou) * w] / d dist_k
+        const float kdw = kd * 0.25f * at.weight;
+#pragma unroll
+        for (int j = 0; j < kRegMax; ++j) {
+            const float p = at.p[k][j];
+            float v = gb * p * ((float)j - at.dist[k]) + kdw * p;
+            if (j == at.tl[k]) v -= kdw * at.wl[k];
+            if (j == at.tl[k] + 1) v -= kdw * (1.f - at.wl[k]);
+            g[j] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < kRegMax / 4; ++j) gp[k * 4 + j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+    }
+}
+
+// Detect._inference / bbox_decode: boxes from the DFL logits (softmax expectation -> dist2bbox -> * stride) and sigmoid
+// class scores.  xywh != 0: (cx, cy, w, h) as the eval-mode head returns (visualize.py:71-78 feeds it to NMS);
+// xywh == 0: (x1, y1, x2, y2) as the assigner wants.  One thread per anchor.
+__global__ void __launch_bounds__(128)
+detect_decode_kernel(const float* __restrict__ distri, const float* __restrict__ scores, const float* __restrict__ anchors,
+                     const float* __restrict__ stride, long long N, int A, int nc, int xywh, float* __restrict__ boxes,
+                     float* __restrict__ probs) {
+    const long long n = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (n >= N) return;
+    const int a = (int)(n % A);
+    float dist[4];
+    for (int k = 0; k < 4; ++k) {
+        const float4* lp = reinterpret_cast<const float4*>(distri + n * (4 * kRegMax) + k * kRegMax);
+        float l[kRegMax];
+#pragma unroll
+        for (int j = 0; j < kRegMax / 4; ++j) {
+            const float4 t = __ldg(lp + j);
+            l[4 * j] = t.x; l[4 * j + 1] = t.y; l[4 * j + 2] = t.z; l[4 * j + 3] = t.w;
+        }
+        float m = l[0];
+#pragma unroll
+        for (int j = 1; j < kRegMax; ++j) m = fmaxf(m, l[j]);
+        float s = 0.f, e = 0.f;
+#pragma unroll
+        for (int j = 0; j < kRegMax; ++j) { const float p = expf(l[j] - m); s += p; e += p * (float)j; }
+        dist[k] = e / s;
+    }
+    const float ax = anchors[2 * a], ay = anchors[2 * a + 1], st = stride[a];
+    const float x1 = ax - dist[0], y1 = ay - dist[1], x2 = ax + dist[2], y2 = ay + dist[3];
+    float4 o;
+    if (xywh) o = make_float4((x1 + x2) * 0.5f * st, (y1 + y2) * 0.5f * st, (x2 - x1) * st, (y2 - y1) * st);
+    else o = make_float4(x1 * st, y1 * st, x2 * st, y2 * st);
+    reinterpret_cast<float4*>(boxes)[n] = o;
+    if (probs)
+        for (int c = 0; c < nc; ++c) probs[n * nc + c] = 1.f / (1.f + expf(-scores[n * nc + c]));
+}
+
+int launch_detect_decode(const float* distri, const float* scores, const float* anchors, const float* stride, int B, int A,
+                         int nc, int reg_max, int xywh, float* boxes, float* probs, cudaStream_t st) {
+    SNN_REQUIRE(reg_max == kRegMax, "detect_decode: reg_max must be %d (got %d)", kRegMax, reg_max);
+    const long long N = (long long)B * A;
+    if (N == 0) return 0;
+    detect_decode_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(distri, scores, anchors, stride, N, A, nc, xywh, boxes, probs);
+    return check_cuda(cudaGetLastError(), "detect_decode_kernel");
+}
+
+int launch_detect_loss_fwd(const float* distri, const float* scores, const float* anchors, const float* stride,
+                           const float* tbox_px, const float* tscores, const uint8_t* fg, int B, int A, int nc, int reg_max,
+                           double* sums, cudaStream_t st) {
+    SNN_REQUIRE(reg_max == kRegMax, "detect_loss: reg_max must be %d (got %d)", kRegMax, reg_max);
+    SNN_CUDA_OK(cudaMemsetAsync(sums, 0, 3 * sizeof(double), st));
+    const long long N = (long long)B * A;
+    if (N == 0) return 0;
+    detect_loss_fwd_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(distri, scores, anchors, stride, tbox_px, tscores, fg,
+                                                                        N, A, nc, sums);
+    return check_cuda(cudaGetLastError(), "detect_loss_fwd_kernel");
+}
+
+int launch_detect_loss_bwd(const float* distri, const float* scores, const float* anchors, const float* stride,
+                           const float* tbox_px, const float* tscores, const uint8_t* fg, int B, int A, int nc, int reg_max,
+                           const float* coef, float* g_distri, float* g_scores, cudaStream_t st) {
+    SNN_REQUIRE(reg_max == kRegMax, "detect_loss: reg_max must be %d (got %d)", kRegMax, reg_max);
+    const long long N = (long long)B * A;
+    if (N == 0) return 0;
+    detect_loss_bwd_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(distri, scores, anchors, stride, tbox_px, tscores, fg,
+                                                                        N, A, nc, coef, g_distri, g_scores);
+    return check_cuda(cudaGetLastError(), "detect_loss_bwd_kernel");
+}
+
+}  // namespace snn

@@ -101,7 +101,8 @@ int launch_nhwc_to_nchw(const void* in, int in_bf16, float* out, int NB, int C, 
 // ConvLSTM gate math (reference model.py:67-69), NHWC: gates fp32 [P][4*Ch] (i|f|g|o), state fp32 [P][Ch]
 // forward also emits h as bf16 (operand of the next recurrent conv / bottleneck conv)
 // ------------------------------------------------------------------------------------------
-SNN_DEVINL float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// accurate expf (not __expf): h feeds a bf16-rounded conv operand, ulp-level differences flip roundings downstream
+SNN_DEVINL float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 __global__ void __launch_bounds__(256)
 lstm_gates_fwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, float* __restrict__ c_next,

@@ -29,6 +29,15 @@ def out_hw(geom, h, w):
     return h, w
 
 
+def _conv_flops(geom, nb, h, w, cin, cout):
+    """Algorithmic flops of one pass (SURVEY.md 8d): 2 * output pixels * Cout * Cin * taps, padding not counted;
+    (h, w) are the conv INPUT dims (transposed conv: every input pixel feeds 4 taps)."""
+    ho, wo = out_hw(geom, h, w)
+    if geom == GEOM_T2x2_S2:
+        return 2.0 * nb * h * w * cout * cin * 4
+    return 2.0 * nb * ho * wo * cout * cin * GEOM_TAPS[geom]
+
+
 def conv_fprop(geom, x0, w_bf16, cout, x1=None, bias=None, out=None, out_dtype=torch.float32, w_coff=0, w_row_off=0,
                accumulate=False):
     """out[NB,Ho,Wo,cout] = conv(cat([x0,x1],C), W[w_row_off:w_row_off+cout, :, w_coff:...]) (+bias)."""
@@ -47,7 +56,7 @@ def conv_fprop(geom, x0, w_bf16, cout, x1=None, bias=None, out=None, out_dtype=t
     assert w_coff + c0 + c1 <= wk and w_row_off + cout <= rows
     call("snn_conv_fprop", geom, nb, h, w, ptr(x0), c0, _nhwc_ld(x0), ptr(x1), c1, 0 if x1 is None else _nhwc_ld(x1),
          ptr(w_bf16), rows, wk, w_coff, cout, w_row_off, ptr(bias), ptr(out), int(out.dtype == torch.float32),
-         _nhwc_ld(out), 0, int(accumulate), stream_ptr())
+         _nhwc_ld(out), 0, int(accumulate), stream_ptr(), work=("flop", _conv_flops(geom, nb, h, w, c0 + c1, cout)))
     return out
 
 
@@ -63,7 +72,8 @@ def conv_dgrad(geom, dy, wt_bf16, in_hw, ci, ci_off=0, out=None, out_dtype=torch
     if out is None:
         out = torch.empty((nb, h, w, ci), device=dy.device, dtype=out_dtype)
     call("snn_conv_dgrad", geom, nb, h, w, ptr(dy), cout, _nhwc_ld(dy), ptr(wt_bf16), rows, ci_off, ci, ptr(out),
-         int(out.dtype == torch.float32), _nhwc_ld(out), 0, int(accumulate), stream_ptr())
+         int(out.dtype == torch.float32), _nhwc_ld(out), 0, int(accumulate), stream_ptr(),
+         work=("flop", _conv_flops(geom, nb, h, w, ci, cout)))
     return out
 
 
@@ -77,7 +87,7 @@ def conv_wgrad(geom, x, dy, dw, w_coff=0):
     assert rows == cout and taps == GEOM_TAPS[geom] and w_coff + ci <= wk
     assert dw.dtype == torch.float32 and dw.is_contiguous() and x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16
     call("snn_conv_wgrad", geom, nb, h, w, ptr(x), ci, _nhwc_ld(x), ptr(dy), cout, _nhwc_ld(dy), ptr(dw), wk, w_coff,
-         stream_ptr())
+         stream_ptr(), work=("flop", _conv_flops(geom, nb, h, w, ci, cout)))
     return dw
 
 
@@ -103,7 +113,7 @@ def bn_stats(y, T):
     c = y.shape[-1]
     p = y.numel() // (T * c)
     sums = torch.empty((T, 2, c), device=y.device, dtype=torch.float64)
-    call("snn_bn_stats", ptr(y), ptr(sums), T, p, c, stream_ptr())
+    call("snn_bn_stats", ptr(y), ptr(sums), T, p, c, stream_ptr(), work=("byte", 4.0 * y.numel()))
     return sums
 
 
@@ -129,8 +139,11 @@ def bn_act_fwd(act, y, scale, shift, T, v_init=None, want_mask=True, want_v_fina
         ss = 0
     if T == 1:
         ss = 0
+    # algorithmic bytes per neuron-timestep: 4 (y fp32) + 2 (spike bf16) + 1/8 (packed mask)
+    nbytes = y.numel() * (6.0 + (0.125 if mask is not None else 0.0))
+    nbytes += (0 if v_init is None else 4.0 * n_per_t) + (0 if v_final is None else 4.0 * n_per_t)
     call("snn_bn_act_fwd", act, ptr(y), ptr(scale), ptr(shift), ptr(v_init), ptr(out), ptr(mask), ptr(v_final), T, n_per_t,
-         c, ss, float(beta), float(theta), stream_ptr())
+         c, ss, float(beta), float(theta), stream_ptr(), work=("byte", nbytes))
     return out, mask, v_final
 
 
@@ -147,9 +160,11 @@ def bn_act_bwd(act, training, y, scale, shift, mean, invstd, gs, T, v_init=None,
     gv_init = torch.empty((p * c,), device=dev, dtype=torch.float32) if want_gv_init else None
     ss = 0 if (T == 1 or scale.shape[0] == 1) else c
     assert gs.dtype == torch.bfloat16 and gs.is_contiguous()
+    # algorithmic bytes per neuron-timestep: 2 (gs bf16) + 4 (y fp32, membrane recomputed) + 4 (gx fp32) | 2 (dy bf16)
+    nbytes = y.numel() * (10.0 if training else 8.0)
     call("snn_bn_act_bwd", act, int(training), ptr(y), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(v_init), ptr(gs),
          ptr(gv_final), ptr(gx), ptr(dy), ptr(gv_init), ptr(red), T, p, c, ss, float(beta), float(theta), float(alpha),
-         stream_ptr())
+         stream_ptr(), work=("byte", nbytes))
     return gx, dy, gv_init, red
 
 
@@ -159,7 +174,7 @@ def bn_bwd_dx(red, gamma, gx, y, scale, mean, invstd, dgamma, dbeta, T):
     coef = torch.empty((T, 2, c), device=y.device, dtype=torch.float32)
     dy = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
     call("snn_bn_bwd_dx", ptr(red), ptr(gamma), ptr(gx), ptr(y), ptr(scale), ptr(mean), ptr(invstd), ptr(coef), ptr(dgamma),
-         ptr(dbeta), ptr(dy), T, p, c, stream_ptr())
+         ptr(dbeta), ptr(dy), T, p, c, stream_ptr(), work=("byte", 10.0 * y.numel()))
     return dy
 
 
@@ -215,12 +230,12 @@ def colsum_accumulate(dy, acc):
 
 
 def grad_sumsq(g, acc, zero_first=True):
-    call("snn_grad_sumsq", ptr(g), g.numel(), ptr(acc), int(zero_first), stream_ptr())
+    call("snn_grad_sumsq", ptr(g), g.numel(), ptr(acc), int(zero_first), stream_ptr(), work=("byte", 4.0 * g.numel()))
 
 
 def adamw_step(p, g, m, v, shadow, hp, sumsq, gnorm_out=None):
     call("snn_adamw_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), p.numel(), ptr(hp), ptr(sumsq), ptr(gnorm_out),
-         stream_ptr())
+         stream_ptr(), work=("byte", (28.0 + (2.0 if shadow is not None else 0.0)) * p.numel()))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -261,3 +276,39 @@ def space_to_depth8(frames, B, T):
     out = torch.empty((T * B, h // 8, w // 8, 192), device=frames.device, dtype=torch.bfloat16)
     call("snn_space_to_depth8", ptr(frames), ptr(out), B, T, h, w, stream_ptr())
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Detect decode + detection-loss tail
+# ---------------------------------------------------------------------------------------------
+def detect_decode(distri, scores, anchors, stride, xywh, want_probs=True):
+    """distri fp32 [B,A,4*reg_max], scores fp32 [B,A,nc] -> boxes [B,A,4] (pixels), probs [B,A,nc] | None."""
+    require_cuda(distri, scores, anchors, stride)
+    b, a, r4 = distri.shape
+    nc = scores.shape[2]
+    assert distri.is_contiguous() and scores.is_contiguous() and distri.dtype == torch.float32 and scores.dtype == torch.float32
+    boxes = torch.empty((b, a, 4), device=distri.device, dtype=torch.float32)
+    probs = torch.empty((b, a, nc), device=distri.device, dtype=torch.float32) if want_probs else None
+    call("snn_detect_decode", ptr(distri), ptr(scores), ptr(anchors), ptr(stride), b, a, nc, r4 // 4, int(xywh), ptr(boxes),
+         ptr(probs), stream_ptr())
+    return boxes, probs
+
+
+def detect_loss_fwd(distri, scores, anchors, stride, tbox_px, tscores, fg):
+    b, a, r4 = distri.shape
+    sums = torch.empty(3, device=distri.device, dtype=torch.float64)
+    for t in (distri, scores, anchors, stride, tbox_px, tscores, fg):
+        assert t.is_contiguous()
+    assert fg.dtype == torch.uint8 and tscores.dtype == torch.float32 and tbox_px.dtype == torch.float32
+    call("snn_detect_loss_fwd", ptr(distri), ptr(scores), ptr(anchors), ptr(stride), ptr(tbox_px), ptr(tscores), ptr(fg), b, a,
+         scores.shape[2], r4 // 4, ptr(sums), stream_ptr())
+    return sums
+
+
+def detect_loss_bwd(distri, scores, anchors, stride, tbox_px, tscores, fg, coef):
+    b, a, r4 = distri.shape
+    g_distri, g_scores = torch.empty_like(distri), torch.empty_like(scores)
+    assert coef.dtype == torch.float32 and coef.is_contiguous() and coef.numel() == 3
+    call("snn_detect_loss_bwd", ptr(distri), ptr(scores), ptr(anchors), ptr(stride), ptr(tbox_px), ptr(tscores), ptr(fg), b, a,
+         scores.shape[2], r4 // 4, ptr(coef), ptr(g_distri), ptr(g_scores), stream_ptr())
+    return g_distri, g_scores

@@ -33,6 +33,7 @@ class RunCtx:
 
     def __init__(self, store, T, want_state=False, want_mask=False, fp32_outputs=False):
         self.store, self.T, self.want_state, self.want_mask, self.fp32_outputs = store, T, want_state, want_mask, fp32_outputs
+        self.record = None      # optional dict: ConvBlock name -> its spike / activation output (tests, spike-rate probes)
 
 
 def _to_nhwc_bf16(x):
@@ -83,6 +84,8 @@ class ConvBlock(nn.Module):
         out, v = ConvBNActFn.apply(x0, x1, v_init, self.conv.weight, self.bn.weight, self.bn.bias, cfg)
         if rc.want_mask:
             self.last_mask = cfg.get("last_mask")
+        if rc.record is not None:
+            rc.record[getattr(self, "_snn_name", str(id(self)))] = out.detach()
         return out, v
 
     def forward(self, x):
@@ -183,6 +186,9 @@ class TemporalUNet(nn.Module):
         self.bottleneck_conv = ConvBlock(w4, w4, neuron=nr)
         self.up1, self.up2, self.up3 = UpBlock(w4, w3, w3, neuron=nr), UpBlock(w3, w2, w2, neuron=nr), UpBlock(w2, w1, w1, neuron=nr)
         self.out_p5, self.out_p4, self.out_p3 = nn.Conv2d(w3, ch_p5, 1), nn.Conv2d(w2, ch_p4, 1), nn.Conv2d(w1, ch_p3, 1)
+        for name, m in self.named_modules():
+            if isinstance(m, ConvBlock):
+                m._snn_name = name
 
     # state = (lstm_state | None, {block name: membrane(s)})
     def forward_seq(self, rc, feats, state=None):

@@ -1,0 +1,105 @@
+"""Training step of the reference (train.py:48-104, 155-169) on the B200 path.
+
+    zero_grad -> T-step unroll with state carry (fused: one launch sequence per LAYER over the folded T*B batch)
+    -> v8DetectionLoss on the LAST step -> backward -> [DDP bucketed all-reduce, overlapped] ->
+    clip_grad_norm_(10) + AdamW fused over the flat buffers -> OneCycleLR advance
+
+Nothing in a step reads device memory from the host: the OneCycle schedule (lr and cycled beta1, torch defaults
+div_factor 25 / final_div_factor 1e4 / pct_start 0.3 / cos) is tabulated once into a device array the optimizer kernel
+indexes, and loss values are returned as device tensors (the caller decides when to ``.item()``; the reference syncs
+3-5 times per batch, train.py:81-100).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+from .ddp import GradBucketer, broadcast_module_state
+from .loss import pad_targets, v8DetectionLoss
+from .params import store_for
+
+
+def one_cycle_table(total_steps, max_lr, weight_decay, pct_start=0.3, div_factor=25.0, final_div_factor=1e4,
+                    base_momentum=0.85, max_momentum=0.95, beta2=0.999, eps=1e-8, max_norm=10.0):
+    """Row k = hyper-parameters of optimizer step k (0-based): torch.optim.lr_scheduler.OneCycleLR(anneal 'cos',
+    cycle_momentum) driving torch.optim.AdamW, as configured at reference train.py:156-169.
+    Columns: lr, beta1, beta2, eps, weight_decay, 1-beta1^(k+1), 1-beta2^(k+1), max_norm."""
+    initial_lr, min_lr = max_lr / div_factor, max_lr / div_factor / final_div_factor
+    end1, end2 = float(pct_start * total_steps) - 1.0, float(total_steps - 1)
+
+    def cos_anneal(start, end, pct):
+        return end + (start - end) / 2.0 * (math.cos(math.pi * pct) + 1.0)
+
+    rows = []
+    for k in range(total_steps):
+        if k <= end1:
+            pct = k / end1 if end1 > 0 else 1.0
+            lr, b1 = cos_anneal(initial_lr, max_lr, pct), cos_anneal(max_momentum, base_momentum, pct)
+        else:
+            pct = (k - end1) / (end2 - end1) if end2 > end1 else 1.0
+            lr, b1 = cos_anneal(max_lr, min_lr, pct), cos_anneal(base_momentum, max_momentum, pct)
+        rows.append([lr, b1, beta2, eps, weight_decay, 1.0 - b1 ** (k + 1), 1.0 - beta2 ** (k + 1), max_norm])
+    return torch.tensor(rows, dtype=torch.float64)
+
+
+class Trainer:
+    def __init__(self, model, max_lr=1e-4, weight_decay=5e-4, total_steps=1000, max_norm=10.0, device=None,
+                 process_group=None, bucket_mb=32):
+        self.model = model
+        self.device = torch.device(device if device is not None else "cuda")
+        model.to(self.device)
+        self.store = store_for(model, self.device)
+        self.loss_fn = v8DetectionLoss(model)
+        self.hp = one_cycle_table(total_steps, max_lr, weight_decay, max_norm=max_norm).float().to(self.device)
+        self.total_steps = total_steps
+        self.step_idx = 0
+        self._sumsq = torch.zeros(1, device=self.device, dtype=torch.float64)
+        self.grad_norm = torch.zeros(1, device=self.device, dtype=torch.float32)
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.bucketer = None
+        if self.world > 1:
+            broadcast_module_state(model, self.store.flat_p, process_group)
+            self.store._versions = None       # masters changed under the bf16 operand copies
+            spans = [(e.offset, self._padded(e)) for e in self.store.entries]
+            self.bucketer = GradBucketer(self.store.flat_g, spans, bucket_mb << 20, process_group)
+            index = {id(e): i for i, e in enumerate(self.store.entries)}
+            self.store.grad_ready_hook = lambda e: self.bucketer.entry_ready(index[id(e)])
+
+    def _padded(self, e):
+        i = self.store.entries.index(e)
+        nxt = self.store.entries[i + 1].offset if i + 1 < len(self.store.entries) else self.store.total
+        return nxt - e.offset
+
+    # ------------------------------------------------------------------------------------------
+    def prepare_batch(self, labels, batch_size):
+        """Host-side label padding ([M,6] collate layout, train.py:27-37) -> dict accepted by the loss."""
+        return {"padded": pad_targets(labels, batch_size)}
+
+    def train_step(self, frames, batch):
+        """frames fp32 [B,T,3,H,W] on the device; batch = {'batch_idx','cls','bboxes'} (train.py:68-72) or
+        prepare_batch(...).  Returns (loss*B [3], loss.detach() [3]) as DEVICE tensors."""
+        model, st = self.model, self.store
+        model.train()
+        st.zero_grad()
+        if self.bucketer is not None:
+            self.bucketer.begin_step()
+        det, _ = model.forward_sequence(frames)
+        loss, items = self.loss_fn(det, batch)
+        loss.sum().backward()
+        if self.bucketer is not None:
+            self.bucketer.finish()
+        self.optimizer_step()
+        return loss.detach(), items
+
+    def optimizer_step(self):
+        st = self.store
+        K.grad_sumsq(st.flat_g, self._sumsq)
+        row = self.hp[min(self.step_idx, self.total_steps - 1)]
+        K.adamw_step(st.flat_p, st.flat_g, st.flat_m, st.flat_v, st.shadow, row, self._sumsq, self.grad_norm)
+        st.opt_epoch += 1
+        self.step_idx += 1
+
+    def lr(self):
+        return float(self.hp[min(self.step_idx, self.total_steps - 1), 0])

@@ -7,6 +7,9 @@ stubbed) and records inputs/outputs/gradients of the reference's own classes:
 
 * ref_blocks.pt   -- narrow ConvBlock / DownBlock / UpBlock / ConvLSTM2d instances, weights included
                      (reference model.py:9-71), train- and eval-mode BN, forward + backward.
+* ref_unet_seq_256.pt -- same as ref_unet_seq.pt at the geometry of BASELINE.json configs[0] (B=2, T=4, feature
+                     maps 32/16/8 of a 256x256 frame); BatchNorm groups are >= 32 samples there, so bf16-operand
+                     kernels can be compared against it at a meaningful tolerance.
 * ref_unet_seq.pt -- full-width TemporalUNet([144,144,144]) (model.py:100-146) initialised with
                      initialize_weights (weight_initialization.py:8-56) under torch.manual_seed(42),
                      T=3 unroll with ConvLSTM state carry (train.py:62-66), loss on the last step,
@@ -102,23 +105,22 @@ def blocks(ref):
     print("ref_blocks.pt", os.path.getsize(os.path.join(OUT, "ref_blocks.pt")))
 
 
-def unet_seq(ref, wi):
+def unet_seq(ref, wi, name="ref_unet_seq.pt", B=2, T=3, hw=(8, 4, 2), feat_seed=4242, store_outs=True):
     torch.manual_seed(42)
     net = ref.TemporalUNet([144, 144, 144], use_conv_lstm=True)
     net.apply(wi.initialize_weights)
     net.train()
     init_ck = {k: (float(v.double().sum()), float(v.double().abs().sum())) for k, v in net.state_dict().items()
                if v.dtype.is_floating_point}
-    g = torch.Generator().manual_seed(4242)
-    B, T = 2, 3
-    feats = [[torch.randn(B, 144, 8, 8, generator=g), torch.randn(B, 144, 4, 4, generator=g),
-              torch.randn(B, 144, 2, 2, generator=g)] for _ in range(T)]
+    g = torch.Generator().manual_seed(feat_seed)
+    feats = [[torch.randn(B, 144, hw[0], hw[0], generator=g), torch.randn(B, 144, hw[1], hw[1], generator=g),
+              torch.randn(B, 144, hw[2], hw[2], generator=g)] for _ in range(T)]
     hid = None
     for f in feats:
         outs, hid = net(f, hid)
     loss = sum((o ** 2).mean() for o in outs)
     loss.backward()
-    fx = dict(B=B, T=T, feat_seed=4242, init_seed=42, init_checksums=init_ck,
+    fx = dict(B=B, T=T, hw=hw, feat_seed=feat_seed, init_seed=42, init_checksums=init_ck,
               outs=[o.detach().clone() for o in outs], h=hid[0].detach().clone(), c=hid[1].detach().clone(),
               loss=float(loss),
               grad_norms={k: float(p.grad.double().norm()) for k, p in net.named_parameters()},
@@ -129,8 +131,8 @@ def unet_seq(ref, wi):
     with torch.no_grad():
         eo, _ = net(feats[0], None)
     fx["eval_outs"] = [o.clone() for o in eo]
-    torch.save(fx, os.path.join(OUT, "ref_unet_seq.pt"))
-    print("ref_unet_seq.pt", os.path.getsize(os.path.join(OUT, "ref_unet_seq.pt")))
+    torch.save(fx, os.path.join(OUT, name))
+    print(name, os.path.getsize(os.path.join(OUT, name)))
 
 
 if __name__ == "__main__":
@@ -138,3 +140,5 @@ if __name__ == "__main__":
     ref, wi = load_reference()
     blocks(ref)
     unet_seq(ref, wi)
+    # BASELINE.json configs[0] geometry: B=2, T=4, 256x256 frames -> feature maps 32/16/8, bottleneck 4x4
+    unet_seq(ref, wi, name="ref_unet_seq_256.pt", B=2, T=4, hw=(32, 16, 8), feat_seed=256256)

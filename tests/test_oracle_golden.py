@@ -83,9 +83,10 @@ def test_convlstm_matches_reference(golden_dir):
         _close(p.grad, fx["grads"][k], 1e-4)
 
 
-def test_unet_sequence_matches_reference(golden_dir):
-    """Seeded init (weight_initialization.py:8-56) + T=3 unroll (train.py:62-66) of the full-width net."""
-    fx = _load(golden_dir, "ref_unet_seq.pt")
+@pytest.mark.parametrize("fixture", ["ref_unet_seq.pt", "ref_unet_seq_256.pt"])
+def test_unet_sequence_matches_reference(golden_dir, fixture):
+    """Seeded init (weight_initialization.py:8-56) + T-step unroll (train.py:62-66) of the full-width net."""
+    fx = _load(golden_dir, fixture)
     torch.manual_seed(fx["init_seed"])
     net = O.OracleTemporalUNet([144, 144, 144], neuron="silu")
     net.apply(O.initialize_weights_oracle)
@@ -97,8 +98,7 @@ def test_unet_sequence_matches_reference(golden_dir):
             assert abs(float(v.double().abs().sum()) - a) <= 1e-9 * max(1.0, abs(a)), k
     g = torch.Generator().manual_seed(fx["feat_seed"])
     B, T = fx["B"], fx["T"]
-    feats = [[torch.randn(B, 144, 8, 8, generator=g), torch.randn(B, 144, 4, 4, generator=g),
-              torch.randn(B, 144, 2, 2, generator=g)] for _ in range(T)]
+    feats = [[torch.randn(B, 144, h, h, generator=g) for h in fx["hw"]] for _ in range(T)]
     outs, hid = O.run_sequence(net, feats)
     for o, r in zip(outs, fx["outs"]):
         _close(o, r, 1e-4)
