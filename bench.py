@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event accounting")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph")
     ap.add_argument("--ref-batch", type=int, default=2, help="sequences per step of the CPU arm (bounded sample)")
     return ap.parse_args()
 
@@ -172,6 +173,17 @@ def summarize_profile(records, steps, pk):
         a["calls"] += 1
         if work:
             a[work[0]] += work[1]
+    shapes = {}
+    for name, work, e0, e1 in records:
+        if work and len(work) > 2:
+            a = shapes.setdefault((name, work[2]), dict(ms=0.0, calls=0, amount=0.0, kind=work[0]))
+            a["ms"] += e0.elapsed_time(e1); a["calls"] += 1; a["amount"] += work[1]
+    by_shape = []
+    for (name, tag), a in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:40]:
+        rate = a["amount"] / (a["ms"] * 1e-3)
+        by_shape.append({"kernel": name, "shape": tag, "ms_per_step": round(a["ms"] / steps, 4), "calls_per_step": a["calls"] / steps,
+                         ("tflops" if a["kind"] == "flop" else "gbs"): round(rate / (1e12 if a["kind"] == "flop" else 1e9), 1)})
+    summarize_profile.by_shape = by_shape
     out = {}
     for name, a in agg.items():
         d = dict(ms_per_step=a["ms"] / steps, calls_per_step=a["calls"] / steps)
@@ -210,7 +222,10 @@ def run_ours(args):
     trainer = Trainer(model, max_lr=MAX_LR, weight_decay=WEIGHT_DECAY, total_steps=1000, device=dev)
     frames_cpu, labels_cpu = synthetic_batch(B, T, HW, HW, nc=NUM_CLASSES, seed=42 + rank)
     frames = frames_cpu.to(dev)
-    batch_dev = {"padded": tuple(t.to(dev) for t in trainer.prepare_batch(labels_cpu, B)["padded"])}
+    MAXB = 8                                              # synthetic labels: 0-7 boxes per sample
+    batch_dev = {"padded": tuple(t.to(dev) for t in trainer.prepare_batch(labels_cpu, B, max_boxes=MAXB)["padded"])}
+    graphed = world == 1 and not args.no_graph
+    step_fn = trainer.train_step_graphed if graphed else trainer.train_step
 
     def barrier():
         torch.cuda.synchronize()
@@ -219,23 +234,30 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ----------------
-    for _ in range(args.warmup):
-        trainer.train_step(frames, batch_dev)
+    launches0 = _lib.launch_count
+    for _ in range(max(args.warmup, 3)):                  # >= 3: two eager steps, then the graph capture + first replay
+        step_fn(frames, batch_dev)
     barrier()
+    calls_per_step = None
+    if graphed:                                           # ABI calls recorded into the graph = launches per replay
+        l0 = _lib.launch_count
+        trainer.train_step(frames, batch_dev)
+        calls_per_step = _lib.launch_count - l0
+        barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    records = None if args.no_profile else []
+    records = None if (args.no_profile or graphed) else []
     _lib.profile = records
     launches0 = _lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        loss, items = trainer.train_step(frames, batch_dev)
+        loss, items = step_fn(frames, batch_dev)
     ev1.record()
     barrier()
     _lib.profile = None
-    launches = _lib.launch_count - launches0
+    launches = calls_per_step * args.steps if graphed else _lib.launch_count - launches0
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -247,7 +269,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         pin = [frames_cpu.clone().pin_memory() for _ in range(2)]
-        lab_pin = [tuple(t.pin_memory() for t in trainer.prepare_batch(labels_cpu, B)["padded"]) for _ in range(2)]
+        lab_pin = [tuple(t.pin_memory() for t in trainer.prepare_batch(labels_cpu, B, max_boxes=MAXB)["padded"]) for _ in range(2)]
         loss_host = torch.zeros(args.steps + args.warmup, 3).pin_memory()
         copy_stream = torch.cuda.Stream(dev)
         main_stream = torch.cuda.current_stream(dev)
@@ -272,7 +294,7 @@ def run_ours(args):
                 if i + 1 < n:
                     h2d(i + 1)                      # prefetch the next batch while this step computes
                 main_stream.wait_event(ready[s])
-                _, it = trainer.train_step(dbuf[s], {"padded": lbuf[s]})
+                _, it = step_fn(dbuf[s], {"padded": lbuf[s]})
                 consumed[s].record(main_stream)
                 loss_host[base + i].copy_(it, non_blocking=True)     # D2H read of the step's result
 
@@ -291,10 +313,26 @@ def run_ours(args):
         h2d_bytes = frames_cpu.numel() * frames_cpu.element_size() + sum(t.numel() * t.element_size() for t in lab_pin[0])
         e2e = {"value": world * B * args.steps / (float(ems) * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": 12, "ms_per_step": float(ems) / args.steps,
-               "api": "Trainer.train_step on double-buffered pinned host frames (fp32 [B,T,3,H,W]) + padded labels"}
+               "api": ("Trainer.train_step_graphed" if graphed else "Trainer.train_step")
+                      + " on double-buffered pinned host frames (fp32 [B,T,3,H,W]) + padded labels"}
 
     # ---------------- per-kernel accounting + roofline of the dominant kernel ----------------
     roofline, kernels_summary = None, None
+    if graphed and not args.no_profile:
+        # a replayed graph has no per-launch events: time the SAME kernels in an instrumented eager pass of the same
+        # K steps right after the timed region (kernel durations do not depend on how they were launched)
+        records = []
+        _lib.profile = records
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        for _ in range(args.steps):
+            trainer.train_step(frames, batch_dev)
+        pe1.record()
+        barrier()
+        _lib.profile = None
+        eager_ms_total = pe0.elapsed_time(pe1)
+    else:
+        eager_ms_total = ms_total
     if records:
         kernels_summary, agg = summarize_profile(records, args.steps, pk)
         top = max(agg.items(), key=lambda kv: kv[1]["ms"])
@@ -336,7 +374,9 @@ def run_ours(args):
                    "l2": "per-step working set (240 MB bf16 weights + GBs of activations) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world}", "feature_extractor": "stand-in frozen pyramid (YOLO11m weights unobtainable offline)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "kernels": kernels_summary, "last_loss_items": last_loss,
+        "kernels": kernels_summary, "kernels_by_shape": getattr(summarize_profile, "by_shape", None), "last_loss_items": last_loss, "cuda_graph": graphed,
+        "kernel_ms_sum_per_step": (sum(v["ms_per_step"] for v in kernels_summary.values()) if kernels_summary else None),
+        "eager_instrumented_ms_per_step": (eager_ms_total / args.steps if kernels_summary else None),
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -371,12 +411,24 @@ def run_lif_microbench(args):
                 e1.record(); torch.cuda.synchronize()
                 return e0.elapsed_time(e1) / reps
 
+            bnb = torch.full((C,), 0.2, device="cuda")
+            dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+            from snn_object_detectionddp_b200._lib import call, ptr, stream_ptr
+            red = torch.zeros(T, 2, C, device="cuda")
+            dy = torch.empty_like(gs)
+            P = n // (T * C)
+            a = (ptr(y), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(bnb), None, ptr(gs), None, ptr(red), ptr(dy), None,
+                 ptr(dg), ptr(db), T, P, C, 0.5, 1.0, 2.0)
             f_ms = timeit(lambda: K.bn_act_fwd(0, y, scale, shift, T))
-            b_ms = timeit(lambda: K.bn_act_bwd(0, True, y, scale, shift, mean, invstd, gs, T))
+            r_ms = timeit(lambda: call("snn_bn_act_bwd2", 0, 0, *a, stream_ptr()))
+            d_ms = timeit(lambda: call("snn_bn_act_bwd2", 1, 0, *a, stream_ptr()))
             be_ms = timeit(lambda: K.bn_act_bwd(0, False, y, scale, shift, mean, invstd, gs, T))
-            rows.append(dict(T=T, C=C, HW=HWs, B=Bn, fwd_gbs=n * 6.125 / f_ms / 1e6, bwd_train_gbs=n * 10.0 / b_ms / 1e6,
-                             bwd_eval_gbs=n * 8.0 / be_ms / 1e6, fwd_ms=f_ms, bwd_train_ms=b_ms))
-            del y, gs
+            # algorithmic bytes / neuron-timestep: fwd 4+2+1/8; train bwd pass 1 (reductions) 4+2, pass 2 (dx) 4+2+2;
+            # frozen-statistics bwd 4+2+2
+            rows.append(dict(T=T, C=C, HW=HWs, B=Bn, fwd_gbs=n * 6.125 / f_ms / 1e6, bwd_reduce_gbs=n * 6.0 / r_ms / 1e6,
+                             bwd_dx_gbs=n * 8.0 / d_ms / 1e6, bwd_train_gbs=n * 14.0 / (r_ms + d_ms) / 1e6,
+                             bwd_eval_gbs=n * 8.0 / be_ms / 1e6, fwd_ms=f_ms, bwd_reduce_ms=r_ms, bwd_dx_ms=d_ms))
+            del y, gs, dy
     for r in rows:
         r["fwd_frac"], r["bwd_frac"] = r["fwd_gbs"] / pk["hbm"], r["bwd_train_gbs"] / pk["hbm"]
     print(json.dumps({"microbench": "lif", "hbm_peak_gbs": pk["hbm"], "peak_source": pk["src"], "rows": rows}), flush=True)

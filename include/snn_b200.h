@@ -11,8 +11,9 @@
  *    including workspaces); `stream` is a cudaStream_t passed as void*.
  *  - activations are NHWC with the T*B batch folded into N ("NB"); element (n,h,w,c) of a view
  *    lives at ptr[((n*H+h)*W+w)*ld + c]  (ld >= C lets a view be a channel slice).
- *  - bf16 = raw uint16 storage; weights for the tensor-core convs are bf16 [rows][taps][K]
- *    (fprop: rows = Cout, K = Cin;  dgrad: rows = Cin, K = Cout), taps = kh*kw in (kh,kw) order.
+ *  - bf16 = raw uint16 storage; weights for the tensor-core convs are bf16 [Cout][taps][Cin] (taps = kh*kw in
+ *    (kh,kw) order; transposed conv: [Cout][4][Cin]) for fprop AND dgrad -- dgrad reads the same buffer as an
+ *    MN-major operand, no transposed copy exists.
  *  - compute dtype: bf16 operands, fp32 accumulate (tcgen05), fp32 everywhere else.
  */
 #ifndef SNN_B200_H
@@ -43,13 +44,14 @@ int snn_conv_fprop(int geom, int NB, int H, int W,
                    int accumulate, void* stream);
 int snn_conv_dgrad(int geom, int NB, int H, int W,
                    const void* dy, int Cout, long long ld_dy,
-                   const void* wt_bf16, int wt_rows, int ci_off, int Ci,
+                   const void* w_bf16 /*[Cout][taps][w_K]*/, int w_K, int ci_off, int Ci,
                    void* dx, int dx_is_f32, long long dx_ld, int dx_coff, int accumulate, void* stream);
 /* dw (fp32 [Cout][taps][w_K]) += ... ; caller zeroes it once per step */
 int snn_conv_wgrad(int geom, int NB, int H, int W,
                    const void* x, int Ci, long long ld_x, const void* dy, int Cout, long long ld_dy,
                    float* dw, int w_K, int w_coff, void* stream);
-/* fp32 master [N][T][K] -> bf16 same layout (w_bf16, may be NULL) and bf16 [K][T][N] (wt_bf16, may be NULL) */
+/* fp32 master [N][T][K] -> bf16 same layout (w_bf16, may be NULL) and bf16 [K][T][N] (wt_bf16, may be NULL; utility,
+ * the convs no longer need the transposed copy) */
 int snn_weight_prep(const float* w, void* w_bf16, void* wt_bf16, int N, int T, int K, void* stream);
 
 /* ---- neuron layer: replaces `self.silu(self.bn(.))` of ConvBlock.forward (model.py:14-18)
@@ -72,6 +74,14 @@ int snn_bn_act_bwd(int act, int training, const float* y, const float* scale, co
                    const void* gs_bf16, const float* gv_final,
                    float* gx, void* dy_bf16, float* gv_init, float* red,
                    int T, int P, int C, int ss_stride_t, float beta, float theta, float alpha, void* stream);
+/* train-mode backward WITHOUT the fp32 gx round trip: gx is recomputed in registers in both passes.
+ *   pass 0: red [T][2][C] = per-(t,c) sum gx, sum gx*xhat (zeroed here)
+ *   pass 1: dy bf16 = scale*(gx - mean gx - xhat*mean(gx*xhat)); gv_init (may be NULL); dgamma/dbeta += (may be NULL)
+ * beta_bn = the BatchNorm bias [C] (x - beta_bn = gamma*xhat).  scale/shift/mean/invstd are [T][C]. */
+int snn_bn_act_bwd2(int pass, int act, const float* y, const float* scale, const float* shift, const float* mean,
+                    const float* invstd, const float* beta_bn, const float* v_init, const void* gs_bf16,
+                    const float* gv_final, float* red, void* dy_bf16, float* gv_init, float* dgamma, float* dbeta,
+                    int T, int P, int C, float beta, float theta, float alpha, void* stream);
 /* BN input gradient from gx and the reductions; dgamma/dbeta (+=) */
 int snn_bn_bwd_dx(const float* red, const float* gamma, const float* gx, const float* y,
                   const float* scale, const float* mean, const float* invstd, float* coef /*[T][2][C]*/,
@@ -103,11 +113,13 @@ int snn_space_to_depth8(const float* frames, void* out_bf16, int B, int T, int H
 /* ---- bias gradient of the biased convs (ConvLSTM2d.conv, UpBlock.up, out_p*): acc[c] += sum_p dy[p][c] ---- */
 int snn_colsum_bf16(const void* dy_bf16, float* acc, long long P, int C, void* stream);
 
-/* ---- optimizer: replaces clip_grad_norm_(10) + AdamW.step (train.py:77-78) over one flat buffer.
- *      hp (device, 8 floats) = {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, max_norm} ---- */
+/* ---- optimizer: replaces clip_grad_norm_(10) + AdamW.step + OneCycleLR.step (train.py:77-80) over one flat buffer.
+ *      hp (device) = rows of 8 floats {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, max_norm};
+ *      step_ptr == NULL: row 0 is used; else row min(*step_ptr, n_rows-1) is used and *step_ptr is incremented
+ *      afterwards (device-side schedule: no host sync, CUDA-graph replayable). ---- */
 int snn_grad_sumsq(const float* g, long long n, double* acc, int zero_first, void* stream);
 int snn_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
-                   const float* hp, const double* sumsq, float* gnorm_out, void* stream);
+                   const float* hp, const double* sumsq, float* gnorm_out, int* step_ptr, int n_rows, void* stream);
 
 /* ---- Detect decode (ultralytics Detect._inference, reached through model.py:209 in eval mode, and
  *      v8DetectionLoss.bbox_decode): boxes fp32 [N][4] in pixels (xywh != 0: cx,cy,w,h; else x1,y1,x2,y2) and

@@ -26,6 +26,7 @@ _SIGNATURES = {
     "snn_bn_finalize": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P],
     "snn_bn_act_fwd": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _F, _P],
     "snn_bn_act_bwd": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
+    "snn_bn_act_bwd2": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _P],
     "snn_bn_bwd_dx": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "snn_lstm_gates_fwd": [_P, _P, _P, _P, _P, _L, _I, _P],
     "snn_lstm_gates_bwd": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
@@ -40,7 +41,7 @@ _SIGNATURES = {
     "snn_detect_loss_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     "snn_detect_loss_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
     "snn_grad_sumsq": [_P, _L, _P, _I, _P],
-    "snn_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P],
+    "snn_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _I, _P],
 }
 
 _lib = None

@@ -46,6 +46,9 @@ int launch_bn_act_fwd(int, const float*, const float*, const float*, const float
 int launch_bn_act_bwd(int, int, const float*, const float*, const float*, const float*, const float*, const float*,
                       const __nv_bfloat16*, const float*, float*, __nv_bfloat16*, float*, float*, int, int, int, int, float,
                       float, float, cudaStream_t);
+int launch_bn_act_bwd2(int, int, const float*, const float*, const float*, const float*, const float*, const float*,
+                       const float*, const __nv_bfloat16*, const float*, float*, __nv_bfloat16*, float*, float*, float*, int, int,
+                       int, float, float, float, cudaStream_t);
 int launch_bn_bwd_dx(const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*,
                      float*, float*, __nv_bfloat16*, int, int, int, cudaStream_t);
 int launch_lstm_gates_fwd(const float*, const float*, float*, float*, __nv_bfloat16*, long long, int, cudaStream_t);
@@ -60,7 +63,7 @@ int launch_dw3x3_dgrad(const __nv_bfloat16*, const float*, __nv_bfloat16*, int, 
 int launch_dw3x3_wgrad(const __nv_bfloat16*, const __nv_bfloat16*, float*, int, int, int, int, cudaStream_t);
 int launch_s2d8(const float*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 int launch_adamw(float*, const float*, float*, float*, __nv_bfloat16*, long long, const float*, const double*, float*,
-                 cudaStream_t);
+                 int*, int, cudaStream_t);
 int launch_detect_decode(const float*, const float*, const float*, const float*, int, int, int, int, int, float*, float*,
                          cudaStream_t);
 int launch_detect_loss_fwd(const float*, const float*, const float*, const float*, const float*, const float*, const uint8_t*,
@@ -116,6 +119,13 @@ int snn_bn_act_bwd(int act, int training, const float* y, const float* scale, co
     return launch_bn_act_bwd(act, training, y, scale, shift, mean, invstd, v_init, (const __nv_bfloat16*)gs, gv_final, gx,
                              (__nv_bfloat16*)dy, gv_init, red, T, P, C, ss_stride_t, beta, theta, alpha, ST);
 }
+int snn_bn_act_bwd2(int pass, int act, const float* y, const float* scale, const float* shift, const float* mean,
+                    const float* invstd, const float* beta_bn, const float* v_init, const void* gs, const float* gv_final,
+                    float* red, void* dy, float* gv_init, float* dgamma, float* dbeta, int T, int P, int C, float beta,
+                    float theta, float alpha, void* stream) {
+    return launch_bn_act_bwd2(pass, act, y, scale, shift, mean, invstd, beta_bn, v_init, (const __nv_bfloat16*)gs, gv_final,
+                              red, (__nv_bfloat16*)dy, gv_init, dgamma, dbeta, T, P, C, beta, theta, alpha, ST);
+}
 int snn_bn_bwd_dx(const float* red, const float* gamma, const float* gx, const float* y, const float* scale,
                   const float* mean, const float* invstd, float* coef, float* dgamma, float* dbeta, void* dy, int T, int P,
                   int C, void* stream) {
@@ -156,8 +166,8 @@ int snn_grad_sumsq(const float* g, long long n, double* acc, int zero_first, voi
     return launch_sumsq(g, n, acc, zero_first, ST);
 }
 int snn_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, long long n, const float* hp,
-                   const double* sumsq, float* gnorm_out, void* stream) {
-    return launch_adamw(p, g, m, v, (__nv_bfloat16*)shadow, n, hp, sumsq, gnorm_out, ST);
+                   const double* sumsq, float* gnorm_out, int* step_ptr, int n_rows, void* stream) {
+    return launch_adamw(p, g, m, v, (__nv_bfloat16*)shadow, n, hp, sumsq, gnorm_out, step_ptr, n_rows, ST);
 }
 int snn_detect_decode(const float* distri, const float* scores, const float* anchors, const float* stride, int B, int A,
                       int nc, int reg_max, int xywh, float* boxes, float* probs, void* stream) {

@@ -39,6 +39,7 @@ struct ConvGemmParams {
     int bn, bh, bw;                   // pixel box (bn*bh*bw == 128)
     int tiles_w, tiles_h, tiles_n;
     int BN;                           // UMMA N
+    int n_blocks;                     // ceil(n_store / BN)
     int n_store;                      // valid output channels
     int wn_off;                       // first weight row (N coordinate) of this launch
     int stages, stage_bytes;
@@ -49,6 +50,8 @@ struct ConvGemmParams {
     long long out_ld;                 // elements between consecutive output pixels
     int out_coff;
     int nphase;
+    int b_mn;                         // B operand MN-major: weights [K rows][tap][N contiguous] read in place (dgrad)
+    int b_boxes;                      // b_mn: number of 64-column boxes per stage
     Phase phase[4];
 };
 
@@ -80,26 +83,27 @@ constexpr int kTmemCols = 256;
 // ------------------------------------------------------------------------------------------
 // fprop-type kernel
 // ------------------------------------------------------------------------------------------
+// Persistent: one CTA per SM walks tiles (m-tile fastest, so co-resident CTAs share the weight tile in L2); the
+// accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the main loop of
+// tile i+1.  Pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+constexpr int kAccCols = 256;
+
 __global__ void __launch_bounds__(192, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int stages = p.stages;
     const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
-
-    // tile coordinates
-    const int mt = blockIdx.x;
-    const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-    const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-    const int ncol0 = blockIdx.y * p.BN;
-    const Phase& ph = p.phase[blockIdx.z];
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int total_tiles = m_tiles * p.n_blocks * p.nphase;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -107,13 +111,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tma_prefetch_desc(&tmA1);
             tma_prefetch_desc(&tmB);
         }
-        tmem_alloc<kTmemCols>(smem_u32(&tmem_base_s));
+        tmem_alloc<2 * kAccCols>(smem_u32(&tmem_base_s));
     } else if (warp == 1 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
-        mbar_init(smem_u32(&tmem_full_bar), 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+            mbar_init(smem_u32(&tmem_empty_bar[a]), 4);   // one arrive per epilogue warp
+        }
         mbar_fence_init();
     }
     tc_fence_before();
@@ -121,111 +128,145 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    int total = 0;
-    for (int s = 0; s < ph.nseg; ++s) total += ph.seg[s].nchunk;
-
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
-            for (int sg = 0; sg < ph.nseg; ++sg) {
-                const Seg g = ph.seg[sg];
-                const CUtensorMap* tmA = g.src ? &tmA1 : &tmA0;
-                for (int kc = 0; kc < g.nchunk; ++kc, ++it) {
-                    const int s = it % stages;
-                    const uint32_t par = (uint32_t)((it / stages) & 1);
-                    mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
-                    const uint32_t fb = smem_u32(&full_bar[s]);
-                    mbar_expect_tx(fb, stage_bytes);
-                    const uint32_t a_s = sbase + (uint32_t)s * stage_bytes;
-                    tma_load_5d(a_s, tmA, fb, g.dc + kc * 64, w0 + g.dw, g.dhp, h0 + g.dh, n0);
-                    tma_load_3d(a_s + 16384u, &tmB, fb, g.wc0 + kc * 64, g.wtap, p.wn_off + ncol0);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile % m_tiles, rest = tile / m_tiles;
+                const int ncol0 = (rest % p.n_blocks) * p.BN;
+                const Phase& ph = p.phase[rest / p.n_blocks];
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+                const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+                for (int sg = 0; sg < ph.nseg; ++sg) {
+                    const Seg g = ph.seg[sg];
+                    const CUtensorMap* tmA = g.src ? &tmA1 : &tmA0;
+                    for (int kc = 0; kc < g.nchunk; ++kc, ++it) {
+                        const int s = it % stages;
+                        const uint32_t par = (uint32_t)((it / stages) & 1);
+                        mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
+                        const uint32_t fb = smem_u32(&full_bar[s]);
+                        mbar_expect_tx(fb, stage_bytes);
+                        const uint32_t a_s = sbase + (uint32_t)s * stage_bytes;
+                        tma_load_5d(a_s, tmA, fb, g.dc + kc * 64, w0 + g.dw, g.dhp, h0 + g.dh, n0);
+                        if (!p.b_mn) {
+                            tma_load_3d(a_s + 16384u, &tmB, fb, g.wc0 + kc * 64, g.wtap, p.wn_off + ncol0);
+                        } else {  // [64 K rows] x [64 N] boxes, one per 64 output columns
+                            for (int nb = 0; nb < p.b_boxes; ++nb)
+                                tma_load_3d(a_s + 16384u + (uint32_t)nb * 8192u, &tmB, fb, p.wn_off + ncol0 + nb * 64, g.wtap,
+                                            g.wc0 + kc * 64);
+                        }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
-            for (int it = 0; it < total; ++it) {
-                const int s = it % stages;
-                const uint32_t par = (uint32_t)((it / stages) & 1);
-                mbar_wait(smem_u32(&full_bar[s]), par);
+            const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, p.b_mn);
+            int it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+                const Phase& ph = p.phase[(tile / m_tiles) / p.n_blocks];
+                int total = 0;
+                for (int s = 0; s < ph.nseg; ++s) total += ph.seg[s].nchunk;
+                const int acc = lt & 1;
+                mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((lt >> 1) & 1) ^ 1));   // epilogue drained this buffer
                 tc_fence_after();
-                const uint32_t a_s = sbase + (uint32_t)s * stage_bytes;
-                const uint32_t b_s = a_s + 16384u;
+                const uint32_t tacc = tmem_base + (uint32_t)(acc * kAccCols);
+                for (int j = 0; j < total; ++j, ++it) {
+                    const int s = it % stages;
+                    const uint32_t par = (uint32_t)((it / stages) & 1);
+                    mbar_wait(smem_u32(&full_bar[s]), par);
+                    tc_fence_after();
+                    const uint32_t a_s = sbase + (uint32_t)s * stage_bytes;
+                    const uint32_t b_s = a_s + 16384u;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    umma_bf16(tmem_base, umma_desc_sw128(a_s + k * 32, 16, 1024), umma_desc_sw128(b_s + k * 32, 16, 1024),
-                              idesc, (uint32_t)((it | k) != 0));
+                    for (int k = 0; k < 4; ++k) {
+                        // K-major B: 32 B per 16-wide K step inside the 128 B row; MN-major B: 16 K rows of 128 B = 2048 B,
+                        // 64-column blocks 8192 B apart (LBO), 8-row groups 1024 B apart (SBO)
+                        const uint64_t bdesc = p.b_mn ? umma_desc_sw128(b_s + k * 2048, 8192, 1024) : umma_desc_sw128(b_s + k * 32, 16, 1024);
+                        umma_bf16(tacc, umma_desc_sw128(a_s + k * 32, 16, 1024), bdesc, idesc, (uint32_t)((j | k) != 0));
+                    }
+                    umma_commit(smem_u32(&empty_bar[s]));
                 }
-                umma_commit(smem_u32(&empty_bar[s]));
+                umma_commit(smem_u32(&tmem_full_bar[acc]));
             }
-            umma_commit(smem_u32(&tmem_full_bar));
         }
     } else {
         // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int wl = row % p.bw, hl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
-        const int n = n0 + nl, hd = h0 + hl, wd = w0 + wl;
-        const bool valid = (n < p.NB) && (hd < p.Hd) && (wd < p.Wd);
-        const long long pix = ((long long)n * p.Ho + (hd * p.os + ph.oph)) * p.Wo + (wd * p.os + ph.opw);
-        mbar_wait(smem_u32(&tmem_full_bar), 0);
-        tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int nchunks = p.BN >> 4;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            uint32_t r[16];
-            tmem_ld16(trow + (uint32_t)(ch * 16), r);
-            tmem_ld_wait();
-            const int col = ncol0 + ch * 16;
-            if (!valid || col >= p.n_store) continue;
-            const int nv = min(16, p.n_store - col);  // 8 or 16 (n_store % 8 == 0)
-            float v[16];
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            const int mt = tile % m_tiles, rest = tile / m_tiles;
+            const int ncol0 = (rest % p.n_blocks) * p.BN;
+            const Phase& ph = p.phase[rest / p.n_blocks];
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+            const int n = tn * p.bn + nl, hd = th * p.bh + hl, wd = tw * p.bw + wl;
+            const bool valid = (n < p.NB) && (hd < p.Hd) && (wd < p.Wd);
+            const long long pix = ((long long)n * p.Ho + (hd * p.os + ph.oph)) * p.Wo + (wd * p.os + ph.opw);
+            const int acc = lt & 1;
+            mbar_wait(smem_u32(&tmem_full_bar[acc]), (uint32_t)((lt >> 1) & 1));
+            tc_fence_after();
+            const uint32_t trow = tmem_base + (uint32_t)(acc * kAccCols) + ((uint32_t)(q * 32) << 16);
+            const int nchunks = p.BN >> 4;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                uint32_t r[16];
+                tmem_ld16(trow + (uint32_t)(ch * 16), r);
+                tmem_ld_wait();
+                const int col = ncol0 + ch * 16;
+                if (!valid || col >= p.n_store) continue;
+                const int nv = min(16, p.n_store - col);  // 8 or 16 (n_store % 8 == 0)
+                float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-            if (p.bias) {
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j < nv) v[j] += __ldg(p.bias + col + j);
-            }
-            if (p.out_f32) {
-                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_ld + p.out_coff + col);
+                    for (int j = 0; j < 16; ++j)
+                        if (j < nv) v[j] += __ldg(p.bias + col + j);
+                }
+                if (p.out_f32) {
+                    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_ld + p.out_coff + col);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j * 4 < nv) {
-                        float4 t = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        if (p.accumulate) {
-                            const float4 old = o[j];
-                            t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+                    for (int j = 0; j < 4; ++j) {
+                        if (j * 4 < nv) {
+                            float4 t = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            if (p.accumulate) {
+                                const float4 old = o[j];
+                                t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+                            }
+                            o[j] = t;
                         }
-                        o[j] = t;
+                    }
+                } else {
+                    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + p.out_coff + col;
+                    uint4* o = reinterpret_cast<uint4*>(ob);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (j * 8 < nv) {
+                            if (p.accumulate) {
+                                const uint4 old = o[j];
+                                v[8 * j + 0] += bf16_lo(old.x); v[8 * j + 1] += bf16_hi(old.x);
+                                v[8 * j + 2] += bf16_lo(old.y); v[8 * j + 3] += bf16_hi(old.y);
+                                v[8 * j + 4] += bf16_lo(old.z); v[8 * j + 5] += bf16_hi(old.z);
+                                v[8 * j + 6] += bf16_lo(old.w); v[8 * j + 7] += bf16_hi(old.w);
+                            }
+                            uint4 t;
+                            t.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); t.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                            t.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); t.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                            o[j] = t;
+                        }
                     }
                 }
-            } else {
-                __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + p.out_coff + col;
-                uint4* o = reinterpret_cast<uint4*>(ob);
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (j * 8 < nv) {
-                        if (p.accumulate) {
-                            const uint4 old = o[j];
-                            v[8 * j + 0] += bf16_lo(old.x); v[8 * j + 1] += bf16_hi(old.x);
-                            v[8 * j + 2] += bf16_lo(old.y); v[8 * j + 3] += bf16_hi(old.y);
-                            v[8 * j + 4] += bf16_lo(old.z); v[8 * j + 5] += bf16_hi(old.z);
-                            v[8 * j + 6] += bf16_lo(old.w); v[8 * j + 7] += bf16_hi(old.w);
-                        }
-                        uint4 t;
-                        t.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); t.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                        t.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); t.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                        o[j] = t;
-                    }
-                }
             }
+            // all TMEM reads of this warp are complete (tmem_ld_wait above): hand the accumulator back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<kTmemCols>(tmem_base);
+    if (warp == 0) tmem_dealloc<2 * kAccCols>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -443,14 +484,19 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
         attr_err = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     });
     SNN_CUDA_OK(attr_err);
-    p.stage_bytes = 16384 + p.BN * 128;
+    p.b_boxes = (p.BN + 63) / 64;
+    p.stage_bytes = p.b_mn ? 16384 + p.b_boxes * 8192 : 16384 + p.BN * 128;
     int stages = smem_budget() / p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (g_debug_flags[1] > 0 && stages > g_debug_flags[1]) stages = g_debug_flags[1];
     SNN_REQUIRE(stages >= 2, "conv_gemm: not enough shared memory for 2 stages");
     p.stages = stages;
     const size_t smem = (size_t)stages * p.stage_bytes + 1024;
-    dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, (p.n_store + p.BN - 1) / p.BN, p.nphase);
+    p.n_blocks = (p.n_store + p.BN - 1) / p.BN;
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks * p.nphase;
+    int grid = num_sms();
+    if (g_debug_flags[5] > 0) grid = g_debug_flags[5];
+    if (grid > total_tiles) grid = total_tiles;
     conv_gemm_kernel<<<grid, 192, smem, st>>>(a0, a1, b, p);
     return check_cuda(cudaGetLastError(), "conv_gemm_kernel launch");
 }
@@ -533,10 +579,11 @@ int conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long long
 }
 
 // ------------------------------------------------------------------------------------------
-// dgrad: dx[NB,H,W,Ci] = conv^T(dy) using weights laid out [Cin_tot][tap][Cout] (K-major in Cout)
+// dgrad: dx[NB,H,W,Ci] = conv^T(dy).  The weights are read IN PLACE from the fprop layout [Cout][tap][Cin_tot]
+// (B operand MN-major: N = input channel contiguous, K = output channel = row) -- no transposed copy exists.
 // (H, W) are the conv's INPUT spatial dims; dy has the geometry's output dims.
 // ------------------------------------------------------------------------------------------
-int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long long ld_dy, const void* wt, int wt_rows,
+int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long long ld_dy, const void* wt, int w_K,
                int ci_off, int Ci, void* dx, int dx_f32, long long dx_ld, int dx_coff, int accumulate, cudaStream_t st) {
     SNN_REQUIRE(Ci % 8 == 0, "conv_dgrad: Ci=%d must be a multiple of 8", Ci);
     ConvGemmParams p;
@@ -548,11 +595,11 @@ int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long lo
     if (geom == GEOM_T2x2_S2) { Hy = 2 * H; Wy = 2 * W; phase_view = 1; }
     set_domain(p, NB, Hd, Wd);
     p.BN = pick_bn(Ci);
-    p.n_store = Ci; p.wn_off = ci_off;
+    p.n_store = Ci; p.wn_off = ci_off; p.b_mn = 1;
     p.out = dx; p.bias = nullptr; p.out_f32 = dx_f32; p.accumulate = accumulate; p.out_ld = dx_ld; p.out_coff = dx_coff;
     CUtensorMap a0, b;
     if (make_act_map(&a0, dy, NB, Hy, Wy, Cout, ld_dy, phase_view, p.bn, p.bh, p.bw)) return 2;
-    if (make_w_map(&b, wt, wt_rows, taps, Cout, p.BN)) return 2;
+    if (make_w_map(&b, wt, Cout, taps, w_K, 64)) return 2;   // box = 64 input channels x 1 tap x 64 output-channel rows
     if (geom == GEOM_3x3_S1 || geom == GEOM_1x1) {
         p.nphase = 1;
         Phase& ph = p.phase[0];

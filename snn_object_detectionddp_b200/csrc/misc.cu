@@ -259,8 +259,10 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-             __nv_bfloat16* __restrict__ shadow, long long n4, const float* __restrict__ hp, const double* __restrict__ sumsq,
-             float* __restrict__ gnorm_out) {
+             __nv_bfloat16* __restrict__ shadow, long long n4, const float* __restrict__ hp_table,
+             const double* __restrict__ sumsq, float* __restrict__ gnorm_out, const int* __restrict__ step_ptr, int n_rows) {
+    // row of the tabulated schedule: picked by a DEVICE step counter so a captured CUDA graph advances on replay
+    const float* hp = hp_table + (step_ptr ? (size_t)min(*step_ptr, n_rows - 1) * 8 : 0);
     const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], bc1 = hp[5], bc2 = hp[6], max_norm = hp[7];
     const float gn = (float)sqrt(*sumsq);
     float clip = max_norm / (gn + 1e-6f);  // torch.nn.utils.clip_grad_norm_: coef clamped to 1
@@ -307,15 +309,19 @@ int launch_sumsq(const float* g, long long n, double* acc, int zero_first, cudaS
     return check_cuda(cudaGetLastError(), "sumsq_kernel");
 }
 
+__global__ void step_advance_kernel(int* step) { *step += 1; }
+
 int launch_adamw(float* p, const float* g, float* m, float* v, __nv_bfloat16* shadow, long long n, const float* hp,
-                 const double* sumsq, float* gnorm_out, cudaStream_t st) {
+                 const double* sumsq, float* gnorm_out, int* step_ptr, int n_rows, cudaStream_t st) {
     SNN_REQUIRE(n % 4 == 0, "adamw: length must be a multiple of 4");
     const long long n4 = n / 4;
     long long blocks = (n4 + 255) / 256;
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, shadow, n4, hp, sumsq, gnorm_out);
+    adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, shadow, n4, hp, sumsq, gnorm_out, step_ptr, n_rows);
+    SNN_CUDA_OK(cudaGetLastError());
+    if (step_ptr) step_advance_kernel<<<1, 1, 0, st>>>(step_ptr);
     return check_cuda(cudaGetLastError(), "adamw_kernel");
 }
 

@@ -19,32 +19,40 @@ enum { ACT_LIF = 0, ACT_SILU = 1 };
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, double* __restrict__ sums,
                                                         int P, int C, int pix_per_block) {
-    extern __shared__ double sh[];  // [2][C]
+    extern __shared__ float shs[];  // [2][C] block partials (fp32: <= a few thousand values each), combined in fp64
     const int t = blockIdx.y;
     const int tpp = C >> 2;  // threads per pixel (float4 each)
     const int rows = 256 / tpp;
     const int cg = threadIdx.x % tpp, row = threadIdx.x / tpp;
-    for (int i = threadIdx.x; i < 2 * C; i += 256) sh[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * C; i += 256) shs[i] = 0.f;
     __syncthreads();
     if (row < rows) {
         const int p0 = blockIdx.x * pix_per_block;
         const int p1 = min(P, p0 + pix_per_block);
         const float4* base = reinterpret_cast<const float4*>(y + (size_t)t * P * C) + cg;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-        for (int p = p0 + row; p < p1; p += rows) {
-            float4 v = __ldg(base + (size_t)p * tpp);
+        int p = p0 + row;
+        for (; p + 3 * rows < p1; p += 4 * rows) {  // 4 independent 128-bit loads in flight per thread
+            const float4 a = __ldcs(base + (size_t)p * tpp), b = __ldcs(base + (size_t)(p + rows) * tpp);
+            const float4 c = __ldcs(base + (size_t)(p + 2 * rows) * tpp), d = __ldcs(base + (size_t)(p + 3 * rows) * tpp);
+            s.x += (a.x + b.x) + (c.x + d.x); s.y += (a.y + b.y) + (c.y + d.y);
+            s.z += (a.z + b.z) + (c.z + d.z); s.w += (a.w + b.w) + (c.w + d.w);
+            q.x += (a.x * a.x + b.x * b.x) + (c.x * c.x + d.x * d.x); q.y += (a.y * a.y + b.y * b.y) + (c.y * c.y + d.y * d.y);
+            q.z += (a.z * a.z + b.z * b.z) + (c.z * c.z + d.z * d.z); q.w += (a.w * a.w + b.w * b.w) + (c.w * c.w + d.w * d.w);
+        }
+        for (; p < p1; p += rows) {
+            const float4 v = __ldcs(base + (size_t)p * tpp);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
             q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
         }
         const int c = cg * 4;
-        atomicAdd(&sh[c + 0], (double)s.x); atomicAdd(&sh[c + 1], (double)s.y);
-        atomicAdd(&sh[c + 2], (double)s.z); atomicAdd(&sh[c + 3], (double)s.w);
-        atomicAdd(&sh[C + c + 0], (double)q.x); atomicAdd(&sh[C + c + 1], (double)q.y);
-        atomicAdd(&sh[C + c + 2], (double)q.z); atomicAdd(&sh[C + c + 3], (double)q.w);
+        atomicAdd(&shs[c + 0], s.x); atomicAdd(&shs[c + 1], s.y); atomicAdd(&shs[c + 2], s.z); atomicAdd(&shs[c + 3], s.w);
+        atomicAdd(&shs[C + c + 0], q.x); atomicAdd(&shs[C + c + 1], q.y);
+        atomicAdd(&shs[C + c + 2], q.z); atomicAdd(&shs[C + c + 3], q.w);
     }
     __syncthreads();
     double* out = sums + (size_t)t * 2 * C;
-    for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(&out[i], sh[i]);
+    for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(&out[i], (double)shs[i]);
 }
 
 // scale/shift per (t,c); running-stat update applied T times in order (the reference calls the
@@ -322,6 +330,170 @@ bn_bwd_dx_kernel(const float* __restrict__ gx, const float* __restrict__ y, cons
 }
 
 // ------------------------------------------------------------------------------------------
+// backward, train mode, RECOMPUTE variant (2 passes over y and gs, nothing but dy is written):
+//   pass 1 (REDUCE): red[t][0][c] = sum gx, red[t][1][c] = sum gx*xhat          reads 4 (y) + 2 (gs) B / neuron-step
+//   pass 2 (DX)    : dy = scale*(gx - mean(gx) - xhat*mean(gx*xhat)) as bf16    reads 6, writes 2 B / neuron-step
+// gx (the surrogate-gradient scan) is recomputed in registers in both passes instead of being stored as fp32 and
+// re-read (the 3-kernel path above moves 10 + 10 B).  Per-(t,c) coefficients live in shared memory; a block owns a
+// channel range [c_base, c_base + Cb) and a pixel range; a thread owns 4 channels of one pixel per iteration.
+//   x = y*scale + shift (same two roundings as the forward kernel -> identical spikes);
+//   xhat*k2*scale = (x - beta_bn)*k2, so pass 2 needs only {scale, shift, scale*k1, k2} per (t,c) and beta_bn per c.
+// ------------------------------------------------------------------------------------------
+template <int ACT>
+SNN_DEVINL float surrogate_step(float uu, float g, float& gv, float beta, float theta, float ka, float kz) {
+    if (ACT == ACT_LIF) {
+        const float z = kz * (uu - theta);
+        const float sg = __fdividef(ka, fmaf(z, z, 1.f));   // MUFU.RCP path (2 ulp): this kernel is issue-bound, not HBM-bound
+        const float keep = (uu >= theta) ? 0.f : 1.f;
+        const float gu = g * sg + gv * (keep - uu * sg);
+        gv = beta * gu;
+        return gu;
+    }
+    const float sgm = __fdividef(1.f, 1.f + __expf(-uu));
+    return g * (sgm * (1.f + uu * (1.f - sgm)));
+}
+
+// thread = 2 channels of one pixel per iteration (64-bit y loads, 32-bit gs loads / dy stores: still one fully used
+// 128/256 B line per warp instruction) -- half the live state of a 4-channel thread, so 4 blocks of 256 fit per SM.
+template <int ACT, int TMAX, bool REDUCE>
+__global__ void __launch_bounds__(256, (TMAX <= 4 ? 4 : (TMAX <= 8 ? 2 : 1)))
+bn_act_bwd2_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                   const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ beta_bn,
+                   const float* __restrict__ red_in, const float* __restrict__ v_init, const __nv_bfloat16* __restrict__ gs,
+                   const float* __restrict__ gv_final, __nv_bfloat16* __restrict__ dy_out, float* __restrict__ gv_init,
+                   float* __restrict__ red_out, float* dgamma, float* dbeta, int T, int P, int C, int Cb, int pix_per_block,
+                   float beta, float theta, float alpha, float invP) {
+    extern __shared__ float shc[];  // coefficient tables [T][NCOEF][Cb] (+ [Cb] beta_bn) ; REDUCE: + [T][2][Cb] accumulators
+    constexpr int NCOEF = REDUCE ? 3 : 4;
+    const int c_base = blockIdx.y * Cb;
+    const int tpp = Cb >> 1;
+    const int rows = 256 / tpp;
+    const int cg = threadIdx.x % tpp, row = threadIdx.x / tpp;
+    const int cl = cg * 2;           // channel offset inside the block's range
+    float* coef = shc;
+    float* bbn = shc + T * NCOEF * Cb;                 // DX only
+    float* accum = shc + T * NCOEF * Cb + (REDUCE ? 0 : Cb);  // REDUCE only
+    for (int i = threadIdx.x; i < T * Cb; i += 256) {
+        const int t = i / Cb, c = i % Cb, gc = t * C + c_base + c;
+        const float sc = scale[gc];
+        coef[(t * NCOEF + 0) * Cb + c] = sc;
+        coef[(t * NCOEF + 1) * Cb + c] = shift[gc];
+        if (REDUCE) {
+            coef[(t * NCOEF + 2) * Cb + c] = mean[gc];
+            accum[(t * 2 + 0) * Cb + c] = 0.f;
+            accum[(t * 2 + 1) * Cb + c] = 0.f;
+        } else {
+            const float s0 = red_in[(t * 2 + 0) * C + c_base + c], s1 = red_in[(t * 2 + 1) * C + c_base + c];
+            coef[(t * NCOEF + 2) * Cb + c] = sc * (s0 * invP);          // scale * mean(gx)
+            coef[(t * NCOEF + 3) * Cb + c] = s1 * invP * invstd[gc];    // mean(gx*xhat) * invstd  (scale*xhat = invstd*(x - beta_bn))
+        }
+    }
+    if (!REDUCE) {
+        for (int c = threadIdx.x; c < Cb; c += 256) bbn[c] = beta_bn ? beta_bn[c_base + c] : 0.f;
+        // parameter gradients of the BN affine: dgamma += sum_t red1, dbeta += sum_t red0 (one block per channel range)
+        if (blockIdx.x == 0) {
+            for (int c = threadIdx.x; c < Cb; c += 256) {
+                float dg = 0.f, db = 0.f;
+                for (int t = 0; t < T; ++t) { db += red_in[(t * 2 + 0) * C + c_base + c]; dg += red_in[(t * 2 + 1) * C + c_base + c]; }
+                if (dgamma) dgamma[c_base + c] += dg;
+                if (dbeta) dbeta[c_base + c] += db;
+            }
+        }
+    }
+    __syncthreads();
+    const float ka = 0.5f * alpha, kz = 1.5707963267948966f * alpha;
+    const int C2 = C >> 1;
+    const size_t nt2 = (size_t)P * C2;
+    float acc_s[TMAX][2], acc_d[TMAX][2];
+    if (REDUCE) {
+#pragma unroll
+        for (int t = 0; t < TMAX; ++t) acc_s[t][0] = acc_s[t][1] = acc_d[t][0] = acc_d[t][1] = 0.f;
+    }
+    if (row < rows) {
+        const int p0 = blockIdx.x * pix_per_block, p1 = min(P, p0 + pix_per_block);
+        for (int p = p0 + row; p < p1; p += rows) {
+            const size_t e2 = (size_t)p * C2 + (c_base >> 1) + cg;
+            float2 yv[TMAX];
+            uint32_t gr[TMAX];
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t) {
+                if (t < T) {
+                    yv[t] = __ldcs(reinterpret_cast<const float2*>(y) + (size_t)t * nt2 + e2);
+                    gr[t] = __ldcs(reinterpret_cast<const uint32_t*>(gs) + (size_t)t * nt2 + e2);
+                }
+            }
+            float v0 = 0.f, v1 = 0.f;
+            if (ACT == ACT_LIF && v_init) {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(v_init) + e2);
+                v0 = a.x; v1 = a.y;
+            }
+            float x[TMAX][2], u[TMAX][2];
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t) {
+                if (t < T) {
+                    const float2 sc = *reinterpret_cast<const float2*>(coef + (t * NCOEF + 0) * Cb + cl);
+                    const float2 sh = *reinterpret_cast<const float2*>(coef + (t * NCOEF + 1) * Cb + cl);
+                    x[t][0] = __fadd_rn(__fmul_rn(yv[t].x, sc.x), sh.x);
+                    x[t][1] = __fadd_rn(__fmul_rn(yv[t].y, sc.y), sh.y);
+                    if (ACT == ACT_LIF) {
+                        const float ua = __fadd_rn(__fmul_rn(beta, v0), x[t][0]), ub = __fadd_rn(__fmul_rn(beta, v1), x[t][1]);
+                        u[t][0] = ua; u[t][1] = ub;
+                        v0 = (ua >= theta) ? 0.f : ua;
+                        v1 = (ub >= theta) ? 0.f : ub;
+                    } else {
+                        u[t][0] = x[t][0]; u[t][1] = x[t][1];
+                    }
+                }
+            }
+            float gv0 = 0.f, gv1 = 0.f;
+            if (ACT == ACT_LIF && gv_final) {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(gv_final) + e2);
+                gv0 = a.x; gv1 = a.y;
+            }
+#pragma unroll
+            for (int t = TMAX - 1; t >= 0; --t) {
+                if (t < T) {
+                    const float gx0 = surrogate_step<ACT>(u[t][0], bf16_lo(gr[t]), gv0, beta, theta, ka, kz);
+                    const float gx1 = surrogate_step<ACT>(u[t][1], bf16_hi(gr[t]), gv1, beta, theta, ka, kz);
+                    if (REDUCE) {
+                        const float2 m = *reinterpret_cast<const float2*>(coef + (t * NCOEF + 2) * Cb + cl);
+                        acc_s[t][0] += gx0; acc_s[t][1] += gx1;
+                        acc_d[t][0] = fmaf(gx0, yv[t].x - m.x, acc_d[t][0]);
+                        acc_d[t][1] = fmaf(gx1, yv[t].y - m.y, acc_d[t][1]);
+                    } else {
+                        const float2 sc = *reinterpret_cast<const float2*>(coef + (t * NCOEF + 0) * Cb + cl);
+                        const float2 k1 = *reinterpret_cast<const float2*>(coef + (t * NCOEF + 2) * Cb + cl);
+                        const float2 k2 = *reinterpret_cast<const float2*>(coef + (t * NCOEF + 3) * Cb + cl);
+                        const float2 bb = *reinterpret_cast<const float2*>(bbn + cl);
+                        *(reinterpret_cast<uint32_t*>(dy_out) + (size_t)t * nt2 + e2) =
+                            pack_bf16x2(sc.x * gx0 - k1.x - (x[t][0] - bb.x) * k2.x, sc.y * gx1 - k1.y - (x[t][1] - bb.y) * k2.y);
+                    }
+                }
+            }
+            if (!REDUCE && ACT == ACT_LIF && gv_init) *(reinterpret_cast<float2*>(gv_init) + e2) = make_float2(gv0, gv1);
+        }
+        if (REDUCE) {
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t) {
+                if (t < T) {
+                    atomicAdd(&accum[(t * 2 + 0) * Cb + cl], acc_s[t][0]); atomicAdd(&accum[(t * 2 + 0) * Cb + cl + 1], acc_s[t][1]);
+                    atomicAdd(&accum[(t * 2 + 1) * Cb + cl], acc_d[t][0]); atomicAdd(&accum[(t * 2 + 1) * Cb + cl + 1], acc_d[t][1]);
+                }
+            }
+        }
+    }
+    if (REDUCE) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < T * Cb; i += 256) {
+            const int t = i / Cb, c = i % Cb;
+            atomicAdd(&red_out[(t * 2 + 0) * C + c_base + c], accum[(t * 2 + 0) * Cb + c]);
+            // sum gx*(y - mean) -> sum gx*xhat
+            atomicAdd(&red_out[(t * 2 + 1) * C + c_base + c], accum[(t * 2 + 1) * Cb + c] * invstd[t * C + c_base + c]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
 static int pick_ppb(int P, int rows, int T) {
@@ -339,9 +511,9 @@ int launch_bn_stats(const float* y, double* sums, int T, int P, int C, cudaStrea
     SNN_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "bn_stats: C=%d must be a multiple of 4 in [4,1024]", C);
     SNN_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * T * C, st));
     const int rows = 256 / (C / 4);
-    const int ppb = pick_ppb(P, rows, T);
+    const int ppb = pick_ppb(P, rows, 1);   // independent of T: a frame's statistics are bit-identical however the T*B batch is folded
     dim3 grid((P + ppb - 1) / ppb, T);
-    bn_stats_kernel<<<grid, 256, sizeof(double) * 2 * C, st>>>(y, sums, P, C, ppb);
+    bn_stats_kernel<<<grid, 256, sizeof(float) * 2 * C, st>>>(y, sums, P, C, ppb);
     return check_cuda(cudaGetLastError(), "bn_stats_kernel");
 }
 
@@ -401,6 +573,55 @@ int launch_bn_act_bwd(int act, int training, const float* y, const float* scale,
         else          { if (T <= 4) SNN_BWD(ACT_SILU, 4, false); else if (T <= 8) SNN_BWD(ACT_SILU, 8, false); else SNN_BWD(ACT_SILU, 16, false); }
     }
 #undef SNN_BWD
+}
+
+template <int ACT, int TMAX, bool REDUCE>
+static int launch_bwd2_t(const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
+                         const float* beta_bn, const float* red_in, const float* v_init, const __nv_bfloat16* gs,
+                         const float* gv_final, __nv_bfloat16* dy, float* gv_init, float* red_out, float* dgamma, float* dbeta,
+                         int T, int P, int C, float beta, float theta, float alpha, cudaStream_t st) {
+    // channel range per block: largest C / 2^k (multiple of 4) whose tables fit in ~96 KB of shared memory
+    const int per_c = T * ((REDUCE ? 3 : 4) + (REDUCE ? 2 : 0)) * 4 + (REDUCE ? 0 : 4);
+    int Cb = C;
+    while (((size_t)Cb * per_c > 48 * 1024 || Cb > 512) && Cb % 4 == 0) Cb >>= 1;
+    SNN_REQUIRE(C % Cb == 0 && Cb % 2 == 0 && Cb <= 512 && (size_t)Cb * per_c <= 200 * 1024,
+                "bn_act_bwd2: cannot tile C=%d (T=%d) into shared memory", C, T);
+    const int rows = 256 / (Cb / 2);
+    const int nyb = C / Cb;
+    long long want_blocks = (long long)num_sms() * (REDUCE ? 4 : 8) / nyb;
+    if (want_blocks < 1) want_blocks = 1;
+    int ppb = (int)((P + want_blocks - 1) / want_blocks);
+    const int min_ppb = rows * (REDUCE ? 8 : 2);
+    if (ppb < min_ppb) ppb = min_ppb;
+    ppb = ((ppb + rows - 1) / rows) * rows;
+    const size_t smem = (size_t)Cb * per_c;
+    auto kern = bn_act_bwd2_kernel<ACT, TMAX, REDUCE>;
+    if (smem > 48 * 1024) SNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((P + ppb - 1) / ppb, nyb);
+    kern<<<grid, 256, smem, st>>>(y, scale, shift, mean, invstd, beta_bn, red_in, v_init, gs, gv_final, dy, gv_init, red_out,
+                                  dgamma, dbeta, T, P, C, Cb, ppb, beta, theta, alpha, 1.0f / (float)P);
+    return check_cuda(cudaGetLastError(), REDUCE ? "bn_act_bwd2_kernel<reduce>" : "bn_act_bwd2_kernel<dx>");
+}
+
+// pass = 0: reduce (writes red [T][2][C], zeroed here); pass = 1: dx (reads red; writes dy, gv_init; dgamma/dbeta +=)
+int launch_bn_act_bwd2(int pass, int act, const float* y, const float* scale, const float* shift, const float* mean,
+                       const float* invstd, const float* beta_bn, const float* v_init, const __nv_bfloat16* gs,
+                       const float* gv_final, float* red, __nv_bfloat16* dy, float* gv_init, float* dgamma, float* dbeta,
+                       int T, int P, int C, float beta, float theta, float alpha, cudaStream_t st) {
+    SNN_REQUIRE(C % 2 == 0 && C >= 2, "bn_act_bwd2: C=%d must be even", C);
+    SNN_REQUIRE(T >= 1 && T <= 16, "bn_act_bwd2: T=%d must be in [1,16]", T);
+    if (pass == 0) SNN_CUDA_OK(cudaMemsetAsync(red, 0, sizeof(float) * 2 * T * C, st));
+#define SNN_BWD2(ACT, TM)                                                                                                   \
+    return pass == 0 ? launch_bwd2_t<ACT, TM, true>(y, scale, shift, mean, invstd, beta_bn, nullptr, v_init, gs, gv_final,   \
+                                                    nullptr, nullptr, red, nullptr, nullptr, T, P, C, beta, theta, alpha, st) \
+                     : launch_bwd2_t<ACT, TM, false>(y, scale, shift, mean, invstd, beta_bn, red, v_init, gs, gv_final, dy,   \
+                                                     gv_init, nullptr, dgamma, dbeta, T, P, C, beta, theta, alpha, st)
+    if (act == ACT_LIF) {
+        if (T <= 4) SNN_BWD2(ACT_LIF, 4); else if (T <= 8) SNN_BWD2(ACT_LIF, 8); else SNN_BWD2(ACT_LIF, 16);
+    } else {
+        if (T <= 4) SNN_BWD2(ACT_SILU, 4); else if (T <= 8) SNN_BWD2(ACT_SILU, 8); else SNN_BWD2(ACT_SILU, 16);
+    }
+#undef SNN_BWD2
 }
 
 int launch_bn_bwd_dx(const float* red, const float* gamma, const float* gx, const float* y, const float* scale,

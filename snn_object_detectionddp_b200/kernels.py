@@ -56,24 +56,25 @@ def conv_fprop(geom, x0, w_bf16, cout, x1=None, bias=None, out=None, out_dtype=t
     assert w_coff + c0 + c1 <= wk and w_row_off + cout <= rows
     call("snn_conv_fprop", geom, nb, h, w, ptr(x0), c0, _nhwc_ld(x0), ptr(x1), c1, 0 if x1 is None else _nhwc_ld(x1),
          ptr(w_bf16), rows, wk, w_coff, cout, w_row_off, ptr(bias), ptr(out), int(out.dtype == torch.float32),
-         _nhwc_ld(out), 0, int(accumulate), stream_ptr(), work=("flop", _conv_flops(geom, nb, h, w, c0 + c1, cout)))
+         _nhwc_ld(out), 0, int(accumulate), stream_ptr(), work=("flop", _conv_flops(geom, nb, h, w, c0 + c1, cout), f"g{geom} nb{nb} {h}x{w} {c0 + c1}->{cout}"))
     return out
 
 
-def conv_dgrad(geom, dy, wt_bf16, in_hw, ci, ci_off=0, out=None, out_dtype=torch.bfloat16, accumulate=False):
-    """dx[NB,H,W,ci] for the conv-input channel range [ci_off, ci_off+ci); wt_bf16 = [Cin_tot][taps][Cout]."""
-    require_cuda(dy, wt_bf16, out)
+def conv_dgrad(geom, dy, w_bf16, in_hw, ci, ci_off=0, out=None, out_dtype=torch.bfloat16, accumulate=False):
+    """dx[NB,H,W,ci] for the conv-input channel range [ci_off, ci_off+ci); w_bf16 = the fprop weights
+    [Cout][taps][Cin_tot], read in place."""
+    require_cuda(dy, w_bf16, out)
     nb, hy, wy, cout = dy.shape
     h, w = in_hw
     assert out_hw(geom, h, w) == (hy, wy), (geom, in_hw, dy.shape)
-    rows, taps, wk = wt_bf16.shape
-    assert taps == GEOM_TAPS[geom] and wk == cout and ci_off + ci <= rows
-    assert dy.dtype == torch.bfloat16 and wt_bf16.dtype == torch.bfloat16 and wt_bf16.is_contiguous()
+    rows, taps, wk = w_bf16.shape
+    assert taps == GEOM_TAPS[geom] and rows == cout and ci_off + ci <= wk
+    assert dy.dtype == torch.bfloat16 and w_bf16.dtype == torch.bfloat16 and w_bf16.is_contiguous()
     if out is None:
         out = torch.empty((nb, h, w, ci), device=dy.device, dtype=out_dtype)
-    call("snn_conv_dgrad", geom, nb, h, w, ptr(dy), cout, _nhwc_ld(dy), ptr(wt_bf16), rows, ci_off, ci, ptr(out),
+    call("snn_conv_dgrad", geom, nb, h, w, ptr(dy), cout, _nhwc_ld(dy), ptr(w_bf16), wk, ci_off, ci, ptr(out),
          int(out.dtype == torch.float32), _nhwc_ld(out), 0, int(accumulate), stream_ptr(),
-         work=("flop", _conv_flops(geom, nb, h, w, ci, cout)))
+         work=("flop", _conv_flops(geom, nb, h, w, ci, cout), f"g{geom} nb{nb} {h}x{w} {ci}<-{cout}"))
     return out
 
 
@@ -87,7 +88,7 @@ def conv_wgrad(geom, x, dy, dw, w_coff=0):
     assert rows == cout and taps == GEOM_TAPS[geom] and w_coff + ci <= wk
     assert dw.dtype == torch.float32 and dw.is_contiguous() and x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16
     call("snn_conv_wgrad", geom, nb, h, w, ptr(x), ci, _nhwc_ld(x), ptr(dy), cout, _nhwc_ld(dy), ptr(dw), wk, w_coff,
-         stream_ptr(), work=("flop", _conv_flops(geom, nb, h, w, ci, cout)))
+         stream_ptr(), work=("flop", _conv_flops(geom, nb, h, w, ci, cout), f"g{geom} nb{nb} {h}x{w} {ci}x{cout}"))
     return dw
 
 
@@ -143,7 +144,7 @@ def bn_act_fwd(act, y, scale, shift, T, v_init=None, want_mask=True, want_v_fina
     nbytes = y.numel() * (6.0 + (0.125 if mask is not None else 0.0))
     nbytes += (0 if v_init is None else 4.0 * n_per_t) + (0 if v_final is None else 4.0 * n_per_t)
     call("snn_bn_act_fwd", act, ptr(y), ptr(scale), ptr(shift), ptr(v_init), ptr(out), ptr(mask), ptr(v_final), T, n_per_t,
-         c, ss, float(beta), float(theta), stream_ptr(), work=("byte", nbytes))
+         c, ss, float(beta), float(theta), stream_ptr(), work=("byte", nbytes, f"T{T} n{n_per_t} C{c}"))
     return out, mask, v_final
 
 
@@ -166,6 +167,27 @@ def bn_act_bwd(act, training, y, scale, shift, mean, invstd, gs, T, v_init=None,
          ptr(gv_final), ptr(gx), ptr(dy), ptr(gv_init), ptr(red), T, p, c, ss, float(beta), float(theta), float(alpha),
          stream_ptr(), work=("byte", nbytes))
     return gx, dy, gv_init, red
+
+
+def bn_act_bwd_train(act, y, scale, shift, mean, invstd, beta_bn, gs, T, dgamma, dbeta, v_init=None, gv_final=None,
+                     want_gv_init=False, beta=0.5, theta=1.0, alpha=2.0):
+    """Train-mode (batch-statistics) backward of BN -> LIF|SiLU in two recompute passes (no fp32 gx round trip).
+    Returns (dy bf16, gv_init | None, red [T][2][C]); dgamma / dbeta (fp32 [C]) are accumulated into."""
+    require_cuda(y, gs)
+    c = y.shape[-1]
+    p = y.numel() // (T * c)
+    dev = y.device
+    assert gs.dtype == torch.bfloat16 and gs.is_contiguous() and y.is_contiguous()
+    assert scale.shape[0] == T and mean.shape[0] == T
+    red = torch.empty((T, 2, c), device=dev, dtype=torch.float32)
+    dy = torch.empty(y.shape, device=dev, dtype=torch.bfloat16)
+    gv_init = torch.empty((p * c,), device=dev, dtype=torch.float32) if want_gv_init else None
+    args = (ptr(y), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(beta_bn), ptr(v_init), ptr(gs), ptr(gv_final), ptr(red),
+            ptr(dy), ptr(gv_init), ptr(dgamma), ptr(dbeta), T, p, c, float(beta), float(theta), float(alpha), stream_ptr())
+    tag = f"T{T} n{p * c} C{c}"
+    call("snn_bn_act_bwd2", 0, act, *args, work=("byte", 6.0 * y.numel(), "reduce " + tag))   # reads y fp32 + gs bf16
+    call("snn_bn_act_bwd2", 1, act, *args, work=("byte", 8.0 * y.numel(), "dx " + tag))       # reads y + gs, writes dy bf16
+    return dy, gv_init, red
 
 
 def bn_bwd_dx(red, gamma, gx, y, scale, mean, invstd, dgamma, dbeta, T):
@@ -233,9 +255,11 @@ def grad_sumsq(g, acc, zero_first=True):
     call("snn_grad_sumsq", ptr(g), g.numel(), ptr(acc), int(zero_first), stream_ptr(), work=("byte", 4.0 * g.numel()))
 
 
-def adamw_step(p, g, m, v, shadow, hp, sumsq, gnorm_out=None):
+def adamw_step(p, g, m, v, shadow, hp, sumsq, gnorm_out=None, step=None):
+    """hp: one row of 8 floats, or (with `step`, a device int32 scalar) the whole [rows, 8] schedule table."""
+    n_rows = hp.shape[0] if (step is not None and hp.dim() == 2) else 1
     call("snn_adamw_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), p.numel(), ptr(hp), ptr(sumsq), ptr(gnorm_out),
-         stream_ptr(), work=("byte", (28.0 + (2.0 if shadow is not None else 0.0)) * p.numel()))
+         ptr(step), n_rows, stream_ptr(), work=("byte", (28.0 + (2.0 if shadow is not None else 0.0)) * p.numel()))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -90,14 +90,18 @@ def task_aligned_assign(pd_scores, pd_bboxes, anc_points, gt_labels, gt_bboxes, 
     return t_boxes.contiguous(), (t_scores * norm).contiguous(), (fg > 0).to(torch.uint8).contiguous()
 
 
-def pad_targets(labels, batch_size, device=None):
+def pad_targets(labels, batch_size, device=None, max_boxes=None):
     """[M,6] rows (batch_idx, cls, cx, cy, w, h) (reference train.py:10-44 collate layout) -> dense
-    (cls long [B,Mx], xywh fp32 [B,Mx,4], valid bool [B,Mx]).  Done where the labels live: call it on the HOST
+    (cls long [B,Mx], xywh fp32 [B,Mx,4], valid bool [B,Mx]); Mx = max boxes per sample, or `max_boxes` if given.  Done where the labels live: call it on the HOST
     tensors of the input pipeline and nothing in the loss has to synchronise."""
     labels = labels.detach()
     idx = labels[:, 0].long()
     counts = torch.bincount(idx, minlength=batch_size) if labels.shape[0] else labels.new_zeros(batch_size, dtype=torch.long)
     mx = max(int(counts.max()) if labels.shape[0] else 0, 1)
+    if max_boxes is not None:          # fixed shape (CUDA-graph replay needs static shapes)
+        if mx > max_boxes:
+            raise ValueError(f"a sample has {mx} boxes > max_boxes={max_boxes}")
+        mx = max_boxes
     order = torch.argsort(idx, stable=True)
     sl = labels[order]
     starts = torch.cumsum(counts, 0) - counts
@@ -123,6 +127,7 @@ class v8DetectionLoss:
         self.topk = tal_topk
         self._gains = None
         self._anchor_cache = {}
+        self._scale_cache = {}
 
     def _anchors(self, shapes, device):
         key = (tuple(shapes), str(device))
@@ -157,8 +162,10 @@ class v8DetectionLoss:
                              batch["bboxes"].view(-1, 4).float()), 1)
             cls, box, valid = pad_targets(lab, B, dev)
         H, W = shapes[0][0] * self.stride[0], shapes[0][1] * self.stride[0]
+        if (H, W, str(dev)) not in self._scale_cache:
+            self._scale_cache[(H, W, str(dev))] = torch.tensor([W, H, W, H], device=dev, dtype=torch.float32)
+        scale = self._scale_cache[(H, W, str(dev))]
         with torch.no_grad():
-            scale = torch.tensor([W, H, W, H], device=dev, dtype=torch.float32)
             xy, wh = box[..., :2] * scale[:2], box[..., 2:] * scale[2:] / 2
             gt_xyxy = torch.cat((xy - wh, xy + wh), -1) * valid[..., None]
             mask_gt = valid & (gt_xyxy.sum(-1) > 0)

@@ -77,15 +77,18 @@ class ConvBNActFn(Function):
         gs = _bf16c(g_out)
         gvf = None if g_vfinal is None else g_vfinal.contiguous().view(-1).float()
         want_gv0 = ctx.has_v and ctx.needs_input_grad[2]
-        gx, dy, gv0, red = K.bn_act_bwd(neuron.act, training, y, scale, shift, mean, invstd, gs, T, v_init=v_init,
-                                        gv_final=gvf, want_gv_init=want_gv0, beta=neuron.beta, theta=neuron.v_th,
-                                        alpha=neuron.alpha)
         if training:
             dgamma = st.grad_view(cfg["bn"].weight)
             dbeta = st.grad_view(cfg["bn"].bias)
-            dy = K.bn_bwd_dx(red, gamma, gx, y, scale, mean, invstd, dgamma, dbeta, T)
+            dy, gv0, _ = K.bn_act_bwd_train(neuron.act, y, scale, shift, mean, invstd, cfg["bn"].bias, gs, T, dgamma, dbeta,
+                                            v_init=v_init, gv_final=gvf, want_gv_init=want_gv0, beta=neuron.beta,
+                                            theta=neuron.v_th, alpha=neuron.alpha)
             st.grad_done(cfg["bn"].weight)
             st.grad_done(cfg["bn"].bias)
+        else:
+            _, dy, gv0, _ = K.bn_act_bwd(neuron.act, False, y, scale, shift, mean, invstd, gs, T, v_init=v_init,
+                                         gv_final=gvf, want_gv_init=want_gv0, beta=neuron.beta, theta=neuron.v_th,
+                                         alpha=neuron.alpha)
         gw3 = st.grad_view(weight, three_d=True)
         if geom == K.GEOM_DW3x3:
             c = weight.shape[0]
@@ -100,9 +103,9 @@ class ConvBNActFn(Function):
         gx0 = gx1 = None
         in_hw = (x0.shape[1], x0.shape[2])
         if ctx.needs_input_grad[0]:
-            gx0 = K.conv_dgrad(geom, dy, st.w_dgrad(weight), in_hw, x0.shape[3], ci_off=0)
+            gx0 = K.conv_dgrad(geom, dy, st.w_fprop(weight), in_hw, x0.shape[3], ci_off=0)
         if ctx.has_x1 and ctx.needs_input_grad[1]:
-            gx1 = K.conv_dgrad(geom, dy, st.w_dgrad(weight), in_hw, x1.shape[3], ci_off=x0.shape[3])
+            gx1 = K.conv_dgrad(geom, dy, st.w_fprop(weight), in_hw, x1.shape[3], ci_off=x0.shape[3])
         if gv0 is not None:
             gv0 = gv0.view(v_init.shape)
         return gx0, gx1, gv0, None, None, None, None
@@ -134,7 +137,7 @@ class ConvBiasFn(Function):
             st.grad_done(bias)
         gx0 = None
         if ctx.needs_input_grad[0]:
-            gx0 = K.conv_dgrad(geom, dy, st.w_dgrad(weight), (x0.shape[1], x0.shape[2]), x0.shape[3])
+            gx0 = K.conv_dgrad(geom, dy, st.w_fprop(weight), (x0.shape[1], x0.shape[2]), x0.shape[3])
         return gx0, None, None, None
 
 
@@ -179,7 +182,7 @@ class ConvLSTMSeqFn(Function):
         ch = weight.shape[0] // 4
         nb, hh, ww, cx = x.shape
         B = nb // T
-        wt = st.w_dgrad(weight)
+        wt = st.w_fprop(weight)
         dgates = torch.empty(gates.shape, device=x.device, dtype=torch.bfloat16)
         dh_rec = None if g_hlast is None else g_hlast.float()
         dc = None if g_clast is None else g_clast.contiguous().float()

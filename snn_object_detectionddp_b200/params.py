@@ -4,7 +4,7 @@ tensor-core operand copies for every trainable tensor of a model.
 Why: (a) the optimizer (reference train.py:77-78: clip_grad_norm_ + AdamW.step) becomes two passes
 over ONE contiguous buffer; (b) DDP buckets are contiguous ranges of the gradient buffer (no
 flatten/unflatten copies); (c) conv weights are kept physically in the [Cout][kh*kw][Cin] order the TMA
-tensor maps want, while ``nn.Parameter`` objects keep the reference's logical shapes and names
+tensor maps want (one bf16 copy serves fprop and dgrad), while ``nn.Parameter`` objects keep the reference's logical shapes and names
 (``state_dict`` / checkpoints interchange with the reference).
 """
 import weakref
@@ -76,11 +76,10 @@ class ParamStore:
                 self.by_param[id(p)] = e
                 off += (e.numel + _PAD - 1) // _PAD * _PAD
         self.total = off
-        self.flat_p = self.flat_g = self.flat_m = self.flat_v = self.shadow = self.flat_wt = None
+        self.flat_p = self.flat_g = self.flat_m = self.flat_v = self.shadow = None
         self.device = None
         self._versions = None
         self.opt_epoch = 0           # bumped by the fused optimizer (it rewrites master + shadow)
-        self._wt_epoch = -1
         self.grad_epoch = 0          # bumped by zero_grad(); used by DDP bucket bookkeeping
         self.grad_ready_hook = None  # callable(entry) fired right after an entry's gradient is complete
         for e in self.entries:
@@ -110,42 +109,32 @@ class ParamStore:
         self.flat_m = old_m if keep else torch.zeros(self.total, device=device, dtype=torch.float32)
         self.flat_v = old_v if keep else torch.zeros(self.total, device=device, dtype=torch.float32)
         self.shadow = torch.zeros(self.total, device=device, dtype=torch.bfloat16)
-        self.flat_wt = torch.zeros(self.total, device=device, dtype=torch.bfloat16)
         self.device = device
         for e in self.entries:
             e.param.data = e.logical_view(self.flat_p)
             e.param.grad = None
         self._versions = None
-        self._wt_epoch = -1
         return self
 
     # -- bf16 operand copies ---------------------------------------------------------------
     def refresh_operands(self):
-        """Make shadow (bf16 [N][T][K]) and flat_wt (bf16 [K][T][N]) current."""
+        """Make `shadow` (bf16 copy of every conv weight, same [Cout][tap][Cin] layout) current.  The fused optimizer
+        writes the shadow itself, so this only does work after the masters were changed some other way
+        (init, load_state_dict, an external optimizer)."""
         vers = tuple(e.param._version for e in self.entries)
-        stale_master = vers != self._versions
-        if not stale_master and self._wt_epoch == self.opt_epoch:
+        if vers == self._versions:
             return
         for e in self.entries:
             if e.kind in ("conv", "convT"):
-                n, t, k = e.shape3
-                wf = self.shadow[e.offset:e.offset + e.numel].view(n, t, k) if stale_master else None
-                wt = self.flat_wt[e.offset:e.offset + e.numel].view(k, t, n)
-                K.weight_prep(e.view3(self.flat_p), want_fprop=stale_master, want_dgrad=True, wf=wf, wt=wt)
+                K.weight_prep(e.view3(self.flat_p), want_fprop=True, want_dgrad=False, wf=e.view3(self.shadow))
         self._versions = vers
-        self._wt_epoch = self.opt_epoch
 
     def w_fprop(self, p):
-        e = self.by_param[id(p)]
-        return e.view3(self.shadow)
+        """bf16 [Cout][taps][Cin] operand of fprop AND dgrad (dgrad reads it MN-major in place)."""
+        return self.by_param[id(p)].view3(self.shadow)
 
     def w_master3(self, p):
         return self.by_param[id(p)].view3(self.flat_p)
-
-    def w_dgrad(self, p):
-        e = self.by_param[id(p)]
-        n, t, k = e.shape3
-        return self.flat_wt[e.offset:e.offset + e.numel].view(k, t, n)
 
     # -- gradients -------------------------------------------------------------------------
     def zero_grad(self):

@@ -54,6 +54,9 @@ class Trainer:
         self.hp = one_cycle_table(total_steps, max_lr, weight_decay, max_norm=max_norm).float().to(self.device)
         self.total_steps = total_steps
         self.step_idx = 0
+        self._step_dev = torch.zeros(1, device=self.device, dtype=torch.int32)     # device-side schedule cursor
+        self._graph = self._graph_key = None
+        self._eager_calls = 0
         self._sumsq = torch.zeros(1, device=self.device, dtype=torch.float64)
         self.grad_norm = torch.zeros(1, device=self.device, dtype=torch.float32)
         self.group = process_group
@@ -73,9 +76,10 @@ class Trainer:
         return nxt - e.offset
 
     # ------------------------------------------------------------------------------------------
-    def prepare_batch(self, labels, batch_size):
-        """Host-side label padding ([M,6] collate layout, train.py:27-37) -> dict accepted by the loss."""
-        return {"padded": pad_targets(labels, batch_size)}
+    def prepare_batch(self, labels, batch_size, max_boxes=None):
+        """Host-side label padding ([M,6] collate layout, train.py:27-37) -> dict accepted by the loss.
+        Pass `max_boxes` for a fixed shape (required by train_step_graphed)."""
+        return {"padded": pad_targets(labels, batch_size, max_boxes=max_boxes)}
 
     def train_step(self, frames, batch):
         """frames fp32 [B,T,3,H,W] on the device; batch = {'batch_idx','cls','bboxes'} (train.py:68-72) or
@@ -96,10 +100,46 @@ class Trainer:
     def optimizer_step(self):
         st = self.store
         K.grad_sumsq(st.flat_g, self._sumsq)
-        row = self.hp[min(self.step_idx, self.total_steps - 1)]
-        K.adamw_step(st.flat_p, st.flat_g, st.flat_m, st.flat_v, st.shadow, row, self._sumsq, self.grad_norm)
+        K.adamw_step(st.flat_p, st.flat_g, st.flat_m, st.flat_v, st.shadow, self.hp, self._sumsq, self.grad_norm,
+                     step=self._step_dev)
         st.opt_epoch += 1
         self.step_idx += 1
+
+    # ------------------------------------------------------------------------------------------
+    def train_step_graphed(self, frames, batch, warmup_calls=2):
+        """Same step, replayed from ONE captured CUDA graph (the ~1000 kernel launches of a step cost more host
+        time than device time otherwise).  `batch` must be prepare_batch(..., max_boxes=M) so shapes are static.
+        The first `warmup_calls` calls run eagerly (they are real steps); the next call captures, then replays.
+        Returned tensors are the graph's static outputs: read them before the next call."""
+        padded = batch["padded"]
+        key = (tuple(frames.shape), tuple(tuple(t.shape) for t in padded))
+        if self.bucketer is not None:
+            return self.train_step(frames, batch)          # collectives stay outside graphs
+        if self._graph is not None and self._graph_key != key:
+            self._graph, self._eager_calls = None, max(0, warmup_calls - 1)      # new shapes: one eager step, re-capture
+        if self._graph is None:
+            if self._eager_calls < warmup_calls:
+                self._eager_calls += 1
+                return self.train_step(frames, {"padded": tuple(t.to(self.device) for t in padded)})
+            self._static_frames = frames.clone()
+            self._static_padded = tuple(t.to(self.device).clone() for t in padded)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.train_step(self._static_frames, {"padded": self._static_padded})
+            self.step_idx -= 1                 # capture records the launches without running them
+            self.store.opt_epoch -= 1
+            self._graph, self._graph_key, self._static_out = g, key, out
+        st = self.store
+        if tuple(e.param._version for e in st.entries) != st._versions:
+            st.refresh_operands()              # masters were modified outside the optimizer (e.g. load_state_dict)
+        self._static_frames.copy_(frames, non_blocking=True)
+        for s_, t_ in zip(self._static_padded, padded):
+            s_.copy_(t_, non_blocking=True)
+        self._graph.replay()
+        self.step_idx += 1
+        st.opt_epoch += 1
+        return self._static_out
 
     def lr(self):
         return float(self.hp[min(self.step_idx, self.total_steps - 1), 0])

@@ -121,17 +121,16 @@ def test_dgrad(geom, nb, h, w, cin, cout):
     K = _k()
     taps = {G31: 9, G32: 9, G11: 1, GT: 4}[geom]
     wgt = _mkw(cout, taps, cin, 11)
-    wt = wgt.permute(2, 1, 0).contiguous()       # [Cin][taps][Cout]
     x = _mk(nb, h, w, cin, 12).float().requires_grad_(True)
     y = ref_conv(geom, x, wgt)
     dy = torch.randn(y.shape, device="cuda").to(torch.bfloat16)
     (gx_ref,) = torch.autograd.grad(y, x, dy.float())
-    gx = K.conv_dgrad(geom, dy, wt, (h, w), cin, out_dtype=torch.float32)
+    gx = K.conv_dgrad(geom, dy, wgt, (h, w), cin, out_dtype=torch.float32)
     assert rel_err(gx, gx_ref) < 1e-5, describe_mismatch(gx, gx_ref)
-    gxb = K.conv_dgrad(geom, dy, wt, (h, w), cin)
+    gxb = K.conv_dgrad(geom, dy, wgt, (h, w), cin)
     assert rel_err(gxb, gx_ref) < 4e-3
     if cin >= 128:   # channel sub-range (concat inputs get separate dgrads)
-        part = K.conv_dgrad(geom, dy, wt, (h, w), 64, ci_off=64, out_dtype=torch.float32)
+        part = K.conv_dgrad(geom, dy, wgt, (h, w), 64, ci_off=64, out_dtype=torch.float32)
         assert rel_err(part, gx_ref[..., 64:128]) < 1e-5
 
 

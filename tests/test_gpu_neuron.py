@@ -232,3 +232,46 @@ def test_clip_adamw_matches_torch():
         assert abs(float(gn) - float(ref_norm)) < 1e-3 * float(ref_norm)
         assert rel_err(p, pt.data) < 1e-6
     assert torch.equal(shadow, p.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("act", [LIF, SILU])
+@pytest.mark.parametrize("T,B,H,W,C", [(4, 2, 8, 8, 128), (8, 2, 4, 4, 256), (5, 2, 4, 4, 1024), (16, 1, 4, 4, 64),
+                                       (4, 1, 8, 8, 144), (16, 2, 2, 2, 1024), (1, 2, 8, 8, 128), (4, 3, 5, 7, 72)])
+def test_recompute_backward_matches_autograd(act, T, B, H, W, C):
+    """2-pass recompute backward (snn_bn_act_bwd2) vs torch autograd through per-timestep batch-stat BN + LIF|SiLU."""
+    setup_exact()
+    K = _k()
+    P = B * H * W
+    y, gamma, beta = _data(T, B, H, W, C, seed=6)
+    y = y + 0.7                                  # non-zero channel means: exercises the (y - mean) accumulation
+    gs = torch.randn(T * B, H, W, C, device="cuda").to(torch.bfloat16)
+    v0 = torch.rand(B, H, W, C, device="cuda") * 0.5 if act == LIF else None
+    gvf = torch.randn(B, H, W, C, device="cuda") if act == LIF else None
+    sums = K.bn_stats(y, T)
+    scale, shift, mean, invstd = K.bn_finalize(sums, gamma, beta, None, None, T, C, P, 1e-5, 0.1, True)
+    out, _, _ = K.bn_act_fwd(act, y, scale, shift, T, v_init=v0)
+    dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dy, gv0, red = K.bn_act_bwd_train(act, y, scale, shift, mean, invstd, beta, gs, T, dgamma, dbeta, v_init=v0,
+                                      gv_final=None if gvf is None else gvf.reshape(-1), want_gv_init=act == LIF)
+    yr = y.clone().requires_grad_(True)
+    g_r, b_r = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yt = yr.reshape(T, P, C)
+    m = yt.mean(1, keepdim=True)
+    var = yt.var(1, unbiased=False, keepdim=True)
+    x = (yt - m) / torch.sqrt(var + 1e-5) * g_r + b_r
+    if act == LIF:
+        v0r = v0.clone().reshape(P, C).requires_grad_(True)
+        s, vfin, u = O.lif_sequence(x, v0r)
+        flips = int((s.detach() != out.reshape(s.shape).float()).sum())
+        loss = (s * gs.float().reshape(s.shape)).sum() + (vfin * gvf.reshape(P, C)).sum()
+        gy_ref, gg_ref, gb_ref, gv0_ref = torch.autograd.grad(loss, (yr, g_r, b_r, v0r))
+    else:
+        s = torch.nn.functional.silu(x)
+        flips = 0
+        loss = (s * gs.float().reshape(s.shape)).sum()
+        gy_ref, gg_ref, gb_ref = torch.autograd.grad(loss, (yr, g_r, b_r))
+    if flips == 0:
+        assert rel_err(dy, gy_ref) < 4e-3
+        assert rel_err(dgamma, gg_ref) < 2e-4 and rel_err(dbeta, gb_ref) < 2e-4
+        if act == LIF:
+            assert rel_err(gv0.reshape(P, C), gv0_ref) < 1e-4
