@@ -224,7 +224,7 @@ def run_ours(args):
     frames = frames_cpu.to(dev)
     MAXB = 8                                              # synthetic labels: 0-7 boxes per sample
     batch_dev = {"padded": tuple(t.to(dev) for t in trainer.prepare_batch(labels_cpu, B, max_boxes=MAXB)["padded"])}
-    graphed = world == 1 and not args.no_graph
+    graphed = not args.no_graph
     step_fn = trainer.train_step_graphed if graphed else trainer.train_step
 
     def barrier():
@@ -374,6 +374,7 @@ def run_ours(args):
                    "l2": "per-step working set (240 MB bf16 weights + GBs of activations) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world}", "feature_extractor": "stand-in frozen pyramid (YOLO11m weights unobtainable offline)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "cuda_graph_active": bool(graphed and trainer._graph is not None and not trainer._graph_failed),
         "kernels": kernels_summary, "kernels_by_shape": getattr(summarize_profile, "by_shape", None), "last_loss_items": last_loss, "cuda_graph": graphed,
         "kernel_ms_sum_per_step": (sum(v["ms_per_step"] for v in kernels_summary.values()) if kernels_summary else None),
         "eager_instrumented_ms_per_step": (eager_ms_total / args.steps if kernels_summary else None),

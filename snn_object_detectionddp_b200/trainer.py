@@ -56,6 +56,7 @@ class Trainer:
         self.step_idx = 0
         self._step_dev = torch.zeros(1, device=self.device, dtype=torch.int32)     # device-side schedule cursor
         self._graph = self._graph_key = None
+        self._graph_failed = False
         self._eager_calls = 0
         self._sumsq = torch.zeros(1, device=self.device, dtype=torch.float64)
         self.grad_norm = torch.zeros(1, device=self.device, dtype=torch.float32)
@@ -113,8 +114,8 @@ class Trainer:
         Returned tensors are the graph's static outputs: read them before the next call."""
         padded = batch["padded"]
         key = (tuple(frames.shape), tuple(tuple(t.shape) for t in padded))
-        if self.bucketer is not None:
-            return self.train_step(frames, batch)          # collectives stay outside graphs
+        if self._graph_failed:
+            return self.train_step(frames, {"padded": tuple(t.to(self.device) for t in padded)})
         if self._graph is not None and self._graph_key != key:
             self._graph, self._eager_calls = None, max(0, warmup_calls - 1)      # new shapes: one eager step, re-capture
         if self._graph is None:
@@ -125,8 +126,16 @@ class Trainer:
             self._static_padded = tuple(t.to(self.device).clone() for t in padded)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                out = self.train_step(self._static_frames, {"padded": self._static_padded})
+            try:
+                # the bucketed NCCL all-reduces are captured too (side-stream branches of the graph overlapping backward)
+                with torch.cuda.graph(g):
+                    out = self.train_step(self._static_frames, {"padded": self._static_padded})
+            except Exception as e:             # e.g. a collective backend that cannot be captured: stay eager, loudly
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the training step failed ({type(e).__name__}: {e}); running eagerly")
+                torch.cuda.synchronize()
+                self._graph_failed = True
+                return self.train_step(frames, {"padded": tuple(t.to(self.device) for t in padded)})
             self.step_idx -= 1                 # capture records the launches without running them
             self.store.opt_epoch -= 1
             self._graph, self._graph_key, self._static_out = g, key, out
