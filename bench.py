@@ -351,11 +351,22 @@ def run_ours(args):
         if os.path.isfile(tr):
             roofline["traffic"] = json.load(open(tr)).get(name)
 
+    def shutdown():
+        """Leave without waiting on NCCL teardown: the captured graph still references the communicator's kernels and
+        destroy_process_group() was seen to block for minutes on the 2-GPU box after the result line was out."""
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if world > 1:
+            trainer._graph = None
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
     if world > 1:
         dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
 
     cpu_baseline = None
@@ -380,8 +391,7 @@ def run_ours(args):
         "eager_instrumented_ms_per_step": (eager_ms_total / args.steps if kernels_summary else None),
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 # ------------------------------------------------------------------------------------------------

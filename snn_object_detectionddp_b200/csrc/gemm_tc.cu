@@ -52,6 +52,8 @@ struct ConvGemmParams {
     int nphase;
     int b_mn;                         // B operand MN-major: weights [K rows][tap][N contiguous] read in place (dgrad)
     int b_boxes;                      // b_mn: number of 64-column boxes per stage
+    int tma_out;                      // epilogue through swizzled smem staging + TMA tensor stores (coalesced) instead of per-thread rows
+    int dbg;                          // timing experiments only: bit 0 = producer skips the TMA loads, bit 1 = no MMA issue
     Phase phase[4];
 };
 
@@ -86,11 +88,18 @@ constexpr int kTmemCols = 256;
 // Persistent: one CTA per SM walks tiles (m-tile fastest, so co-resident CTAs share the weight tile in L2); the
 // accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the main loop of
 // tile i+1.  Pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+//
+// PAIR = true: the two CTAs of a cluster work on ONE 256-pixel x BN tile with tcgen05 cta_group::2.  Each CTA stages
+// its own 128 pixels of A and only HALF of the weight tile (BN/2 columns), the leader CTA issues the MMAs for both.
+// Why: profiles/r1 shows every large conv pinned at 10-13 TB/s of L2->SM traffic (the fabric cap), i.e. bound by
+// operand bytes per flop, M*N/(M+N) = 85 flop/B for a 128x256 single-CTA tile; the pair tile is 128 flop/B.
 constexpr int kAccCols = 256;
 
+template <bool PAIR>
 __global__ void __launch_bounds__(192, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                 const __grid_constant__ ConvGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -98,20 +107,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_s;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp: provably uniform
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int stages = p.stages;
-    const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
-    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int total_tiles = m_tiles * p.n_blocks * p.nphase;
+    const uint32_t stage_bytes = (uint32_t)p.stage_bytes;     // per CTA
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;      // 0 = leader (MMA issuer)
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;    // 128-pixel tiles
+    const int m_work = PAIR ? (m_tiles + 1) >> 1 : m_tiles;   // work items along M (pairs of m-tiles)
+    const int total_tiles = m_work * p.n_blocks * p.nphase;
+    const int bn_cta = PAIR ? p.BN >> 1 : p.BN;               // B columns staged by this CTA
 
     if (warp == 0) {
         if (lane == 0) {
             tma_prefetch_desc(&tmA0);
             tma_prefetch_desc(&tmA1);
             tma_prefetch_desc(&tmB);
+            if (p.tma_out) tma_prefetch_desc(&tmO);
         }
-        tmem_alloc<2 * kAccCols>(smem_u32(&tmem_base_s));
+        __syncwarp();
+        if (PAIR) tmem_alloc_pair<2 * kAccCols>(smem_u32(&tmem_base_s));
+        else tmem_alloc<2 * kAccCols>(smem_u32(&tmem_base_s));
     } else if (warp == 1 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
@@ -119,75 +136,112 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-            mbar_init(smem_u32(&tmem_empty_bar[a]), 4);   // one arrive per epilogue warp
+            mbar_init(smem_u32(&tmem_empty_bar[a]), PAIR ? 8 : 4);   // one arrive per epilogue warp (of both CTAs)
         }
         mbar_fence_init();
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
+    // Both role loops below run WARP-UNIFORM (all 32 lanes walk the loop, one elected lane issues the TMA / MMA
+    // instructions): loop state then lives in uniform registers and the per-chunk instruction count of the issuing
+    // thread -- which, not the tensor pipe, bounded v1 at ~635 cycles per 64-wide K chunk -- drops several-fold.
     if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile % m_tiles, rest = tile / m_tiles;
-                const int ncol0 = (rest % p.n_blocks) * p.BN;
-                const Phase& ph = p.phase[rest / p.n_blocks];
-                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-                const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-                for (int sg = 0; sg < ph.nseg; ++sg) {
-                    const Seg g = ph.seg[sg];
-                    const CUtensorMap* tmA = g.src ? &tmA1 : &tmA0;
-                    for (int kc = 0; kc < g.nchunk; ++kc, ++it) {
-                        const int s = it % stages;
-                        const uint32_t par = (uint32_t)((it / stages) & 1);
-                        mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
+        const bool lead = elect_one();
+        int s = 0;
+        uint32_t par = 0;
+        uint32_t a_s = sbase;
+        for (int tile = worker; tile < total_tiles; tile += nworkers) {
+            const int mt = (tile % m_work) * (PAIR ? 2 : 1) + (int)rank, rest = tile / m_work;
+            const int ncol0 = p.wn_off + (rest % p.n_blocks) * p.BN + (int)rank * bn_cta;
+            const Phase& ph = p.phase[rest / p.n_blocks];
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+            const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;   // tn == tiles_n (odd tail of a pair): all OOB -> zeros
+            const int nseg = ph.nseg;
+            for (int sg = 0; sg < nseg; ++sg) {
+                const Seg g = ph.seg[sg];
+                const CUtensorMap* tmA = g.src ? &tmA1 : &tmA0;
+                const int cw = w0 + g.dw, chh = h0 + g.dh;
+                int ca = g.dc, cb = g.wc0;
+                for (int kc = 0; kc < g.nchunk; ++kc, ca += 64, cb += 64) {
+                    mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
+                    if (lead) {
                         const uint32_t fb = smem_u32(&full_bar[s]);
-                        mbar_expect_tx(fb, stage_bytes);
-                        const uint32_t a_s = sbase + (uint32_t)s * stage_bytes;
-                        tma_load_5d(a_s, tmA, fb, g.dc + kc * 64, w0 + g.dw, g.dhp, h0 + g.dh, n0);
-                        if (!p.b_mn) {
-                            tma_load_3d(a_s + 16384u, &tmB, fb, g.wc0 + kc * 64, g.wtap, p.wn_off + ncol0);
-                        } else {  // [64 K rows] x [64 N] boxes, one per 64 output columns
-                            for (int nb = 0; nb < p.b_boxes; ++nb)
-                                tma_load_3d(a_s + 16384u + (uint32_t)nb * 8192u, &tmB, fb, p.wn_off + ncol0 + nb * 64, g.wtap,
-                                            g.wc0 + kc * 64);
+                        if (p.dbg & 1) {
+                            if (rank == 0) mbar_arrive(fb);
+                        } else if (!PAIR) {
+                            mbar_expect_tx(fb, stage_bytes);
+                            tma_load_5d(a_s, tmA, fb, ca, cw, g.dhp, chh, n0);
+                            if (!p.b_mn) {
+                                tma_load_3d(a_s + 16384u, &tmB, fb, cb, g.wtap, ncol0);
+                            } else {  // [64 K rows] x [64 N] boxes, one per 64 output columns
+                                for (int nb = 0; nb < p.b_boxes; ++nb)
+                                    tma_load_3d(a_s + 16384u + (uint32_t)nb * 8192u, &tmB, fb, ncol0 + nb * 64, g.wtap, cb);
+                            }
+                        } else {
+                            if (rank == 0) mbar_expect_tx(fb, 2u * stage_bytes);      // both CTAs' bytes land on the leader's barrier
+                            tma_load_5d_pair(a_s, tmA, fb, ca, cw, g.dhp, chh, n0);
+                            if (!p.b_mn) {
+                                tma_load_3d_pair(a_s + 16384u, &tmB, fb, cb, g.wtap, ncol0);
+                            } else {
+                                for (int nb = 0; nb < p.b_boxes; ++nb)
+                                    tma_load_3d_pair(a_s + 16384u + (uint32_t)nb * 8192u, &tmB, fb, ncol0 + nb * 64, g.wtap, cb);
+                            }
                         }
                     }
+                    a_s += stage_bytes;
+                    if (++s == stages) { s = 0; par ^= 1u; a_s = sbase; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, p.b_mn);
-            int it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-                const Phase& ph = p.phase[(tile / m_tiles) / p.n_blocks];
+        if (rank == 0) {
+            const bool lead = elect_one();
+            const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, p.BN, 0, p.b_mn);
+            // smem matrix descriptors: high word constant (SBO = 1024 B, version 1, 128B swizzle); low word = address >> 4
+            // plus the leading-dimension offset field (K-major: unused = 16 B; MN-major B: 64-column blocks 8192 B apart)
+            const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t a_lo_c = (16u >> 4) << 16;
+            const uint32_t b_lo_c = (p.b_mn ? (8192u >> 4) : (16u >> 4)) << 16;
+            const uint32_t b_kstep = p.b_mn ? (2048u >> 4) : (32u >> 4);   // 16 K rows of 128 B | 32 B inside the 128 B row
+            const uint32_t dbg_nomma = (uint32_t)(p.dbg & 2);
+            int s = 0, lt = 0;
+            uint32_t par = 0;
+            uint32_t a_s = sbase;
+            for (int tile = worker; tile < total_tiles; tile += nworkers, ++lt) {
+                const Phase& ph = p.phase[(tile / m_work) / p.n_blocks];
                 int total = 0;
-                for (int s = 0; s < ph.nseg; ++s) total += ph.seg[s].nchunk;
+                for (int i = 0; i < ph.nseg; ++i) total += ph.seg[i].nchunk;
                 const int acc = lt & 1;
                 mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((lt >> 1) & 1) ^ 1));   // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(acc * kAccCols);
-                for (int j = 0; j < total; ++j, ++it) {
-                    const int s = it % stages;
-                    const uint32_t par = (uint32_t)((it / stages) & 1);
+                for (int j = 0; j < total; ++j) {
                     mbar_wait(smem_u32(&full_bar[s]), par);
                     tc_fence_after();
-                    const uint32_t a_s = sbase + (uint32_t)s * stage_bytes;
-                    const uint32_t b_s = a_s + 16384u;
+                    if (lead) {
+                        const uint32_t a_lo = a_lo_c | ((a_s & 0x3FFFFu) >> 4);
+                        const uint32_t b_lo = b_lo_c | (((a_s + 16384u) & 0x3FFFFu) >> 4);
+                        if (!dbg_nomma) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        // K-major B: 32 B per 16-wide K step inside the 128 B row; MN-major B: 16 K rows of 128 B = 2048 B,
-                        // 64-column blocks 8192 B apart (LBO), 8-row groups 1024 B apart (SBO)
-                        const uint64_t bdesc = p.b_mn ? umma_desc_sw128(b_s + k * 2048, 8192, 1024) : umma_desc_sw128(b_s + k * 32, 16, 1024);
-                        umma_bf16(tacc, umma_desc_sw128(a_s + k * 32, 16, 1024), bdesc, idesc, (uint32_t)((j | k) != 0));
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
+                                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + b_kstep * k);
+                                const uint32_t accf = k ? 1u : (uint32_t)(j != 0);
+                                if (PAIR) umma_bf16_pair(tacc, adesc, bdesc, idesc, accf);
+                                else umma_bf16(tacc, adesc, bdesc, idesc, accf);
+                            }
+                        }
+                        if (PAIR) umma_commit_pair(smem_u32(&empty_bar[s])); else umma_commit(smem_u32(&empty_bar[s]));
+                        if (j == total - 1) {
+                            if (PAIR) umma_commit_pair(smem_u32(&tmem_full_bar[acc])); else umma_commit(smem_u32(&tmem_full_bar[acc]));
+                        }
                     }
-                    umma_commit(smem_u32(&empty_bar[s]));
+                    a_s += stage_bytes;
+                    if (++s == stages) { s = 0; par ^= 1u; a_s = sbase; }
                 }
-                umma_commit(smem_u32(&tmem_full_bar[acc]));
             }
         }
     } else {
@@ -196,8 +250,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int row = q * 32 + lane;
         const int wl = row % p.bw, hl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
         int lt = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-            const int mt = tile % m_tiles, rest = tile / m_tiles;
+        for (int tile = worker; tile < total_tiles; tile += nworkers, ++lt) {
+            const int mt = (tile % m_work) * (PAIR ? 2 : 1) + (int)rank, rest = tile / m_work;
             const int ncol0 = (rest % p.n_blocks) * p.BN;
             const Phase& ph = p.phase[rest / p.n_blocks];
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
@@ -208,6 +262,78 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_wait(smem_u32(&tmem_full_bar[acc]), (uint32_t)((lt >> 1) & 1));
             tc_fence_after();
             const uint32_t trow = tmem_base + (uint32_t)(acc * kAccCols) + ((uint32_t)(q * 32) << 16);
+            if (p.tma_out) {
+                // Coalesced epilogue: 32 rows x 128 B of the accumulator go through a 128B-swizzled staging tile (thread =
+                // row; the XOR keeps the 16-byte stores of a quarter-warp on distinct banks) and leave with ONE TMA
+                // tensor store per warp and chunk.  The v1 epilogue (thread = row writing 64 B pieces 1 KB+ apart) cost
+                // 30k cycles per 128x256 tile in LSU transactions -- more than the MMA main loop (profiles/r1 probe).
+                const int CH = p.out_f32 ? 32 : 64;                       // columns per 128-byte row
+                const int row0 = q * 32;
+                const int bw_ = p.bw, bh_ = p.bh;
+                const int cw = tw * bw_ + row0 % bw_, chh = th * bh_ + (row0 / bw_) % bh_, cn = tn * p.bn + row0 / (bw_ * bh_);
+                const int cbase = (p.os == 2 ? ph.opw * (int)p.out_ld : 0);
+                const int cph = (p.os == 2 ? ph.oph : 0);
+                const uint32_t stg0 = sbase + (uint32_t)stages * stage_bytes + (uint32_t)q * 8192u;
+                const int nch = (min(p.BN, p.n_store - ncol0) + CH - 1) / CH;
+                for (int cc = 0; cc < nch; ++cc) {
+                    const uint32_t buf = stg0 + (uint32_t)(cc & 1) * 4096u;
+                    uint32_t r[32];
+                    if (p.out_f32) {
+                        tmem_ld16(trow + (uint32_t)(cc * 32), r);
+                        tmem_ld16(trow + (uint32_t)(cc * 32 + 16), r + 16);
+                        tmem_ld_wait();
+                        if (p.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int c = ncol0 + cc * 32 + j;
+                                if (c < p.n_store) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(p.bias + c));
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t t32[32];
+                            tmem_ld16(trow + (uint32_t)(cc * 64 + hh * 32), t32);
+                            tmem_ld16(trow + (uint32_t)(cc * 64 + hh * 32 + 16), t32 + 16);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float a = __uint_as_float(t32[2 * j]), b = __uint_as_float(t32[2 * j + 1]);
+                                if (p.bias) {
+                                    const int c = ncol0 + cc * 64 + hh * 32 + 2 * j;
+                                    if (c < p.n_store) { a += __ldg(p.bias + c); b += __ldg(p.bias + c + 1); }
+                                }
+                                r[hh * 16 + j] = pack_bf16x2(a, b);
+                            }
+                        }
+                    }
+                    if (cc >= 2) {                       // the store that read this buffer two chunks ago has drained it
+                        if (lane == 0) bulk_wait_group_read<1>();
+                        __syncwarp();
+                    }
+                    const uint32_t rowaddr = buf + (uint32_t)lane * 128u;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        st_shared_v4(rowaddr + (uint32_t)((c ^ (lane & 7)) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (p.accumulate) tma_reduce_add_5d(&tmO, buf, cbase + ncol0 + cc * CH, cw, cph, chh, cn);
+                        else tma_store_5d(&tmO, buf, cbase + ncol0 + cc * CH, cw, cph, chh, cn);
+                        bulk_commit_group();
+                    }
+                }
+                // TMEM reads are complete: hand the accumulator back, then drain the staging buffers for the next tile
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[acc]) & kPeerBitMask);
+                    else mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+                    bulk_wait_group_read<0>();
+                }
+                __syncwarp();
+                continue;
+            }
             const int nchunks = p.BN >> 4;
             for (int ch = 0; ch < nchunks; ++ch) {
                 uint32_t r[16];
@@ -261,12 +387,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             // all TMEM reads of this warp are complete (tmem_ld_wait above): hand the accumulator back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[acc]) & kPeerBitMask);   // the leader's barrier
+                else mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+            }
         }
     }
+    if (p.tma_out && warp >= 2 && lane == 0) bulk_wait_group<0>();   // all tensor stores of this thread are complete
+    __syncwarp();
     tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<2 * kAccCols>(tmem_base);
+    if (PAIR) {
+        cluster_sync_all();       // the peer's smem / TMEM / barriers stay alive until the leader's last MMA and commit landed
+        if (warp == 0) { __syncwarp(); tmem_dealloc_pair<2 * kAccCols>(tmem_base); }
+    } else {
+        __syncthreads();
+        if (warp == 0) tmem_dealloc<2 * kAccCols>(tmem_base);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -451,6 +587,32 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int wN, int wT, int wK, i
     return 0;
 }
 
+// output tensor (NB, Ho, Wo, n_store) with pixel stride ld, fp32 or bf16 -> 5-D STORE map; box = one epilogue warp's
+// 32 rows x 128 bytes.  os == 2 (transposed conv / stride-2 dgrad): the phase view of make_act_map, the store's channel
+// coordinate selects the column phase.
+static int make_out_map(CUtensorMap* m, void* ptr, int f32, int NB, int Ho, int Wo, int n_store, long long ld, int os,
+                        int sbw, int sbh, int sbn) {
+    if (get_encode()) return 2;
+    const cuuint64_t es = f32 ? 4 : 2;
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5] = {(cuuint32_t)(f32 ? 32 : 64), (cuuint32_t)sbw, 1, (cuuint32_t)sbh, (cuuint32_t)sbn}, est[5] = {1, 1, 1, 1, 1};
+    if (os == 1) {
+        dims[0] = n_store; dims[1] = Wo; dims[2] = 1; dims[3] = Ho; dims[4] = NB;
+        strides[0] = ld * es; strides[1] = (cuuint64_t)Wo * ld * es; strides[2] = (cuuint64_t)Wo * ld * es;
+        strides[3] = (cuuint64_t)Ho * Wo * ld * es;
+    } else {
+        dims[0] = ld + n_store; dims[1] = Wo / 2; dims[2] = 2; dims[3] = Ho / 2; dims[4] = NB;
+        strides[0] = 2 * ld * es; strides[1] = (cuuint64_t)Wo * ld * es; strides[2] = (cuuint64_t)2 * Wo * ld * es;
+        strides[3] = (cuuint64_t)Ho * Wo * ld * es;
+    }
+    CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, ptr, dims, strides, box, est,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SNN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out) failed: %d (NB=%d Ho=%d Wo=%d C=%d ld=%lld os=%d box=%d,%d,%d)",
+                (int)r, NB, Ho, Wo, n_store, ld, os, sbw, sbh, sbn);
+    return 0;
+}
+
 static int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 // choose a power-of-two pixel box (bn, bh, bw) with bn*bh*bw == npix that wastes the least
@@ -477,28 +639,73 @@ void debug_set(int k, int v) { if (k >= 0 && k < 8) g_debug_flags[k] = v; }
 
 static int smem_budget() { return 220 * 1024; }
 
-static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, ConvGemmParams& p, cudaStream_t st) {
+// w / w_dims: the weight tensor behind the B operand (the map is built here because its box depends on PAIR)
+static int make_w_map(CUtensorMap* m, const void* ptr, int wN, int wT, int wK, int box_n);
+struct WDesc { const void* ptr; int wN, wT, wK; };
+
+static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const WDesc& wd, ConvGemmParams& p, cudaStream_t st) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        attr_err = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     });
     SNN_CUDA_OK(attr_err);
-    p.b_boxes = (p.BN + 63) / 64;
-    p.stage_bytes = p.b_mn ? 16384 + p.b_boxes * 8192 : 16384 + p.BN * 128;
-    int stages = smem_budget() / p.stage_bytes;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    // CTA pairs need an even split of the B tile: K-major rows in multiples of 8 and N % 16 == 0 (cta_group::2),
+    // MN-major 64-column boxes; g_debug_flags[6] == 1 forces the single-CTA kernel (tests / A-B timing)
+    bool pair = m_tiles >= 2 && g_debug_flags[6] != 1;
+    if (pair) pair = p.b_mn ? (p.BN % 128 == 0) : (p.BN % 16 == 0);
+    const int bn_cta = pair ? p.BN / 2 : p.BN;
+    p.b_boxes = (bn_cta + 63) / 64;
+    p.stage_bytes = p.b_mn ? 16384 + p.b_boxes * 8192 : 16384 + bn_cta * 128;
+    // coalesced TMA-store epilogue whenever the output view is expressible as a tensor map
+    const int es = p.out_f32 ? 4 : 2, CH = p.out_f32 ? 32 : 64;
+    char* obase = reinterpret_cast<char*>(p.out) + (long long)p.out_coff * es;
+    p.tma_out = g_debug_flags[0] != 1 && !(p.accumulate && !p.out_f32) && ((uintptr_t)obase % 16 == 0) && ((p.out_ld * es) % 16 == 0) &&
+                (p.os == 1 || (p.n_store % CH == 0 && p.Ho % 2 == 0 && p.Wo % 2 == 0));
+    const int stage_extra = p.tma_out ? 4 * 8192 : 0;     // 4 epilogue warps x 2 staging tiles of 32 rows x 128 B
+    int stages = (smem_budget() - stage_extra) / p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (g_debug_flags[1] > 0 && stages > g_debug_flags[1]) stages = g_debug_flags[1];
     SNN_REQUIRE(stages >= 2, "conv_gemm: not enough shared memory for 2 stages");
     p.stages = stages;
-    const size_t smem = (size_t)stages * p.stage_bytes + 1024;
+    const size_t smem = (size_t)stages * p.stage_bytes + stage_extra + 1024;
     p.n_blocks = (p.n_store + p.BN - 1) / p.BN;
-    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks * p.nphase;
-    int grid = num_sms();
-    if (g_debug_flags[5] > 0) grid = g_debug_flags[5];
-    if (grid > total_tiles) grid = total_tiles;
-    conv_gemm_kernel<<<grid, 192, smem, st>>>(a0, a1, b, p);
-    return check_cuda(cudaGetLastError(), "conv_gemm_kernel launch");
+    p.dbg = g_debug_flags[7];
+    CUtensorMap b, o;
+    if (make_w_map(&b, wd.ptr, wd.wN, wd.wT, wd.wK, p.b_mn ? 64 : bn_cta)) return 2;
+    if (p.tma_out) {
+        const int sbw = p.bw >= 32 ? 32 : p.bw, sbh = (32 / sbw) < p.bh ? (32 / sbw) : p.bh, sbn = 32 / (sbw * sbh);
+        if (make_out_map(&o, obase, p.out_f32, p.NB, p.Ho, p.Wo, p.n_store, p.out_ld, p.os, sbw, sbh, sbn)) return 2;
+    } else {
+        o = b;
+    }
+    if (!pair) {
+        const int total_tiles = m_tiles * p.n_blocks * p.nphase;
+        int grid = num_sms();
+        if (g_debug_flags[5] > 0) grid = g_debug_flags[5];
+        if (grid > total_tiles) grid = total_tiles;
+        conv_gemm_kernel<false><<<grid, 192, smem, st>>>(a0, a1, b, o, p);
+        return check_cuda(cudaGetLastError(), "conv_gemm_kernel launch");
+    }
+    const int total_tiles = ((m_tiles + 1) / 2) * p.n_blocks * p.nphase;
+    int pairs = num_sms() / 2;
+    if (g_debug_flags[5] > 0) pairs = g_debug_flags[5];
+    if (pairs > total_tiles) pairs = total_tiles;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cfg.blockDim = dim3(192, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return check_cuda(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, a0, a1, b, o, p), "conv_gemm_kernel<pair> launch");
 }
 
 static int pick_bn(int n_store) {
@@ -548,10 +755,10 @@ int conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long long
     p.BN = pick_bn(Cout);
     p.n_store = Cout; p.wn_off = w_row_off;
     p.out = out; p.bias = bias; p.out_f32 = out_f32; p.accumulate = accumulate; p.out_ld = out_ld; p.out_coff = out_coff;
-    CUtensorMap a0, a1, b;
+    CUtensorMap a0, a1;
     if (make_act_map(&a0, x0, NB, H, W, C0, ld0, phase_view, p.bn, p.bh, p.bw)) return 2;
     if (x1) { if (make_act_map(&a1, x1, NB, H, W, C1, ld1, phase_view, p.bn, p.bh, p.bw)) return 2; } else a1 = a0;
-    if (make_w_map(&b, w, w_rows, taps, w_K, p.BN)) return 2;
+    const WDesc wd = {w, w_rows, taps, w_K};
     if (geom == GEOM_T2x2_S2) {
         p.nphase = 4;
         for (int a = 0; a < 2; ++a)
@@ -575,7 +782,7 @@ int conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long long
                 if (x1) ph.seg[ph.nseg++] = mkseg(1, (int)(dcm * ld1), dw, dhp, dh, kh * k + kw, w_coff + C0, C1);
             }
     }
-    return launch_conv_gemm(a0, a1, b, p, st);
+    return launch_conv_gemm(a0, a1, wd, p, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -597,9 +804,9 @@ int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long lo
     p.BN = pick_bn(Ci);
     p.n_store = Ci; p.wn_off = ci_off; p.b_mn = 1;
     p.out = dx; p.bias = nullptr; p.out_f32 = dx_f32; p.accumulate = accumulate; p.out_ld = dx_ld; p.out_coff = dx_coff;
-    CUtensorMap a0, b;
+    CUtensorMap a0;
     if (make_act_map(&a0, dy, NB, Hy, Wy, Cout, ld_dy, phase_view, p.bn, p.bh, p.bw)) return 2;
-    if (make_w_map(&b, wt, Cout, taps, w_K, 64)) return 2;   // box = 64 input channels x 1 tap x 64 output-channel rows
+    const WDesc wd = {wt, Cout, taps, w_K};                  // box = 64 input channels x 1 tap x 64 output-channel rows
     if (geom == GEOM_3x3_S1 || geom == GEOM_1x1) {
         p.nphase = 1;
         Phase& ph = p.phase[0];
@@ -630,7 +837,7 @@ int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long lo
         for (int a = 0; a < 2; ++a)
             for (int bb = 0; bb < 2; ++bb) ph.seg[ph.nseg++] = mkseg(0, (int)(bb * ld_dy), 0, a, 0, a * 2 + bb, 0, Cout);
     }
-    return launch_conv_gemm(a0, a0, b, p, st);
+    return launch_conv_gemm(a0, a0, wd, p, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -685,7 +892,9 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
         }
     const int m_tiles = (Cout + 127) / 128;
     const int base_ctas = m_tiles * p.n_ci_tiles * taps;
-    int ksplit = (num_sms() * 2 + base_ctas - 1) / base_ctas;
+    // split-K so that the grid is at most two FULL waves of one CTA per SM (rounding up gave 297 CTAs on 148 SMs:
+    // a third wave for one CTA, profiles/r1)
+    int ksplit = (num_sms() * 2) / base_ctas;
     const int max_split = (p.total_tiles + 3) / 4;  // >= 4 pixel tiles per CTA
     if (ksplit > max_split) ksplit = max_split;
     if (ksplit < 1) ksplit = 1;

@@ -334,150 +334,178 @@ bn_bwd_dx_kernel(const float* __restrict__ gx, const float* __restrict__ y, cons
 //   pass 1 (REDUCE): red[t][0][c] = sum gx, red[t][1][c] = sum gx*xhat          reads 4 (y) + 2 (gs) B / neuron-step
 //   pass 2 (DX)    : dy = scale*(gx - mean(gx) - xhat*mean(gx*xhat)) as bf16    reads 6, writes 2 B / neuron-step
 // gx (the surrogate-gradient scan) is recomputed in registers in both passes instead of being stored as fp32 and
-// re-read (the 3-kernel path above moves 10 + 10 B).  Per-(t,c) coefficients live in shared memory; a block owns a
-// channel range [c_base, c_base + Cb) and a pixel range; a thread owns 4 channels of one pixel per iteration.
+// re-read (the 3-kernel path above moves 10 + 10 B).  A block owns a channel range [c_base, c_base + Cb) and a pixel
+// range; a thread owns ONE CHANNEL PAIR of one pixel per iteration and does all arithmetic with the packed
+// fp32x2 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: one issue slot per pair) -- the v1 scalar kernel was
+// issue-bound at 44 warp-instructions per neuron-step (profiles/r1).  Per-(t, channel pair) coefficients are float4
+// rows in shared memory.
 //   x = y*scale + shift (same two roundings as the forward kernel -> identical spikes);
-//   xhat*k2*scale = (x - beta_bn)*k2, so pass 2 needs only {scale, shift, scale*k1, k2} per (t,c) and beta_bn per c.
+//   xhat*k2*scale = (x - beta_bn)*k2, so pass 2 needs only {scale, shift, -scale*k1, -k2} per (t,c) and beta_bn per c.
 // ------------------------------------------------------------------------------------------
-template <int ACT>
-SNN_DEVINL float surrogate_step(float uu, float g, float& gv, float beta, float theta, float ka, float kz) {
-    if (ACT == ACT_LIF) {
-        const float z = kz * (uu - theta);
-        const float sg = __fdividef(ka, fmaf(z, z, 1.f));   // MUFU.RCP path (2 ulp): this kernel is issue-bound, not HBM-bound
-        const float keep = (uu >= theta) ? 0.f : 1.f;
-        const float gu = g * sg + gv * (keep - uu * sg);
-        gv = beta * gu;
-        return gu;
-    }
-    const float sgm = __fdividef(1.f, 1.f + __expf(-uu));
-    return g * (sgm * (1.f + uu * (1.f - sgm)));
+SNN_DEVINL float2 f2(float a, float b) { return make_float2(a, b); }
+SNN_DEVINL float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+SNN_DEVINL float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
-// thread = 2 channels of one pixel per iteration (64-bit y loads, 32-bit gs loads / dy stores: still one fully used
-// 128/256 B line per warp instruction) -- half the live state of a 4-channel thread, so 4 blocks of 256 fit per SM.
-template <int ACT, int TMAX, bool REDUCE>
+// EXACT: T == TMAX is a compile-time constant (no per-step guards; T = 1, 4, 8, 16 are the shapes on the path).
+// Coefficient tables are [channel pair][t] float4 rows with an odd row pitch of (TMAX|1) entries: a thread's T
+// entries sit at compile-time offsets from one base address and LDS.128 quarter-warps are bank-conflict free.
+template <int ACT, int TMAX, bool REDUCE, bool EXACT>
 __global__ void __launch_bounds__(256, (TMAX <= 4 ? 4 : (TMAX <= 8 ? 2 : 1)))
 bn_act_bwd2_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ beta_bn,
                    const float* __restrict__ red_in, const float* __restrict__ v_init, const __nv_bfloat16* __restrict__ gs,
                    const float* __restrict__ gv_final, __nv_bfloat16* __restrict__ dy_out, float* __restrict__ gv_init,
-                   float* __restrict__ red_out, float* dgamma, float* dbeta, int T, int P, int C, int Cb, int pix_per_block,
+                   float* __restrict__ red_out, float* dgamma, float* dbeta, int T_rt, int P, int C, int Cb, int pix_per_block,
                    float beta, float theta, float alpha, float invP) {
-    extern __shared__ float shc[];  // coefficient tables [T][NCOEF][Cb] (+ [Cb] beta_bn) ; REDUCE: + [T][2][Cb] accumulators
-    constexpr int NCOEF = REDUCE ? 3 : 4;
+    extern __shared__ float4 shc4[];
+    constexpr int PITCH = TMAX | 1;
+    const int T = EXACT ? TMAX : T_rt;
     const int c_base = blockIdx.y * Cb;
-    const int tpp = Cb >> 1;
+    const int tpp = Cb >> 1;         // threads (channel pairs) per pixel
     const int rows = 256 / tpp;
     const int cg = threadIdx.x % tpp, row = threadIdx.x / tpp;
-    const int cl = cg * 2;           // channel offset inside the block's range
-    float* coef = shc;
-    float* bbn = shc + T * NCOEF * Cb;                 // DX only
-    float* accum = shc + T * NCOEF * Cb + (REDUCE ? 0 : Cb);  // REDUCE only
-    for (int i = threadIdx.x; i < T * Cb; i += 256) {
-        const int t = i / Cb, c = i % Cb, gc = t * C + c_base + c;
-        const float sc = scale[gc];
-        coef[(t * NCOEF + 0) * Cb + c] = sc;
-        coef[(t * NCOEF + 1) * Cb + c] = shift[gc];
+    float4* tabA = shc4;                                           // [tpp][PITCH] {scale.xy, shift.xy}
+    float4* tabB = shc4 + tpp * PITCH;                             // REDUCE: {-mean.xy, 0, 0} ; DX: {-scale*mean(gx).xy, -mean(gx*xhat)*invstd.xy}
+    float* accum = reinterpret_cast<float*>(tabB + tpp * PITCH);   // REDUCE: [T][2][Cb]
+    for (int i = threadIdx.x; i < T * tpp; i += 256) {
+        const int t = i / tpp, j = i % tpp, gc = t * C + c_base + 2 * j;
+        const float2 sc = *reinterpret_cast<const float2*>(scale + gc), sh = *reinterpret_cast<const float2*>(shift + gc);
+        tabA[j * PITCH + t] = make_float4(sc.x, sc.y, sh.x, sh.y);
         if (REDUCE) {
-            coef[(t * NCOEF + 2) * Cb + c] = mean[gc];
-            accum[(t * 2 + 0) * Cb + c] = 0.f;
-            accum[(t * 2 + 1) * Cb + c] = 0.f;
+            const float2 m = *reinterpret_cast<const float2*>(mean + gc);
+            tabB[j * PITCH + t] = make_float4(-m.x, -m.y, 0.f, 0.f);
         } else {
-            const float s0 = red_in[(t * 2 + 0) * C + c_base + c], s1 = red_in[(t * 2 + 1) * C + c_base + c];
-            coef[(t * NCOEF + 2) * Cb + c] = sc * (s0 * invP);          // scale * mean(gx)
-            coef[(t * NCOEF + 3) * Cb + c] = s1 * invP * invstd[gc];    // mean(gx*xhat) * invstd  (scale*xhat = invstd*(x - beta_bn))
+            const float2 r0 = *reinterpret_cast<const float2*>(red_in + (t * 2 + 0) * C + c_base + 2 * j);
+            const float2 r1 = *reinterpret_cast<const float2*>(red_in + (t * 2 + 1) * C + c_base + 2 * j);
+            const float2 is = *reinterpret_cast<const float2*>(invstd + gc);
+            tabB[j * PITCH + t] = make_float4(-(sc.x * (r0.x * invP)), -(sc.y * (r0.y * invP)), -(r1.x * invP * is.x), -(r1.y * invP * is.y));
         }
     }
-    if (!REDUCE) {
-        for (int c = threadIdx.x; c < Cb; c += 256) bbn[c] = beta_bn ? beta_bn[c_base + c] : 0.f;
+    if (REDUCE) {
+        for (int i = threadIdx.x; i < T * 2 * Cb; i += 256) accum[i] = 0.f;
+    } else if (blockIdx.x == 0) {
         // parameter gradients of the BN affine: dgamma += sum_t red1, dbeta += sum_t red0 (one block per channel range)
-        if (blockIdx.x == 0) {
-            for (int c = threadIdx.x; c < Cb; c += 256) {
-                float dg = 0.f, db = 0.f;
-                for (int t = 0; t < T; ++t) { db += red_in[(t * 2 + 0) * C + c_base + c]; dg += red_in[(t * 2 + 1) * C + c_base + c]; }
-                if (dgamma) dgamma[c_base + c] += dg;
-                if (dbeta) dbeta[c_base + c] += db;
-            }
+        for (int c = threadIdx.x; c < Cb; c += 256) {
+            float dg = 0.f, db = 0.f;
+            for (int t = 0; t < T; ++t) { db += red_in[(t * 2 + 0) * C + c_base + c]; dg += red_in[(t * 2 + 1) * C + c_base + c]; }
+            if (dgamma) dgamma[c_base + c] += dg;
+            if (dbeta) dbeta[c_base + c] += db;
         }
     }
     __syncthreads();
     const float ka = 0.5f * alpha, kz = 1.5707963267948966f * alpha;
+    const float2 kz2 = f2(kz, kz), nkzth2 = f2(-kz * theta, -kz * theta), one2 = f2(1.f, 1.f), ka2 = f2(ka, ka), beta2 = f2(beta, beta);
     const int C2 = C >> 1;
-    const size_t nt2 = (size_t)P * C2;
-    float acc_s[TMAX][2], acc_d[TMAX][2];
+    const size_t nt2 = (size_t)P * C2;        // channel pairs per timestep
+    float2 acc_s[TMAX], acc_d[TMAX];
     if (REDUCE) {
 #pragma unroll
-        for (int t = 0; t < TMAX; ++t) acc_s[t][0] = acc_s[t][1] = acc_d[t][0] = acc_d[t][1] = 0.f;
+        for (int t = 0; t < TMAX; ++t) acc_s[t] = acc_d[t] = f2(0.f, 0.f);
     }
     if (row < rows) {
+        float2 nbb = f2(0.f, 0.f);
+        if (!REDUCE && beta_bn) {
+            const float2 b = *reinterpret_cast<const float2*>(beta_bn + c_base + 2 * cg);
+            nbb = f2(-b.x, -b.y);
+        }
+        const float4* tA = tabA + cg * PITCH;
+        const float4* tB = tabB + cg * PITCH;
         const int p0 = blockIdx.x * pix_per_block, p1 = min(P, p0 + pix_per_block);
-        for (int p = p0 + row; p < p1; p += rows) {
-            const size_t e2 = (size_t)p * C2 + (c_base >> 1) + cg;
-            float2 yv[TMAX];
+        size_t e2 = (size_t)(p0 + row) * C2 + (c_base >> 1) + cg;
+        const size_t e2_step = (size_t)rows * C2;
+        for (int p = p0 + row; p < p1; p += rows, e2 += e2_step) {
+            float2 yv[TMAX];      // REDUCE: y ; DX: overwritten with x = y*scale + shift
             uint32_t gr[TMAX];
+            {
+                // pass 1 leaves y / gs in L2 for pass 2 (tensors up to ~80 MB fit the 126 MB L2); pass 2 streams
+                const float2* yp = reinterpret_cast<const float2*>(y) + e2;
+                const uint32_t* gp = reinterpret_cast<const uint32_t*>(gs) + e2;
 #pragma unroll
-            for (int t = 0; t < TMAX; ++t) {
-                if (t < T) {
-                    yv[t] = __ldcs(reinterpret_cast<const float2*>(y) + (size_t)t * nt2 + e2);
-                    gr[t] = __ldcs(reinterpret_cast<const uint32_t*>(gs) + (size_t)t * nt2 + e2);
-                }
-            }
-            float v0 = 0.f, v1 = 0.f;
-            if (ACT == ACT_LIF && v_init) {
-                const float2 a = __ldg(reinterpret_cast<const float2*>(v_init) + e2);
-                v0 = a.x; v1 = a.y;
-            }
-            float x[TMAX][2], u[TMAX][2];
-#pragma unroll
-            for (int t = 0; t < TMAX; ++t) {
-                if (t < T) {
-                    const float2 sc = *reinterpret_cast<const float2*>(coef + (t * NCOEF + 0) * Cb + cl);
-                    const float2 sh = *reinterpret_cast<const float2*>(coef + (t * NCOEF + 1) * Cb + cl);
-                    x[t][0] = __fadd_rn(__fmul_rn(yv[t].x, sc.x), sh.x);
-                    x[t][1] = __fadd_rn(__fmul_rn(yv[t].y, sc.y), sh.y);
-                    if (ACT == ACT_LIF) {
-                        const float ua = __fadd_rn(__fmul_rn(beta, v0), x[t][0]), ub = __fadd_rn(__fmul_rn(beta, v1), x[t][1]);
-                        u[t][0] = ua; u[t][1] = ub;
-                        v0 = (ua >= theta) ? 0.f : ua;
-                        v1 = (ub >= theta) ? 0.f : ub;
-                    } else {
-                        u[t][0] = x[t][0]; u[t][1] = x[t][1];
+                for (int t = 0; t < TMAX; ++t) {
+                    if (EXACT || t < T) {
+                        yv[t] = REDUCE ? __ldg(yp) : __ldcs(yp);
+                        gr[t] = REDUCE ? __ldg(gp) : __ldcs(gp);
+                        yp += nt2; gp += nt2;
                     }
                 }
             }
-            float gv0 = 0.f, gv1 = 0.f;
-            if (ACT == ACT_LIF && gv_final) {
-                const float2 a = __ldg(reinterpret_cast<const float2*>(gv_final) + e2);
-                gv0 = a.x; gv1 = a.y;
+            float2 v = f2(0.f, 0.f);
+            if (ACT == ACT_LIF && v_init) v = __ldg(reinterpret_cast<const float2*>(v_init) + e2);
+            float2 u[TMAX];       // LIF: membrane before reset ; SiLU: x
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t) {
+                if (EXACT || t < T) {
+                    const float4 a = tA[t];
+                    // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (even with -fmad=false), which would
+                    // break the two-rounding contract shared with the forward kernel: packed multiply, scalar adds
+                    const float2 xm = __fmul2_rn(yv[t], f2(a.x, a.y));
+                    const float2 x = f2(__fadd_rn(xm.x, a.z), __fadd_rn(xm.y, a.w));
+                    if (!REDUCE) yv[t] = x;
+                    if (ACT == ACT_LIF) {
+                        const float2 um = __fmul2_rn(beta2, v);
+                        const float2 uu = f2(__fadd_rn(um.x, x.x), __fadd_rn(um.y, x.y));
+                        u[t] = uu;
+                        v.x = (uu.x >= theta) ? 0.f : uu.x;
+                        v.y = (uu.y >= theta) ? 0.f : uu.y;
+                    } else {
+                        u[t] = x;
+                    }
+                }
             }
+            float2 gv = f2(0.f, 0.f);
+            if (ACT == ACT_LIF && gv_final) gv = __ldg(reinterpret_cast<const float2*>(gv_final) + e2);
+            uint32_t* dp = reinterpret_cast<uint32_t*>(dy_out) + e2 + (size_t)(T - 1) * nt2;
 #pragma unroll
             for (int t = TMAX - 1; t >= 0; --t) {
-                if (t < T) {
-                    const float gx0 = surrogate_step<ACT>(u[t][0], bf16_lo(gr[t]), gv0, beta, theta, ka, kz);
-                    const float gx1 = surrogate_step<ACT>(u[t][1], bf16_hi(gr[t]), gv1, beta, theta, ka, kz);
-                    if (REDUCE) {
-                        const float2 m = *reinterpret_cast<const float2*>(coef + (t * NCOEF + 2) * Cb + cl);
-                        acc_s[t][0] += gx0; acc_s[t][1] += gx1;
-                        acc_d[t][0] = fmaf(gx0, yv[t].x - m.x, acc_d[t][0]);
-                        acc_d[t][1] = fmaf(gx1, yv[t].y - m.y, acc_d[t][1]);
+                if (EXACT || t < T) {
+                    const float2 g = f2(bf16_lo(gr[t]), bf16_hi(gr[t]));
+                    const float2 uu = u[t];
+                    float2 gx;
+                    if (ACT == ACT_LIF) {
+                        const float2 z = __ffma2_rn(kz2, uu, nkzth2);                 // kz * (u - theta)
+                        const float2 den = __ffma2_rn(z, z, one2);
+                        const float2 sg = __fmul2_rn(ka2, f2(rcp_approx(den.x), rcp_approx(den.y)));
+                        const float2 keep = f2((uu.x >= theta) ? 0.f : 1.f, (uu.y >= theta) ? 0.f : 1.f);
+                        const float2 w = __ffma2_rn(f2(-uu.x, -uu.y), sg, keep);     // d v[t] / d u[t]
+                        gx = __ffma2_rn(g, sg, __fmul2_rn(gv, w));
+                        gv = __fmul2_rn(beta2, gx);
                     } else {
-                        const float2 sc = *reinterpret_cast<const float2*>(coef + (t * NCOEF + 0) * Cb + cl);
-                        const float2 k1 = *reinterpret_cast<const float2*>(coef + (t * NCOEF + 2) * Cb + cl);
-                        const float2 k2 = *reinterpret_cast<const float2*>(coef + (t * NCOEF + 3) * Cb + cl);
-                        const float2 bb = *reinterpret_cast<const float2*>(bbn + cl);
-                        *(reinterpret_cast<uint32_t*>(dy_out) + (size_t)t * nt2 + e2) =
-                            pack_bf16x2(sc.x * gx0 - k1.x - (x[t][0] - bb.x) * k2.x, sc.y * gx1 - k1.y - (x[t][1] - bb.y) * k2.y);
+                        const float2 e = f2(ex2_approx(-1.4426950408889634f * uu.x), ex2_approx(-1.4426950408889634f * uu.y));
+                        const float2 d1 = __fadd2_rn(e, one2);
+                        const float2 sgm = f2(rcp_approx(d1.x), rcp_approx(d1.y));
+                        const float2 oms = __fadd2_rn(one2, f2(-sgm.x, -sgm.y));
+                        gx = __fmul2_rn(g, __fmul2_rn(sgm, __ffma2_rn(uu, oms, one2)));
+                    }
+                    const float4 k = tB[t];
+                    if (REDUCE) {
+                        acc_s[t] = __fadd2_rn(acc_s[t], gx);
+                        acc_d[t] = __ffma2_rn(gx, __fadd2_rn(yv[t], f2(k.x, k.y)), acc_d[t]);
+                    } else {
+                        const float4 a = tA[t];
+                        const float2 t1 = __ffma2_rn(f2(a.x, a.y), gx, f2(k.x, k.y));
+                        const float2 d = __ffma2_rn(__fadd2_rn(yv[t], nbb), f2(k.z, k.w), t1);
+                        *dp = pack_bf16x2(d.x, d.y);
+                        dp -= nt2;
                     }
                 }
             }
-            if (!REDUCE && ACT == ACT_LIF && gv_init) *(reinterpret_cast<float2*>(gv_init) + e2) = make_float2(gv0, gv1);
+            if (!REDUCE && ACT == ACT_LIF && gv_init) *(reinterpret_cast<float2*>(gv_init) + e2) = gv;
         }
         if (REDUCE) {
+            const int cl = cg * 2;
 #pragma unroll
             for (int t = 0; t < TMAX; ++t) {
-                if (t < T) {
-                    atomicAdd(&accum[(t * 2 + 0) * Cb + cl], acc_s[t][0]); atomicAdd(&accum[(t * 2 + 0) * Cb + cl + 1], acc_s[t][1]);
-                    atomicAdd(&accum[(t * 2 + 1) * Cb + cl], acc_d[t][0]); atomicAdd(&accum[(t * 2 + 1) * Cb + cl + 1], acc_d[t][1]);
+                if (EXACT || t < T) {
+                    atomicAdd(&accum[(t * 2 + 0) * Cb + cl], acc_s[t].x); atomicAdd(&accum[(t * 2 + 0) * Cb + cl + 1], acc_s[t].y);
+                    atomicAdd(&accum[(t * 2 + 1) * Cb + cl], acc_d[t].x); atomicAdd(&accum[(t * 2 + 1) * Cb + cl + 1], acc_d[t].y);
                 }
             }
         }
@@ -580,26 +608,33 @@ static int launch_bwd2_t(const float* y, const float* scale, const float* shift,
                          const float* beta_bn, const float* red_in, const float* v_init, const __nv_bfloat16* gs,
                          const float* gv_final, __nv_bfloat16* dy, float* gv_init, float* red_out, float* dgamma, float* dbeta,
                          int T, int P, int C, float beta, float theta, float alpha, cudaStream_t st) {
-    // channel range per block: largest C / 2^k (multiple of 4) whose tables fit in ~96 KB of shared memory
-    const int per_c = T * ((REDUCE ? 3 : 4) + (REDUCE ? 2 : 0)) * 4 + (REDUCE ? 0 : 4);
+    // bytes of shared memory per channel: two float4 tables per channel PAIR with pitch (TMAX|1), + REDUCE accumulators
+    const int per_c = (TMAX | 1) * 16 + (REDUCE ? T * 8 : 0);
+    // channel range per block: largest C / 2^k (multiple of 4) whose tables fit in ~48 KB of shared memory
     int Cb = C;
     while (((size_t)Cb * per_c > 48 * 1024 || Cb > 512) && Cb % 4 == 0) Cb >>= 1;
     SNN_REQUIRE(C % Cb == 0 && Cb % 2 == 0 && Cb <= 512 && (size_t)Cb * per_c <= 200 * 1024,
                 "bn_act_bwd2: cannot tile C=%d (T=%d) into shared memory", C, T);
     const int rows = 256 / (Cb / 2);
     const int nyb = C / Cb;
-    long long want_blocks = (long long)num_sms() * (REDUCE ? 4 : 8) / nyb;
+    const int occ = TMAX <= 4 ? 4 : (TMAX <= 8 ? 2 : 1);
+    long long want_blocks = (long long)num_sms() * occ * (REDUCE ? 1 : 2) / nyb;    // REDUCE: one full wave; DX: two
     if (want_blocks < 1) want_blocks = 1;
     int ppb = (int)((P + want_blocks - 1) / want_blocks);
     const int min_ppb = rows * (REDUCE ? 8 : 2);
     if (ppb < min_ppb) ppb = min_ppb;
     ppb = ((ppb + rows - 1) / rows) * rows;
     const size_t smem = (size_t)Cb * per_c;
-    auto kern = bn_act_bwd2_kernel<ACT, TMAX, REDUCE>;
-    if (smem > 48 * 1024) SNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((P + ppb - 1) / ppb, nyb);
-    kern<<<grid, 256, smem, st>>>(y, scale, shift, mean, invstd, beta_bn, red_in, v_init, gs, gv_final, dy, gv_init, red_out,
-                                  dgamma, dbeta, T, P, C, Cb, ppb, beta, theta, alpha, 1.0f / (float)P);
+#define SNN_GO(EX)                                                                                                         \
+    do {                                                                                                                   \
+        auto kern = bn_act_bwd2_kernel<ACT, TMAX, REDUCE, EX>;                                                             \
+        if (smem > 48 * 1024) SNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, 256, smem, st>>>(y, scale, shift, mean, invstd, beta_bn, red_in, v_init, gs, gv_final, dy, gv_init,   \
+                                      red_out, dgamma, dbeta, T, P, C, Cb, ppb, beta, theta, alpha, 1.0f / (float)P);      \
+    } while (0)
+    if (T == TMAX) SNN_GO(true); else SNN_GO(false);
+#undef SNN_GO
     return check_cuda(cudaGetLastError(), REDUCE ? "bn_act_bwd2_kernel<reduce>" : "bn_act_bwd2_kernel<dx>");
 }
 
@@ -617,9 +652,9 @@ int launch_bn_act_bwd2(int pass, int act, const float* y, const float* scale, co
                      : launch_bwd2_t<ACT, TM, false>(y, scale, shift, mean, invstd, beta_bn, red, v_init, gs, gv_final, dy,   \
                                                      gv_init, nullptr, dgamma, dbeta, T, P, C, beta, theta, alpha, st)
     if (act == ACT_LIF) {
-        if (T <= 4) SNN_BWD2(ACT_LIF, 4); else if (T <= 8) SNN_BWD2(ACT_LIF, 8); else SNN_BWD2(ACT_LIF, 16);
+        if (T == 1) SNN_BWD2(ACT_LIF, 1); else if (T <= 4) SNN_BWD2(ACT_LIF, 4); else if (T <= 8) SNN_BWD2(ACT_LIF, 8); else SNN_BWD2(ACT_LIF, 16);
     } else {
-        if (T <= 4) SNN_BWD2(ACT_SILU, 4); else if (T <= 8) SNN_BWD2(ACT_SILU, 8); else SNN_BWD2(ACT_SILU, 16);
+        if (T == 1) SNN_BWD2(ACT_SILU, 1); else if (T <= 4) SNN_BWD2(ACT_SILU, 4); else if (T <= 8) SNN_BWD2(ACT_SILU, 8); else SNN_BWD2(ACT_SILU, 16);
     }
 #undef SNN_BWD2
 }

@@ -64,6 +64,36 @@ def test_fprop(geom, nb, h, w, cin, cout):
     assert rel_err(out, ref) < 1e-5, describe_mismatch(out, ref)
 
 
+@pytest.mark.parametrize("geom,nb,h,w,cin,cout", [(G31, 6, 32, 32, 128, 256), (G31, 5, 16, 16, 400, 512), (G32, 4, 16, 16, 256, 512),
+                                                  (G11, 3, 32, 32, 128, 144), (GT, 8, 8, 8, 512, 256)])
+def test_fprop_cta_pair_equals_single_cta(geom, nb, h, w, cin, cout):
+    """The cta_group::2 (two CTAs per 256-pixel tile) and the single-CTA kernels accumulate every output element over
+    the same K order -> bit-identical results; odd m-tile counts exercise the all-out-of-bounds tail of a pair.  Same
+    for the two epilogues (swizzled staging + TMA tensor store vs per-thread row stores)."""
+    setup_exact()
+    K = _k()
+    from snn_object_detectionddp_b200 import _lib
+    taps = {G31: 9, G32: 9, G11: 1, GT: 4}[geom]
+    x, wgt = _mk(nb, h, w, cin, 11), _mkw(cout, taps, cin, 12)
+    bias = torch.randn(cout, device="cuda")
+    L = _lib.lib()
+    outs = {}
+    try:
+        for name, single, legacy in (("pair+tma", 0, 0), ("single+tma", 1, 0), ("pair+rows", 0, 1), ("single+rows", 1, 1)):
+            L.snn_debug_set(6, single)
+            L.snn_debug_set(0, legacy)
+            for dt in (torch.float32, torch.bfloat16):
+                outs[(name, dt)] = K.conv_fprop(geom, x, wgt, cout, bias=bias, out_dtype=dt)
+    finally:
+        L.snn_debug_set(6, 0)
+        L.snn_debug_set(0, 0)
+    torch.cuda.synchronize()
+    for dt in (torch.float32, torch.bfloat16):
+        for name in ("single+tma", "pair+rows", "single+rows"):
+            assert torch.equal(outs[("pair+tma", dt)], outs[(name, dt)]), (name, dt)
+    assert rel_err(outs[("pair+tma", torch.float32)], ref_conv(geom, x, wgt, bias)) < 1e-5
+
+
 def test_fprop_concat_two_sources():
     """enc2 = conv(cat([down1(x1), p4])) (reference model.py:126) without materialising the cat."""
     setup_exact()

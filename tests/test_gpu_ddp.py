@@ -65,7 +65,9 @@ def _worker(rank, world, port, mode, out):
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
-        out.put((same, flat.cpu(), [l.cpu() for l in losses], launched, bool(tr._graph is not None), len(tr.bucketer.buckets)))
+        # plain numpy payloads: torch tensors travel through mp queues as shared-memory handles that die with this process
+        out.put((same, flat.cpu().numpy(), [l.cpu().numpy() for l in losses], launched, bool(tr._graph is not None),
+                 len(tr.bucketer.buckets)))
 
 
 def _run(mode):
@@ -75,10 +77,12 @@ def _run(mode):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
     for p in procs:
         p.start()
+    res = q.get()            # read before join: a child blocks in exit until its queue payload is consumed
     for p in procs:
         p.join(600)
         assert p.exitcode == 0
-    return q.get()
+    same, flat, losses, launched, graphed, nb = res
+    return same, torch.from_numpy(flat), [torch.from_numpy(l) for l in losses], launched, graphed, nb
 
 
 needs2 = pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

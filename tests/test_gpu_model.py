@@ -172,7 +172,9 @@ def test_fused_sequence_equals_per_frame_loop():
     for a, b in zip(outs, o2):
         assert torch.equal(a[-B:].permute(0, 3, 1, 2), b), "fused sequence differs from the per-frame loop"
     assert torch.equal(h.permute(0, 3, 1, 2), hid[0]) and torch.equal(c.permute(0, 3, 1, 2), hid[1])
-    assert torch.equal(mem["enc1"], hid[2]["enc1"])
+    # membranes: the per-(t,c) BN statistics are reduced across thread blocks in an order that is not fixed, so the
+    # fp32 scale/shift may differ in the last ulp between two launches; spikes (outputs) are compared exactly above
+    assert torch.allclose(mem["enc1"], hid[2]["enc1"], rtol=1e-5, atol=1e-6)
 
 
 def _flip_report(name, s_prod, s_orc, u_orc, theta=1.0):
