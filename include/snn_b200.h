@@ -42,6 +42,19 @@ int snn_conv_fprop(int geom, int NB, int H, int W,
                    const void* w_bf16, int w_rows, int w_K, int w_coff, int Cout, int w_row_off,
                    const float* bias, void* out, int out_is_f32, long long out_ld, int out_coff,
                    int accumulate, void* stream);
+/* ConvBlock forward with the train-mode BatchNorm statistics fused into the conv epilogue (replaces the separate pass of
+ * F.batch_norm over the conv output, model.py:14): out is dense fp32 [NB,Ho,Wo,Cout]; `partials` receives one
+ * (sum, sum of squares) pair per 32-pixel group and channel, fp32 [groups][2][Cout], written without atomics.
+ * snn_conv_stats_groups() returns `groups` for the geometry (0: not available -> snn_conv_fprop + snn_bn_stats) and the
+ * number of groups per timestep; snn_bn_stats_from_partials() reduces them in a fixed order to the [T][2][C] fp64 sums
+ * snn_bn_finalize() consumes.  frames_per_step = B (the folded batch holds T*B frames, timestep-major). */
+long long snn_conv_stats_groups(int geom, int NB, int H, int W, int frames_per_step, int* groups_per_step);
+int snn_conv_fprop_stats(int geom, int NB, int H, int W,
+                         const void* x0, int C0, long long ld0, const void* x1, int C1, long long ld1,
+                         const void* w_bf16, int w_rows, int w_K, int w_coff, int Cout, int w_row_off,
+                         float* out, int frames_per_step, float* partials, void* stream);
+int snn_bn_stats_from_partials(const float* partials, double* sums /*[T][2][C]*/, int T, int C, int groups_per_step,
+                               void* stream);
 int snn_conv_dgrad(int geom, int NB, int H, int W,
                    const void* dy, int Cout, long long ld_dy,
                    const void* w_bf16 /*[Cout][taps][w_K]*/, int w_K, int ci_off, int Ci,
@@ -57,7 +70,10 @@ int snn_weight_prep(const float* w, void* w_bf16, void* wt_bf16, int N, int T, i
 /* ---- neuron layer: replaces `self.silu(self.bn(.))` of ConvBlock.forward (model.py:14-18)
  *      y is the conv output, fp32 [T][P][C].  Train-mode BN statistics are per timestep
  *      (the reference calls the module once per frame, train.py:64-66). ---- */
-int snn_bn_stats(const float* y, double* sums /*[T][2][C]*/, int T, int P, int C, void* stream);
+/* deterministic (no atomics): per-block partial sums go to `workspace` (snn_bn_stats_workspace_floats() floats, caller
+ * owned), then a fixed-order fp64 combine */
+long long snn_bn_stats_workspace_floats(int T, int P, int C);
+int snn_bn_stats(const float* y, double* sums /*[T][2][C]*/, float* workspace, int T, int P, int C, void* stream);
 int snn_bn_finalize(const double* sums, const float* gamma, const float* beta,
                     float* running_mean, float* running_var,
                     float* scale, float* shift, float* mean, float* invstd /* each [T][C] (train) or [C] (eval) */,

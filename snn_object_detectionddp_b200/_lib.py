@@ -19,10 +19,12 @@ _P, _I, _L, _F = _c.c_void_p, _c.c_int, _c.c_longlong, _c.c_float
 
 _SIGNATURES = {
     "snn_conv_fprop": [_I, _I, _I, _I, _P, _I, _L, _P, _I, _L, _P, _I, _I, _I, _I, _I, _P, _P, _I, _L, _I, _I, _P],
+    "snn_conv_fprop_stats": [_I, _I, _I, _I, _P, _I, _L, _P, _I, _L, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+    "snn_bn_stats_from_partials": [_P, _P, _I, _I, _I, _P],
     "snn_conv_dgrad": [_I, _I, _I, _I, _P, _I, _L, _P, _I, _I, _I, _P, _I, _L, _I, _I, _P],
     "snn_conv_wgrad": [_I, _I, _I, _I, _P, _I, _L, _P, _I, _L, _P, _I, _I, _P],
     "snn_weight_prep": [_P, _P, _P, _I, _I, _I, _P],
-    "snn_bn_stats": [_P, _P, _I, _I, _I, _P],
+    "snn_bn_stats": [_P, _P, _P, _I, _I, _I, _P],
     "snn_bn_finalize": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P],
     "snn_bn_act_fwd": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _F, _P],
     "snn_bn_act_bwd": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
@@ -53,7 +55,7 @@ class SnnKernelError(RuntimeError):
 
 
 def exported_symbols():
-    return sorted(list(_SIGNATURES) + ["snn_last_error", "snn_version", "snn_debug_set"])
+    return sorted(list(_SIGNATURES) + ["snn_last_error", "snn_version", "snn_debug_set", "snn_conv_stats_groups", "snn_bn_stats_workspace_floats"])
 
 
 def lib():
@@ -71,6 +73,10 @@ def lib():
             fn.restype = _I
         L.snn_last_error.restype = ctypes.c_char_p
         L.snn_version.restype = _I
+        L.snn_conv_stats_groups.argtypes = [_I, _I, _I, _I, _I, ctypes.POINTER(_I)]
+        L.snn_conv_stats_groups.restype = _L
+        L.snn_bn_stats_workspace_floats.argtypes = [_I, _I, _I]
+        L.snn_bn_stats_workspace_floats.restype = _L
         L.snn_debug_set.argtypes = [_I, _I]
         L.snn_debug_set.restype = None
         _lib = L

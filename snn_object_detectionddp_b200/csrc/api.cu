@@ -33,12 +33,15 @@ int num_sms() {
 // launchers defined in the other translation units
 void debug_set(int k, int v);
 int conv_fprop(int, int, int, int, const void*, int, long long, const void*, int, long long, const void*, int, int, int, int,
-               int, const float*, void*, int, long long, int, int, cudaStream_t);
+               int, const float*, void*, int, long long, int, int, cudaStream_t, float*, int);
+long long conv_stats_groups(int, int, int, int, int, int*);
+int launch_bn_stats_from_partials(const float*, double*, int, int, int, cudaStream_t);
 int conv_dgrad(int, int, int, int, const void*, int, long long, const void*, int, int, int, void*, int, long long, int, int,
                cudaStream_t);
 int conv_wgrad(int, int, int, int, const void*, int, long long, const void*, int, long long, float*, int, int, cudaStream_t);
 int launch_weight_prep(const float*, __nv_bfloat16*, __nv_bfloat16*, int, int, int, cudaStream_t);
-int launch_bn_stats(const float*, double*, int, int, int, cudaStream_t);
+int launch_bn_stats(const float*, double*, float*, int, int, int, cudaStream_t);
+long long bn_stats_workspace_floats(int, int, int);
 int launch_bn_finalize(const double*, const float*, const float*, float*, float*, float*, float*, float*, float*, int, int, int,
                        float, float, int, cudaStream_t);
 int launch_bn_act_fwd(int, const float*, const float*, const float*, const float*, __nv_bfloat16*, uint8_t*, float*, int,
@@ -87,7 +90,19 @@ int snn_conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long 
                    const float* bias, void* out, int out_is_f32, long long out_ld, int out_coff, int accumulate,
                    void* stream) {
     return conv_fprop(geom, NB, H, W, x0, C0, ld0, x1, C1, ld1, w, w_rows, w_K, w_coff, Cout, w_row_off, bias, out,
-                      out_is_f32, out_ld, out_coff, accumulate, ST);
+                      out_is_f32, out_ld, out_coff, accumulate, ST, nullptr, 0);
+}
+long long snn_conv_stats_groups(int geom, int NB, int H, int W, int frames_per_step, int* groups_per_step) {
+    return conv_stats_groups(geom, NB, H, W, frames_per_step, groups_per_step);
+}
+int snn_conv_fprop_stats(int geom, int NB, int H, int W, const void* x0, int C0, long long ld0, const void* x1, int C1,
+                         long long ld1, const void* w, int w_rows, int w_K, int w_coff, int Cout, int w_row_off, float* out,
+                         int frames_per_step, float* partials, void* stream) {
+    return conv_fprop(geom, NB, H, W, x0, C0, ld0, x1, C1, ld1, w, w_rows, w_K, w_coff, Cout, w_row_off, nullptr, out, 1,
+                      Cout, 0, 0, ST, partials, frames_per_step);
+}
+int snn_bn_stats_from_partials(const float* partials, double* sums, int T, int C, int groups_per_step, void* stream) {
+    return launch_bn_stats_from_partials(partials, sums, T, C, groups_per_step, ST);
 }
 int snn_conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long long ld_dy, const void* wt, int wt_rows,
                    int ci_off, int Ci, void* dx, int dx_is_f32, long long dx_ld, int dx_coff, int accumulate, void* stream) {
@@ -100,7 +115,10 @@ int snn_conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long l
 int snn_weight_prep(const float* w, void* wf, void* wt, int N, int T, int K, void* stream) {
     return launch_weight_prep(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wt, N, T, K, ST);
 }
-int snn_bn_stats(const float* y, double* sums, int T, int P, int C, void* stream) { return launch_bn_stats(y, sums, T, P, C, ST); }
+int snn_bn_stats(const float* y, double* sums, float* workspace, int T, int P, int C, void* stream) {
+    return launch_bn_stats(y, sums, workspace, T, P, C, ST);
+}
+long long snn_bn_stats_workspace_floats(int T, int P, int C) { return bn_stats_workspace_floats(T, P, C); }
 int snn_bn_finalize(const double* sums, const float* gamma, const float* beta, float* rm, float* rv, float* scale,
                     float* shift, float* mean, float* invstd, int T, int C, int P, float eps, float momentum, int training,
                     void* stream) {

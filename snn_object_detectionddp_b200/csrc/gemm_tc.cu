@@ -52,6 +52,7 @@ struct ConvGemmParams {
     int nphase;
     int b_mn;                         // B operand MN-major: weights [K rows][tap][N contiguous] read in place (dgrad)
     int b_boxes;                      // b_mn: number of 64-column boxes per stage
+    float* stats;                     // tma_out + fp32: per-(32-row group, column) sum / sum-of-squares partials [4*m_tiles][2][n_store]
     int tma_out;                      // epilogue through swizzled smem staging + TMA tensor stores (coalesced) instead of per-thread rows
     int dbg;                          // timing experiments only: bit 0 = producer skips the TMA loads, bit 1 = no MMA issue
     Phase phase[4];
@@ -317,6 +318,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         st_shared_v4(rowaddr + (uint32_t)((c ^ (lane & 7)) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
                     fence_proxy_async_smem();
                     __syncwarp();
+                    if (p.stats && mt < m_tiles) {
+                        // train-mode BatchNorm statistics of the conv output, fused: lane c sums column c of the staged
+                        // 32 x 32 tile in a fixed row order (deterministic; rows of out-of-range pixels are exact zeros).
+                        // The swizzle makes the 32 lanes of every row read 32 distinct banks.
+                        float sm = 0.f, sq = 0.f;
+                        const uint32_t cadr = buf + (uint32_t)((lane & 3) << 2);
+#pragma unroll 8
+                        for (int rr = 0; rr < 32; ++rr) {
+                            float v;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(cadr + (uint32_t)rr * 128u + (uint32_t)((((lane >> 2) ^ (rr & 7))) << 4)));
+                            sm += v;
+                            sq = fmaf(v, v, sq);
+                        }
+                        const int col = ncol0 + cc * 32 + lane;
+                        if (col < p.n_store) {
+                            float* dst = p.stats + ((size_t)(mt * 4 + q) * 2) * (size_t)p.n_store + col;
+                            dst[0] = sm;
+                            dst[p.n_store] = sq;
+                        }
+                    }
                     if (lane == 0) {
                         if (p.accumulate) tma_reduce_add_5d(&tmO, buf, cbase + ncol0 + cc * CH, cw, cph, chh, cn);
                         else tma_store_5d(&tmO, buf, cbase + ncol0 + cc * CH, cw, cph, chh, cn);
@@ -418,7 +439,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_s;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int stages = p.stages;
     const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
@@ -437,6 +458,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             tma_prefetch_desc(&tmG);
             tma_prefetch_desc(&tmX);
         }
+        __syncwarp();
         tmem_alloc<kTmemCols>(smem_u32(&tmem_base_s));
     } else if (warp == 1 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -452,43 +474,55 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     const uint32_t tmem_base = tmem_base_s;
     const int total = max(0, t_end - t_begin);
 
+    // warp-uniform role loops (see conv_gemm_kernel): one elected lane issues, loop state stays in uniform registers
     if (warp == 0) {
-        if (lane == 0) {
-            for (int it = 0; it < total; ++it) {
-                const int tile = t_begin + it;
-                const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tn = tile / (p.tiles_w * p.tiles_h);
-                const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-                const int s = it % stages;
-                const uint32_t par = (uint32_t)((it / stages) & 1);
-                mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
+        const bool lead = elect_one();
+        int s = 0;
+        uint32_t par = 0;
+        uint32_t g_s = sbase;
+        int tw = t_begin % p.tiles_w, th = (t_begin / p.tiles_w) % p.tiles_h, tn = t_begin / (p.tiles_w * p.tiles_h);
+        const int gc0 = tp.g_dc + co0, xc0 = tp.x_dc + ci0;
+        for (int it = 0; it < total; ++it) {
+            const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+            mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
+            if (lead) {
                 const uint32_t fb = smem_u32(&full_bar[s]);
                 mbar_expect_tx(fb, stage_bytes);
-                const uint32_t g_s = sbase + (uint32_t)s * stage_bytes;
-                tma_load_5d(g_s, &tmG, fb, tp.g_dc + co0, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
-                tma_load_5d(g_s + kBox, &tmG, fb, tp.g_dc + co0 + 64, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
+                tma_load_5d(g_s, &tmG, fb, gc0, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
+                tma_load_5d(g_s + kBox, &tmG, fb, gc0 + 64, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
                 const uint32_t x_s = g_s + 2 * kBox;
                 for (int b = 0; b < nxb; ++b)
-                    tma_load_5d(x_s + b * kBox, &tmX, fb, tp.x_dc + ci0 + b * 64, w0 + tp.x_dw, tp.x_dhp, h0 + tp.x_dh, n0);
+                    tma_load_5d(x_s + b * kBox, &tmX, fb, xc0 + b * 64, w0 + tp.x_dw, tp.x_dhp, h0 + tp.x_dh, n0);
             }
+            g_s += stage_bytes;
+            if (++s == stages) { s = 0; par ^= 1u; g_s = sbase; }
+            if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, p.NT, 1, 1);
-            for (int it = 0; it < total; ++it) {
-                const int s = it % stages;
-                const uint32_t par = (uint32_t)((it / stages) & 1);
-                mbar_wait(smem_u32(&full_bar[s]), par);
-                tc_fence_after();
-                const uint32_t g_s = sbase + (uint32_t)s * stage_bytes;
-                const uint32_t x_s = g_s + 2 * kBox;
+        const bool lead = elect_one();
+        const uint32_t idesc = umma_idesc_bf16(128, p.NT, 1, 1);
+        const uint32_t desc_hi = ((uint32_t)p.sbo_bytes >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t lo_c = (((uint32_t)p.lbo_bytes >> 4) & 0x3FFFu) << 16;
+        int s = 0;
+        uint32_t par = 0;
+        uint32_t g_s = sbase;
+        for (int it = 0; it < total; ++it) {
+            mbar_wait(smem_u32(&full_bar[s]), par);
+            tc_fence_after();
+            if (lead) {
+                const uint32_t a_lo = lo_c | ((g_s & 0x3FFFFu) >> 4);
+                const uint32_t b_lo = lo_c | (((g_s + 2 * kBox) & 0x3FFFFu) >> 4);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {  // 16 pixels (rows of 128 B) per MMA
-                    umma_bf16(tmem_base, umma_desc_sw128(g_s + k * 2048, p.lbo_bytes, p.sbo_bytes),
-                              umma_desc_sw128(x_s + k * 2048, p.lbo_bytes, p.sbo_bytes), idesc, (uint32_t)((it | k) != 0));
+                    const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (2048u >> 4) * k);
+                    const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (2048u >> 4) * k);
+                    umma_bf16(tmem_base, adesc, bdesc, idesc, k ? 1u : (uint32_t)(it != 0));
                 }
                 umma_commit(smem_u32(&empty_bar[s]));
+                if (it == total - 1) umma_commit(smem_u32(&tmem_full_bar));
             }
-            umma_commit(smem_u32(&tmem_full_bar));
+            g_s += stage_bytes;
+            if (++s == stages) { s = 0; par ^= 1u; g_s = sbase; }
         }
     } else if (total > 0) {
         const int q = warp & 3;
@@ -665,6 +699,7 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     char* obase = reinterpret_cast<char*>(p.out) + (long long)p.out_coff * es;
     p.tma_out = g_debug_flags[0] != 1 && !(p.accumulate && !p.out_f32) && ((uintptr_t)obase % 16 == 0) && ((p.out_ld * es) % 16 == 0) &&
                 (p.os == 1 || (p.n_store % CH == 0 && p.Ho % 2 == 0 && p.Wo % 2 == 0));
+    SNN_REQUIRE(!p.stats || p.tma_out, "conv_fprop: fused statistics need the TMA-store epilogue (output alignment)");
     const int stage_extra = p.tma_out ? 4 * 8192 : 0;     // 4 epilogue warps x 2 staging tiles of 32 rows x 128 B
     int stages = (smem_budget() - stage_extra) / p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
@@ -736,15 +771,33 @@ static void s2_tap(int k, int* phase, int* d) {
     if (k == 0) { *phase = 1; *d = -1; } else if (k == 1) { *phase = 0; *d = 0; } else { *phase = 1; *d = 0; }
 }
 
+// Fused BatchNorm statistics (conv_fprop(..., stats, B)): the epilogue writes one (sum, sumsq) partial per 32-row group and
+// column; 4 groups per 128-pixel tile, tiles enumerated (n, h, w).  Available when every tile lies inside ONE timestep:
+// the pixel box covers bn images and B (frames per timestep) is a multiple of bn.  Returns the number of groups
+// (0 = not available: use snn_bn_stats) and the number of groups per timestep.
+long long conv_stats_groups(int geom, int NB, int H, int W, int B, int* groups_per_t) {
+    if (geom != GEOM_3x3_S1 && geom != GEOM_3x3_S2 && geom != GEOM_1x1) return 0;
+    if (B <= 0 || NB % B != 0) return 0;
+    int Hd = H, Wd = W;
+    if (geom == GEOM_3x3_S2) { Hd = H / 2; Wd = W / 2; }
+    ConvGemmParams p;
+    set_domain(p, NB, Hd, Wd);
+    if (p.bn > 1 && B % p.bn != 0) return 0;
+    const int tiles_hw = p.tiles_w * p.tiles_h;
+    if (groups_per_t) *groups_per_t = 4 * (B / p.bn) * tiles_hw;
+    return 4LL * tiles_hw * p.tiles_n;
+}
+
 // ------------------------------------------------------------------------------------------
 // fprop: out[NB,Ho,Wo,Cout] = conv(cat(x0,x1)) (+bias) ; geometry decides Ho, Wo
 // ------------------------------------------------------------------------------------------
 int conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long long ld0, const void* x1, int C1, long long ld1,
                const void* w, int w_rows, int w_K, int w_coff, int Cout, int w_row_off, const float* bias, void* out,
-               int out_f32, long long out_ld, int out_coff, int accumulate, cudaStream_t st) {
+               int out_f32, long long out_ld, int out_coff, int accumulate, cudaStream_t st, float* stats, int frames_per_step) {
     SNN_REQUIRE(Cout % 8 == 0, "conv_fprop: Cout=%d must be a multiple of 8", Cout);
     ConvGemmParams p;
     memset(&p, 0, sizeof(p));
+    p.stats = stats;
     const int taps = geom == GEOM_3x3_S1 || geom == GEOM_3x3_S2 ? 9 : (geom == GEOM_1x1 ? 1 : 4);
     const int phase_view = geom == GEOM_3x3_S2;
     int Hd = H, Wd = W;
@@ -759,6 +812,12 @@ int conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long long
     if (make_act_map(&a0, x0, NB, H, W, C0, ld0, phase_view, p.bn, p.bh, p.bw)) return 2;
     if (x1) { if (make_act_map(&a1, x1, NB, H, W, C1, ld1, phase_view, p.bn, p.bh, p.bw)) return 2; } else a1 = a0;
     const WDesc wd = {w, w_rows, taps, w_K};
+    if (stats) {
+        int gpt = 0;
+        SNN_REQUIRE(conv_stats_groups(geom, NB, H, W, frames_per_step, &gpt) > 0 && out_f32 && !accumulate && !bias && out_coff == 0,
+                    "conv_fprop: fused BatchNorm statistics are not available for this call (geom %d NB %d %dx%d B %d)", geom,
+                    NB, H, W, frames_per_step);
+    }
     if (geom == GEOM_T2x2_S2) {
         p.nphase = 4;
         for (int a = 0; a < 2; ++a)

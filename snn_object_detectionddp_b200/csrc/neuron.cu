@@ -17,15 +17,13 @@ enum { ACT_LIF = 0, ACT_SILU = 1 };
 // ------------------------------------------------------------------------------------------
 // per-(t, c) sum / sum-of-squares of y (train-mode BN batch statistics, one group per timestep)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, double* __restrict__ sums,
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, float* __restrict__ part /*[T][gridDim.x][2][C]*/,
                                                         int P, int C, int pix_per_block) {
-    extern __shared__ float shs[];  // [2][C] block partials (fp32: <= a few thousand values each), combined in fp64
+    extern __shared__ float shs[];  // [rows][2][C] per-row partials, combined in a fixed order (deterministic)
     const int t = blockIdx.y;
     const int tpp = C >> 2;  // threads per pixel (float4 each)
     const int rows = 256 / tpp;
     const int cg = threadIdx.x % tpp, row = threadIdx.x / tpp;
-    for (int i = threadIdx.x; i < 2 * C; i += 256) shs[i] = 0.f;
-    __syncthreads();
     if (row < rows) {
         const int p0 = blockIdx.x * pix_per_block;
         const int p1 = min(P, p0 + pix_per_block);
@@ -33,26 +31,68 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
         int p = p0 + row;
         for (; p + 3 * rows < p1; p += 4 * rows) {  // 4 independent 128-bit loads in flight per thread
-            const float4 a = __ldcs(base + (size_t)p * tpp), b = __ldcs(base + (size_t)(p + rows) * tpp);
-            const float4 c = __ldcs(base + (size_t)(p + 2 * rows) * tpp), d = __ldcs(base + (size_t)(p + 3 * rows) * tpp);
+            const float4 a = __ldg(base + (size_t)p * tpp), b = __ldg(base + (size_t)(p + rows) * tpp);
+            const float4 c = __ldg(base + (size_t)(p + 2 * rows) * tpp), d = __ldg(base + (size_t)(p + 3 * rows) * tpp);
             s.x += (a.x + b.x) + (c.x + d.x); s.y += (a.y + b.y) + (c.y + d.y);
             s.z += (a.z + b.z) + (c.z + d.z); s.w += (a.w + b.w) + (c.w + d.w);
             q.x += (a.x * a.x + b.x * b.x) + (c.x * c.x + d.x * d.x); q.y += (a.y * a.y + b.y * b.y) + (c.y * c.y + d.y * d.y);
             q.z += (a.z * a.z + b.z * b.z) + (c.z * c.z + d.z * d.z); q.w += (a.w * a.w + b.w * b.w) + (c.w * c.w + d.w * d.w);
         }
         for (; p < p1; p += rows) {
-            const float4 v = __ldcs(base + (size_t)p * tpp);
+            const float4 v = __ldg(base + (size_t)p * tpp);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
             q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
         }
-        const int c = cg * 4;
-        atomicAdd(&shs[c + 0], s.x); atomicAdd(&shs[c + 1], s.y); atomicAdd(&shs[c + 2], s.z); atomicAdd(&shs[c + 3], s.w);
-        atomicAdd(&shs[C + c + 0], q.x); atomicAdd(&shs[C + c + 1], q.y);
-        atomicAdd(&shs[C + c + 2], q.z); atomicAdd(&shs[C + c + 3], q.w);
+        float4* r0 = reinterpret_cast<float4*>(shs + (size_t)row * 2 * C);
+        r0[cg] = s;
+        r0[tpp + cg] = q;
     }
     __syncthreads();
-    double* out = sums + (size_t)t * 2 * C;
-    for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(&out[i], (double)shs[i]);
+    float* out = part + ((size_t)t * gridDim.x + blockIdx.x) * 2 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += 256) {
+        float a = 0.f;
+        for (int r = 0; r < rows; ++r) a += shs[(size_t)r * 2 * C + i];
+        out[i] = a;
+    }
+}
+
+// sums[t][0|1][c] = sum over the timestep's 32-row groups of the conv epilogue's partials [group][2][C], in a FIXED order
+// (32 row-lanes each walk their groups in order, then are combined in order) -> bit-reproducible statistics.
+constexpr int kRL = 128;   // row-lanes per block of the partial reducer (x 8 channels = 1024 threads)
+__global__ void __launch_bounds__(kRL * 8) bn_stats_from_partials_kernel(const float* __restrict__ part, double* __restrict__ sums,
+                                                                          int C, int groups_per_t) {
+    __shared__ double sh[2][kRL][8];
+    const int t = blockIdx.y;
+    const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int c = blockIdx.x * 8 + cl;
+    double s = 0.0, q = 0.0;
+    if (c < C) {
+        const float* base = part + ((size_t)t * groups_per_t * 2) * C + c;
+        int r = rl;
+        for (; r + 3 * kRL < groups_per_t; r += 4 * kRL) {   // 4 groups (8 loads) in flight per thread
+            const float* r0 = base + (size_t)r * 2 * C;
+            const float* r1 = base + (size_t)(r + kRL) * 2 * C;
+            const float* r2 = base + (size_t)(r + 2 * kRL) * 2 * C;
+            const float* r3 = base + (size_t)(r + 3 * kRL) * 2 * C;
+            const float a0 = __ldg(r0), b0 = __ldg(r0 + C), a1 = __ldg(r1), b1 = __ldg(r1 + C);
+            const float a2 = __ldg(r2), b2 = __ldg(r2 + C), a3 = __ldg(r3), b3 = __ldg(r3 + C);
+            s += (double)a0; q += (double)b0; s += (double)a1; q += (double)b1;
+            s += (double)a2; q += (double)b2; s += (double)a3; q += (double)b3;
+        }
+        for (; r < groups_per_t; r += kRL) {
+            const float* r0 = base + (size_t)r * 2 * C;
+            s += (double)__ldg(r0); q += (double)__ldg(r0 + C);
+        }
+    }
+    sh[0][rl][cl] = s; sh[1][rl][cl] = q;
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        const int which = threadIdx.x >> 3, cc = threadIdx.x & 7;
+        double a = 0.0;
+        for (int i = 0; i < kRL; ++i) a += sh[which][i][cc];
+        const int co = blockIdx.x * 8 + cc;
+        if (co < C) sums[((size_t)t * 2 + which) * C + co] = a;
+    }
 }
 
 // scale/shift per (t,c); running-stat update applied T times in order (the reference calls the
@@ -535,14 +575,36 @@ static int pick_ppb(int P, int rows, int T) {
     return ppb;
 }
 
-int launch_bn_stats(const float* y, double* sums, int T, int P, int C, cudaStream_t st) {
-    SNN_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "bn_stats: C=%d must be a multiple of 4 in [4,1024]", C);
-    SNN_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * T * C, st));
+static int bn_stats_blocks(int P, int C, int* ppb_out) {
     const int rows = 256 / (C / 4);
     const int ppb = pick_ppb(P, rows, 1);   // independent of T: a frame's statistics are bit-identical however the T*B batch is folded
-    dim3 grid((P + ppb - 1) / ppb, T);
-    bn_stats_kernel<<<grid, 256, sizeof(float) * 2 * C, st>>>(y, sums, P, C, ppb);
-    return check_cuda(cudaGetLastError(), "bn_stats_kernel");
+    if (ppb_out) *ppb_out = ppb;
+    return (P + ppb - 1) / ppb;
+}
+long long bn_stats_workspace_floats(int T, int P, int C) {
+    if (C % 4 != 0 || C < 4 || C > 1024 || T < 1 || P < 1) return 0;
+    return (long long)T * bn_stats_blocks(P, C, nullptr) * 2 * C;
+}
+int launch_bn_stats_from_partials(const float* part, double* sums, int T, int C, int groups_per_t, cudaStream_t st);
+
+// two deterministic stages: per-block partials (no atomics) -> fixed-order fp64 combine
+int launch_bn_stats(const float* y, double* sums, float* workspace, int T, int P, int C, cudaStream_t st) {
+    SNN_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "bn_stats: C=%d must be a multiple of 4 in [4,1024]", C);
+    SNN_REQUIRE(workspace != nullptr, "bn_stats: workspace of snn_bn_stats_workspace_floats() floats required");
+    int ppb = 0;
+    const int nblk = bn_stats_blocks(P, C, &ppb);
+    const int rows = 256 / (C / 4);
+    dim3 grid(nblk, T);
+    bn_stats_kernel<<<grid, 256, sizeof(float) * 2 * C * rows, st>>>(y, workspace, P, C, ppb);
+    SNN_CUDA_OK(cudaGetLastError());
+    return launch_bn_stats_from_partials(workspace, sums, T, C, nblk, st);
+}
+
+int launch_bn_stats_from_partials(const float* part, double* sums, int T, int C, int groups_per_t, cudaStream_t st) {
+    SNN_REQUIRE(T >= 1 && C >= 1 && groups_per_t >= 1, "bn_stats_from_partials: bad sizes");
+    dim3 grid((C + 7) / 8, T);
+    bn_stats_from_partials_kernel<<<grid, kRL * 8, 0, st>>>(part, sums, C, groups_per_t);
+    return check_cuda(cudaGetLastError(), "bn_stats_from_partials_kernel");
 }
 
 int launch_bn_finalize(const double* sums, const float* gamma, const float* beta, float* rm, float* rv, float* scale,

@@ -107,18 +107,20 @@ class Detect(nn.Module):
         """feats: 3 bf16 NHWC maps [T*B,h,w,ch].  Every timestep runs (BatchNorm running statistics advance once per
         frame exactly like the reference's per-frame calls); the returned HeadOut holds the last step (train.py:66)."""
         boxes, clss = [], []
-        f32 = dict(store=rc.store, geom=GEOM_1x1, out_dtype=torch.float32)
+        live_n = None if (rc.live_T is None or rc.live_T >= rc.T or not last_only) else rc.live_T * B
+        f32 = dict(store=rc.store, geom=GEOM_1x1, out_dtype=torch.float32, live_n=live_n)
         for i in range(self.nl):
             x = feats[i]
             if x.dtype != torch.bfloat16:
                 x = x.to(torch.bfloat16)
-            b, _ = self.cv2[i][0].forward_seq(rc, x)
-            b, _ = self.cv2[i][1].forward_seq(rc, b)
+            dead = dict(dead_frames_ok=last_only)
+            b, _ = self.cv2[i][0].forward_seq(rc, x, **dead)
+            b, _ = self.cv2[i][1].forward_seq(rc, b, **dead)
             b = ConvBiasFn.apply(b, self.cv2[i][2].weight, self.cv2[i][2].bias, f32)
-            c, _ = self.cv3[i][0][0].forward_seq(rc, x)
-            c, _ = self.cv3[i][0][1].forward_seq(rc, c)
-            c, _ = self.cv3[i][1][0].forward_seq(rc, c)
-            c, _ = self.cv3[i][1][1].forward_seq(rc, c)
+            c, _ = self.cv3[i][0][0].forward_seq(rc, x, **dead)
+            c, _ = self.cv3[i][0][1].forward_seq(rc, c, **dead)
+            c, _ = self.cv3[i][1][0].forward_seq(rc, c, **dead)
+            c, _ = self.cv3[i][1][1].forward_seq(rc, c, **dead)
             c = ConvBiasFn.apply(c, self.cv3[i][2].weight, self.cv3[i][2].bias, f32)
             if last_only:
                 b, c = b[-B:], c[-B:]

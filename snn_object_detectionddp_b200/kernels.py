@@ -60,6 +60,38 @@ def conv_fprop(geom, x0, w_bf16, cout, x1=None, bias=None, out=None, out_dtype=t
     return out
 
 
+_STATS_GROUPS = {}
+
+
+def conv_fprop_stats(geom, x0, w_bf16, cout, T, x1=None):
+    """ConvBlock conv with the per-timestep BatchNorm sums fused into its epilogue.
+    Returns (y fp32 [NB,Ho,Wo,cout], sums fp64 [T][2][cout]); sums is None when the geometry cannot keep every 128-pixel
+    tile inside one timestep (then the caller runs bn_stats on y)."""
+    require_cuda(x0, x1, w_bf16)
+    nb, h, w, c0 = x0.shape
+    key = (geom, nb, h, w, T)
+    if key not in _STATS_GROUPS:
+        gpt = _lib.ctypes.c_int(0)
+        n = _lib.lib().snn_conv_stats_groups(geom, nb, h, w, nb // T, _lib.ctypes.byref(gpt)) if nb % T == 0 else 0
+        _STATS_GROUPS[key] = (int(n), int(gpt.value))
+    groups, gpt = _STATS_GROUPS[key]
+    if groups == 0:
+        return conv_fprop(geom, x0, w_bf16, cout, x1=x1), None
+    ho, wo = out_hw(geom, h, w)
+    out = torch.empty((nb, ho, wo, cout), device=x0.device, dtype=torch.float32)
+    rows, taps, wk = w_bf16.shape
+    c1 = 0 if x1 is None else x1.shape[3]
+    assert x0.dtype == torch.bfloat16 and w_bf16.dtype == torch.bfloat16 and w_bf16.is_contiguous() and taps == GEOM_TAPS[geom]
+    assert c0 + c1 <= wk and cout <= rows
+    part = torch.empty((groups, 2, cout), device=x0.device, dtype=torch.float32)
+    call("snn_conv_fprop_stats", geom, nb, h, w, ptr(x0), c0, _nhwc_ld(x0), ptr(x1), c1, 0 if x1 is None else _nhwc_ld(x1),
+         ptr(w_bf16), rows, wk, 0, cout, 0, ptr(out), nb // T, ptr(part), stream_ptr(),
+         work=("flop", _conv_flops(geom, nb, h, w, c0 + c1, cout), f"g{geom} nb{nb} {h}x{w} {c0 + c1}->{cout}"))
+    sums = torch.empty((T, 2, cout), device=x0.device, dtype=torch.float64)
+    call("snn_bn_stats_from_partials", ptr(part), ptr(sums), T, cout, gpt, stream_ptr(), work=("byte", 4.0 * part.numel()))
+    return out, sums
+
+
 def conv_dgrad(geom, dy, w_bf16, in_hw, ci, ci_off=0, out=None, out_dtype=torch.bfloat16, accumulate=False):
     """dx[NB,H,W,ci] for the conv-input channel range [ci_off, ci_off+ci); w_bf16 = the fprop weights
     [Cout][taps][Cin_tot], read in place."""
@@ -114,7 +146,8 @@ def bn_stats(y, T):
     c = y.shape[-1]
     p = y.numel() // (T * c)
     sums = torch.empty((T, 2, c), device=y.device, dtype=torch.float64)
-    call("snn_bn_stats", ptr(y), ptr(sums), T, p, c, stream_ptr(), work=("byte", 4.0 * y.numel()))
+    ws = torch.empty((int(_lib.lib().snn_bn_stats_workspace_floats(T, p, c)),), device=y.device, dtype=torch.float32)
+    call("snn_bn_stats", ptr(y), ptr(sums), ptr(ws), T, p, c, stream_ptr(), work=("byte", 4.0 * y.numel()))
     return sums
 
 

@@ -31,9 +31,14 @@ from ._lib import GEOM_1x1, GEOM_3x3_S1, GEOM_3x3_S2, GEOM_T2x2_S2
 class RunCtx:
     """Per-call context handed down the module tree."""
 
-    def __init__(self, store, T, want_state=False, want_mask=False, fp32_outputs=False):
+    def __init__(self, store, T, want_state=False, want_mask=False, fp32_outputs=False, live_T=None):
         self.store, self.T, self.want_state, self.want_mask, self.fp32_outputs = store, T, want_state, want_mask, fp32_outputs
         self.record = None      # optional dict: ConvBlock name -> its spike / activation output (tests, spike-rate probes)
+        # number of trailing timesteps whose head outputs are consumed (train.py:64-66 keeps only the LAST preds): layers
+        # WITHOUT temporal state (U-Net output 1x1 convs, Detect head) still run forward on every frame -- their
+        # BatchNorm running statistics advance per frame as in the reference -- but skip the all-zero backward of the
+        # dead frames.  None = every timestep is live.
+        self.live_T = live_T
 
 
 def _to_nhwc_bf16(x):
@@ -78,9 +83,14 @@ class ConvBlock(nn.Module):
             raise NotImplementedError("ConvBlock supports k3/p1/s{1,2}, k1/p0/s1 and depthwise k3 (the shapes on the path)")
         self.last_mask = None
 
-    def forward_seq(self, rc, x0, x1=None, v_init=None):
+    def forward_seq(self, rc, x0, x1=None, v_init=None, dead_frames_ok=False):
+        """dead_frames_ok: the caller guarantees this block's output reaches the loss only through the last rc.live_T
+        timesteps and feeds nothing with temporal state (true for the Detect head, NOT for U-Net blocks: the encoder
+        feeds the ConvLSTM and LIF blocks carry membranes)."""
         cfg = dict(store=rc.store, geom=self.geom, T=rc.T, bn=self.bn, neuron=self.neuron, training=self.training,
                    want_state=rc.want_state, want_mask=rc.want_mask)
+        if dead_frames_ok and rc.live_T is not None and self.neuron.kind == "silu" and rc.live_T < rc.T:
+            cfg["live_T"] = rc.live_T
         out, v = ConvBNActFn.apply(x0, x1, v_init, self.conv.weight, self.bn.weight, self.bn.bias, cfg)
         if rc.want_mask:
             self.last_mask = cfg.get("last_mask")
@@ -207,7 +217,9 @@ class TemporalUNet(nn.Module):
         d2, nm["up2"] = self.up2.forward_seq(rc, d1, x2, m.get("up2"))
         d3, nm["up3"] = self.up3.forward_seq(rc, d2, x1, m.get("up3"))
         od = torch.float32 if rc.fp32_outputs else torch.bfloat16
-        mk = lambda conv, x_: ConvBiasFn.apply(x_, conv.weight, conv.bias, dict(store=rc.store, geom=GEOM_1x1, out_dtype=od))
+        live_n = None if (rc.live_T is None or rc.live_T >= rc.T) else rc.live_T * (p3.shape[0] // rc.T)
+        mk = lambda conv, x_: ConvBiasFn.apply(x_, conv.weight, conv.bias,
+                                               dict(store=rc.store, geom=GEOM_1x1, out_dtype=od, live_n=live_n))
         outs = (mk(self.out_p3, d3), mk(self.out_p4, d2), mk(self.out_p5, d1))
         return outs, (new_lstm, nm)
 
@@ -316,6 +328,7 @@ class YOLOTemporalUNet(nn.Module):
         self.detection_head.reg_max = self.args.reg_max
         self.register_buffer("strides", strides, persistent=False)
         self.model = nn.ModuleList([self.detection_head])
+        self.skip_dead_backward = True      # see RunCtx.live_T (False: run the all-zero backward of the dead frames too)
 
     # ---- fused sequence path -------------------------------------------------------------
     def forward_sequence(self, frames, hidden_state=None, return_state=False, all_steps=False):
@@ -325,7 +338,7 @@ class YOLOTemporalUNet(nn.Module):
         st = store_for(self, frames.device)
         st.refresh_operands()
         feats = self.feature_extractor.forward_seq(frames, B, T)
-        rc = RunCtx(st, T, want_state=return_state)
+        rc = RunCtx(st, T, want_state=return_state, live_T=None if (all_steps or not self.skip_dead_backward) else 1)
         outs, new_state = self.temporal_unet.forward_seq(rc, feats, _unpack_hidden(hidden_state))
         det = self.detection_head.forward_seq(rc, outs, B, last_only=not all_steps)
         hidden = _pack_hidden(new_state, self.temporal_unet.neuron.kind) if return_state else None

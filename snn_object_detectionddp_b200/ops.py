@@ -32,6 +32,15 @@ def _bf16c(g):
     return g.contiguous()
 
 
+def _pad_dead(g_live, x_full, live):
+    """Gradient of the live tail -> full-size gradient with zeros for the dead leading frames."""
+    if g_live is None or live is None or g_live.shape[0] == x_full.shape[0]:
+        return g_live
+    g = torch.zeros(x_full.shape, device=g_live.device, dtype=g_live.dtype)
+    g[x_full.shape[0] - g_live.shape[0]:] = g_live
+    return g
+
+
 class ConvBNActFn(Function):
     """conv(cat[x0,x1]) -> per-timestep BatchNorm -> LIF scan over T (or SiLU).  One ConvBlock (model.py:9-18)."""
 
@@ -39,14 +48,18 @@ class ConvBNActFn(Function):
     def forward(ctx, x0, x1, v_init, weight, gamma, beta, cfg):
         st, geom, T, bn, neuron, training = cfg["store"], cfg["geom"], cfg["T"], cfg["bn"], cfg["neuron"], cfg["training"]
         cout = weight.shape[0]
+        sums = None
         if geom == K.GEOM_DW3x3:
             y = K.dw3x3_fprop(x0, st.w_master3(weight).view(9, cout))
+        elif training:
+            y, sums = K.conv_fprop_stats(geom, x0, st.w_fprop(weight), cout, T, x1=x1)    # BN sums fused into the epilogue
         else:
             y = K.conv_fprop(geom, x0, st.w_fprop(weight), cout, x1=x1)
         nb, ho, wo, _ = y.shape
         P = (nb // T) * ho * wo
         if training:
-            sums = K.bn_stats(y, T)
+            if sums is None:
+                sums = K.bn_stats(y, T)
             scale, shift, mean, invstd = K.bn_finalize(sums, gamma, beta, bn.running_mean, bn.running_var, T, cout, P,
                                                        bn.eps, bn.momentum, True)
             if bn.num_batches_tracked is not None:
@@ -74,6 +87,18 @@ class ConvBNActFn(Function):
         x0, x1, v_init, weight, gamma, y, scale, shift, mean, invstd = ctx.saved_tensors
         if g_out is None:
             g_out = torch.zeros(y.shape, device=y.device, dtype=torch.bfloat16)
+        live_T = cfg.get("live_T")
+        x0_full = x0
+        if live_T is not None and training and neuron.kind == "silu" and not ctx.has_v and g_vfinal is None:
+            # stateless layer, only the last live_T timesteps carry gradient: the per-timestep BatchNorm groups are
+            # independent, so the backward of the dead frames (all zeros) is skipped, not computed
+            n0 = (y.shape[0] // T) * (T - live_T)
+            x0, y, g_out = x0[n0:], y[n0:], g_out[n0:]
+            x1 = None if x1 is None else x1[n0:]
+            scale, shift, mean, invstd = scale[T - live_T:], shift[T - live_T:], mean[T - live_T:], invstd[T - live_T:]
+            T = live_T
+        else:
+            live_T = None
         gs = _bf16c(g_out)
         gvf = None if g_vfinal is None else g_vfinal.contiguous().view(-1).float()
         want_gv0 = ctx.has_v and ctx.needs_input_grad[2]
@@ -95,7 +120,7 @@ class ConvBNActFn(Function):
             K.dw3x3_wgrad(x0, dy, gw3.view(9, c))
             st.grad_done(weight)
             gx0 = K.dw3x3_dgrad(dy, st.w_master3(weight).view(9, c)) if ctx.needs_input_grad[0] else None
-            return gx0, None, (None if gv0 is None else gv0.view(v_init.shape)), None, None, None, None
+            return _pad_dead(gx0, x0_full, live_T), None, (None if gv0 is None else gv0.view(v_init.shape)), None, None, None, None
         K.conv_wgrad(geom, x0, dy, gw3, w_coff=0)
         if ctx.has_x1:
             K.conv_wgrad(geom, x1, dy, gw3, w_coff=x0.shape[3])
@@ -108,6 +133,9 @@ class ConvBNActFn(Function):
             gx1 = K.conv_dgrad(geom, dy, st.w_fprop(weight), in_hw, x1.shape[3], ci_off=x0.shape[3])
         if gv0 is not None:
             gv0 = gv0.view(v_init.shape)
+        if live_T is not None:
+            gx0 = _pad_dead(gx0, x0_full, live_T)
+            gx1 = None if gx1 is None else _pad_dead(gx1, ctx.saved_tensors[1], live_T)
         return gx0, gx1, gv0, None, None, None, None
 
 
@@ -128,6 +156,11 @@ class ConvBiasFn(Function):
         cfg = ctx.cfg
         st, geom = cfg["store"], cfg["geom"]
         x0, weight, bias = ctx.saved_tensors
+        live_n = cfg.get("live_n")
+        x0_full = x0
+        if live_n is not None and live_n < x0.shape[0]:
+            n0 = x0.shape[0] - live_n          # only the trailing live_n samples carry gradient (see RunCtx.live_T)
+            x0, g_out = x0[n0:], g_out[n0:]
         dy = _bf16c(g_out)
         gw3 = st.grad_view(weight, three_d=True)
         K.conv_wgrad(geom, x0, dy, gw3)
@@ -137,7 +170,12 @@ class ConvBiasFn(Function):
             st.grad_done(bias)
         gx0 = None
         if ctx.needs_input_grad[0]:
-            gx0 = K.conv_dgrad(geom, dy, st.w_fprop(weight), (x0.shape[1], x0.shape[2]), x0.shape[3])
+            if x0 is x0_full:
+                gx0 = K.conv_dgrad(geom, dy, st.w_fprop(weight), (x0.shape[1], x0.shape[2]), x0.shape[3])
+            else:
+                gx0 = torch.zeros(x0_full.shape, device=dy.device, dtype=torch.bfloat16)
+                K.conv_dgrad(geom, dy, st.w_fprop(weight), (x0.shape[1], x0.shape[2]), x0.shape[3],
+                             out=gx0[x0_full.shape[0] - x0.shape[0]:])
         return gx0, None, None, None
 
 

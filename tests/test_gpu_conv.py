@@ -94,6 +94,36 @@ def test_fprop_cta_pair_equals_single_cta(geom, nb, h, w, cin, cout):
     assert rel_err(outs[("pair+tma", torch.float32)], ref_conv(geom, x, wgt, bias)) < 1e-5
 
 
+@pytest.mark.parametrize("geom,T,B,h,w,cin,cout,c1", [(G31, 4, 2, 32, 32, 144, 128, 0), (G31, 3, 2, 16, 16, 256, 256, 144),
+                                                      (G32, 2, 4, 16, 16, 128, 256, 0), (G31, 2, 8, 4, 4, 256, 512, 0),
+                                                      (G31, 2, 8, 12, 20, 64, 144, 0), (G11, 2, 2, 16, 16, 144, 64, 0),
+                                                      (G31, 4, 2, 4, 4, 128, 128, 0)])
+def test_fprop_fused_bn_statistics(geom, T, B, h, w, cin, cout, c1):
+    """Per-timestep BatchNorm sums produced by the conv epilogue == a separate pass over the conv output (fp64 sums of
+    the same fp32 values: 1e-6 of sum |y|), the conv output itself is unchanged, and two launches agree bit for bit.  The last
+    case (B = 2 on 4x4 maps: a 128-pixel tile spans 4 timesteps) must report 'not available'."""
+    setup_exact()
+    K = _k()
+    taps = {G31: 9, G32: 9, G11: 1}[geom]
+    x0 = _mk(T * B, h, w, cin, 21, spikes=True)
+    x1 = _mk(T * B, h, w, c1, 22) if c1 else None
+    wgt = _mkw(cout, taps, cin + c1, 23)
+    y, sums = K.conv_fprop_stats(geom, x0, wgt, cout, T, x1=x1)
+    y_ref = K.conv_fprop(geom, x0, wgt, cout, x1=x1)
+    assert torch.equal(y, y_ref)
+    if (h, w, B) == (4, 4, 2):
+        assert sums is None
+        return
+    assert sums is not None
+    yt = y_ref.double().reshape(T, -1, cout)
+    ref = torch.stack([yt.sum(1), (yt * yt).sum(1)], 1)
+    # 32-row partials are fp32 sums: error is relative to sum |y| (not to a possibly cancelling total)
+    scale = torch.stack([yt.abs().sum(1), (yt * yt).sum(1)], 1)
+    assert bool(((sums - ref).abs() <= 1e-6 * scale + 1e-9).all()), float(((sums - ref).abs() / (scale + 1e-9)).max())
+    y2, sums2 = K.conv_fprop_stats(geom, x0, wgt, cout, T, x1=x1)
+    assert torch.equal(sums, sums2) and torch.equal(y, y2)
+
+
 def test_fprop_concat_two_sources():
     """enc2 = conv(cat([down1(x1), p4])) (reference model.py:126) without materialising the cat."""
     setup_exact()

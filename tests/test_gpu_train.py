@@ -160,6 +160,43 @@ def test_training_steps_track_the_oracle(neuron):
         assert max(agree) < 1e-3
 
 
+def test_skipping_dead_frame_backward_changes_nothing():
+    """Only the last frame's predictions reach the loss (train.py:64-74).  Stateless layers (U-Net output convs, Detect
+    head) skip the all-zero backward of the earlier frames.  The forward is deterministic (loss and BN buffers must be
+    bit-identical); the backward is not (fp32 atomics in the BN reductions and the split-K wgrad), and this tiny
+    geometry (2 frames, 2x2 bottleneck) amplifies that noise through ~40 batch-norm backward passes, so the gradients
+    are compared (a) tightly on the layers the shortcut touches and (b) against the run-to-run noise elsewhere."""
+    setup_exact()
+    from snn_object_detectionddp_b200.params import store_for
+    from snn_object_detectionddp_b200.loss import v8DetectionLoss
+    res = []
+    for skip in (True, False, False):
+        _, net = _models("lif", seed=7)
+        net.skip_dead_backward = skip
+        net.train()
+        B, T, HW = 2, 3, 128
+        frames, labels = MO.synthetic_batch(B, T, HW, HW, seed=13)
+        frames, labels = frames.to(DEV), labels.to(DEV)
+        st = store_for(net, DEV)
+        st.zero_grad()
+        det, _ = net.forward_sequence(frames)
+        loss, items = v8DetectionLoss(net)(det, {"batch_idx": labels[:, 0], "cls": labels[:, 1], "bboxes": labels[:, 2:]})
+        loss.sum().backward()
+        torch.cuda.synchronize()
+        res.append((items.clone(), st.flat_g.clone(), {k: v.clone() for k, v in net.state_dict().items() if "running" in k}, st))
+    (it_a, g_a, bn_a, st), (it_b, g_b, bn_b, _), (it_c, g_c, _, _) = res
+    assert torch.equal(it_a, it_b) and torch.equal(it_b, it_c)
+    for k in bn_a:
+        assert torch.equal(bn_a[k], bn_b[k]), k
+    assert float(g_b.abs().max()) > 0
+    noise = float(rel_err(g_b, g_c))
+    assert float(rel_err(g_a, g_b)) < 3 * noise + 1e-5, (float(rel_err(g_a, g_b)), noise)
+    for e in st.entries:
+        if e.name.startswith("detection_head.") or ".out_p" in e.name:
+            sl = slice(e.offset, e.offset + e.numel)
+            assert float(rel_err(g_a[sl], g_b[sl])) < 3 * float(rel_err(g_b[sl], g_c[sl])) + 2e-4, e.name
+
+
 def test_drop_in_forward_signature_and_eval_outputs():
     """model(frame, hidden) -> (detections, hidden) with the reference's return structure (model.py:197-211):
     train -> list of 3 maps [B, nc+64, h, w]; eval -> (decoded [B, 4+nc, A], maps)."""
