@@ -143,6 +143,19 @@ int snn_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf
 int snn_detect_decode(const float* distri, const float* scores, const float* anchors, const float* stride,
                       int B, int A, int nc, int reg_max, int xywh, float* boxes, float* probs, void* stream);
 
+/* ---- non-maximum suppression: replaces ultralytics.utils.nms.non_max_suppression (+ torchvision.ops.nms) as called at
+ *      visualize.py:73-78 (conf 0.3, iou 0.45, multi_label=True) and eval_2.py:108 (conf 0.001, iou 0.6).
+ *      pred fp32 [B][4+nc][A] = what Detect returns in eval mode (xywh pixels + class scores).  Per image: candidates with
+ *      score > conf_thres (multi_label: every (anchor, class) pair; else the best class), sorted by score descending with
+ *      ties in enumeration order, greedy IoU suppression with the per-class box offset cls*max_wh (unless agnostic), at most
+ *      max_det (<= 512) rows.  out fp32 [B][max_det][6] = x1 y1 x2 y2 conf cls, out_idx int32 [B][max_det] = enumeration
+ *      index (anchor*nc + cls | anchor) of each kept row, counts int32 [B].  `keys` is a caller-owned workspace of
+ *      B * snn_nms_workspace_keys() 64-bit words.  No host synchronisation. ---- */
+long long snn_nms_workspace_keys(int nc, int A, int multi_label);
+int snn_nms(const float* pred, int B, int nc, int A, float conf_thres, float iou_thres, int multi_label, int agnostic,
+            int max_det, int max_nms, float max_wh, unsigned long long* keys, long long keys_per_image,
+            float* out, int* out_idx, int* counts, void* stream);
+
 /* ---- detection-loss tail: replaces the per-anchor part of ultralytics v8DetectionLoss called at train.py:74
  *      (BCE class loss, CIoU box loss, DFL) given the assigner's targets.  N = B*A anchors (A = anchors per image,
  *      scale-major), distri fp32 [N][4*reg_max], scores / tscores fp32 [N][nc], anchors fp32 [A][2] (grid units),

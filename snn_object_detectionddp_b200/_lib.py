@@ -42,6 +42,7 @@ _SIGNATURES = {
     "snn_detect_decode": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "snn_detect_loss_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     "snn_detect_loss_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "snn_nms": [_P, _I, _I, _I, _F, _F, _I, _I, _I, _I, _F, _P, _L, _P, _P, _P, _P],
     "snn_grad_sumsq": [_P, _L, _P, _I, _P],
     "snn_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _I, _P],
 }
@@ -55,7 +56,7 @@ class SnnKernelError(RuntimeError):
 
 
 def exported_symbols():
-    return sorted(list(_SIGNATURES) + ["snn_last_error", "snn_version", "snn_debug_set", "snn_conv_stats_groups", "snn_bn_stats_workspace_floats"])
+    return sorted(list(_SIGNATURES) + ["snn_last_error", "snn_version", "snn_debug_set", "snn_conv_stats_groups", "snn_bn_stats_workspace_floats", "snn_nms_workspace_keys"])
 
 
 def lib():
@@ -77,6 +78,8 @@ def lib():
         L.snn_conv_stats_groups.restype = _L
         L.snn_bn_stats_workspace_floats.argtypes = [_I, _I, _I]
         L.snn_bn_stats_workspace_floats.restype = _L
+        L.snn_nms_workspace_keys.argtypes = [_I, _I, _I]
+        L.snn_nms_workspace_keys.restype = _L
         L.snn_debug_set.argtypes = [_I, _I]
         L.snn_debug_set.restype = None
         _lib = L

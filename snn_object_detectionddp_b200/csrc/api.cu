@@ -35,6 +35,9 @@ void debug_set(int k, int v);
 int conv_fprop(int, int, int, int, const void*, int, long long, const void*, int, long long, const void*, int, int, int, int,
                int, const float*, void*, int, long long, int, int, cudaStream_t, float*, int);
 long long conv_stats_groups(int, int, int, int, int, int*);
+long long nms_workspace_keys(int, int, int);
+int launch_nms(const float*, int, int, int, float, float, int, int, int, int, float, unsigned long long*, long long, float*, int*,
+               int*, cudaStream_t);
 int launch_bn_stats_from_partials(const float*, double*, int, int, int, cudaStream_t);
 int conv_dgrad(int, int, int, int, const void*, int, long long, const void*, int, int, int, void*, int, long long, int, int,
                cudaStream_t);
@@ -100,6 +103,13 @@ int snn_conv_fprop_stats(int geom, int NB, int H, int W, const void* x0, int C0,
                          int frames_per_step, float* partials, void* stream) {
     return conv_fprop(geom, NB, H, W, x0, C0, ld0, x1, C1, ld1, w, w_rows, w_K, w_coff, Cout, w_row_off, nullptr, out, 1,
                       Cout, 0, 0, ST, partials, frames_per_step);
+}
+long long snn_nms_workspace_keys(int nc, int A, int multi_label) { return nms_workspace_keys(nc, A, multi_label && nc > 1); }
+int snn_nms(const float* pred, int B, int nc, int A, float conf_thres, float iou_thres, int multi_label, int agnostic,
+            int max_det, int max_nms, float max_wh, unsigned long long* keys, long long keys_per_image, float* out,
+            int* out_idx, int* counts, void* stream) {
+    return launch_nms(pred, B, nc, A, conf_thres, iou_thres, multi_label, agnostic, max_det, max_nms, max_wh, keys,
+                      keys_per_image, out, out_idx, counts, ST);
 }
 int snn_bn_stats_from_partials(const float* partials, double* sums, int T, int C, int groups_per_step, void* stream) {
     return launch_bn_stats_from_partials(partials, sums, T, C, groups_per_step, ST);

@@ -54,6 +54,7 @@ struct ConvGemmParams {
     int b_boxes;                      // b_mn: number of 64-column boxes per stage
     float* stats;                     // tma_out + fp32: per-(32-row group, column) sum / sum-of-squares partials [4*m_tiles][2][n_store]
     int tma_out;                      // epilogue through swizzled smem staging + TMA tensor stores (coalesced) instead of per-thread rows
+    int ksplit;                       // K split over the tap segments (fp32 output, TMA reduce-add): fills the GPU on small-M convs
     int dbg;                          // timing experiments only: bit 0 = producer skips the TMA loads, bit 1 = no MMA issue
     Phase phase[4];
 };
@@ -117,7 +118,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;    // 128-pixel tiles
     const int m_work = PAIR ? (m_tiles + 1) >> 1 : m_tiles;   // work items along M (pairs of m-tiles)
-    const int total_tiles = m_work * p.n_blocks * p.nphase;
+    const int total_tiles = m_work * p.n_blocks * p.nphase * p.ksplit;   // tile = (m, n-block, phase, k-split), m fastest
     const int bn_cta = PAIR ? p.BN >> 1 : p.BN;               // B columns staged by this CTA
 
     if (warp == 0) {
@@ -157,11 +158,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int tile = worker; tile < total_tiles; tile += nworkers) {
             const int mt = (tile % m_work) * (PAIR ? 2 : 1) + (int)rank, rest = tile / m_work;
             const int ncol0 = p.wn_off + (rest % p.n_blocks) * p.BN + (int)rank * bn_cta;
-            const Phase& ph = p.phase[rest / p.n_blocks];
+            const int pk = rest / p.n_blocks;
+            const Phase& ph = p.phase[pk % p.nphase];
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
             const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;   // tn == tiles_n (odd tail of a pair): all OOB -> zeros
-            const int nseg = ph.nseg;
-            for (int sg = 0; sg < nseg; ++sg) {
+            const int spp = ph.nseg / p.ksplit, sg0 = (pk / p.nphase) * spp;
+            for (int sg = sg0; sg < sg0 + spp; ++sg) {
                 const Seg g = ph.seg[sg];
                 const CUtensorMap* tmA = g.src ? &tmA1 : &tmA0;
                 const int cw = w0 + g.dw, chh = h0 + g.dh;
@@ -212,9 +214,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             uint32_t par = 0;
             uint32_t a_s = sbase;
             for (int tile = worker; tile < total_tiles; tile += nworkers, ++lt) {
-                const Phase& ph = p.phase[(tile / m_work) / p.n_blocks];
+                const int pk = (tile / m_work) / p.n_blocks;
+                const Phase& ph = p.phase[pk % p.nphase];
+                const int spp = ph.nseg / p.ksplit, sg0 = (pk / p.nphase) * spp;
                 int total = 0;
-                for (int i = 0; i < ph.nseg; ++i) total += ph.seg[i].nchunk;
+                for (int i = sg0; i < sg0 + spp; ++i) total += ph.seg[i].nchunk;
                 const int acc = lt & 1;
                 mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((lt >> 1) & 1) ^ 1));   // epilogue drained this buffer
                 tc_fence_after();
@@ -251,10 +255,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int row = q * 32 + lane;
         const int wl = row % p.bw, hl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
         int lt = 0;
+        uint32_t gcc = 0;     // staging-tile counter across all tiles of this warp: two buffers in rotation
         for (int tile = worker; tile < total_tiles; tile += nworkers, ++lt) {
             const int mt = (tile % m_work) * (PAIR ? 2 : 1) + (int)rank, rest = tile / m_work;
             const int ncol0 = (rest % p.n_blocks) * p.BN;
-            const Phase& ph = p.phase[rest / p.n_blocks];
+            const Phase& ph = p.phase[(rest / p.n_blocks) % p.nphase];
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
             const int n = tn * p.bn + nl, hd = th * p.bh + hl, wd = tw * p.bw + wl;
             const bool valid = (n < p.NB) && (hd < p.Hd) && (wd < p.Wd);
@@ -276,8 +281,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const int cph = (p.os == 2 ? ph.oph : 0);
                 const uint32_t stg0 = sbase + (uint32_t)stages * stage_bytes + (uint32_t)q * 8192u;
                 const int nch = (min(p.BN, p.n_store - ncol0) + CH - 1) / CH;
-                for (int cc = 0; cc < nch; ++cc) {
-                    const uint32_t buf = stg0 + (uint32_t)(cc & 1) * 4096u;
+                for (int cc = 0; cc < nch; ++cc, ++gcc) {
+                    const uint32_t buf = stg0 + (gcc & 1u) * 4096u;
                     uint32_t r[32];
                     if (p.out_f32) {
                         tmem_ld16(trow + (uint32_t)(cc * 32), r);
@@ -308,7 +313,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             }
                         }
                     }
-                    if (cc >= 2) {                       // the store that read this buffer two chunks ago has drained it
+                    if (gcc >= 2) {                      // the store that read this buffer two chunks ago has drained it
                         if (lane == 0) bulk_wait_group_read<1>();
                         __syncwarp();
                     }
@@ -344,15 +349,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         bulk_commit_group();
                     }
                 }
-                // TMEM reads are complete: hand the accumulator back, then drain the staging buffers for the next tile
+                // TMEM reads are complete: hand the accumulator back (staging buffers keep rotating across tiles)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     if (PAIR) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[acc]) & kPeerBitMask);
                     else mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-                    bulk_wait_group_read<0>();
                 }
-                __syncwarp();
                 continue;
             }
             const int nchunks = p.BN >> 4;
@@ -709,6 +712,7 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     const size_t smem = (size_t)stages * p.stage_bytes + stage_extra + 1024;
     p.n_blocks = (p.n_store + p.BN - 1) / p.BN;
     p.dbg = g_debug_flags[7];
+    if (p.ksplit < 1) p.ksplit = 1;
     CUtensorMap b, o;
     if (make_w_map(&b, wd.ptr, wd.wN, wd.wT, wd.wK, p.b_mn ? 64 : bn_cta)) return 2;
     if (p.tma_out) {
@@ -718,14 +722,14 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
         o = b;
     }
     if (!pair) {
-        const int total_tiles = m_tiles * p.n_blocks * p.nphase;
+        const int total_tiles = m_tiles * p.n_blocks * p.nphase * p.ksplit;
         int grid = num_sms();
         if (g_debug_flags[5] > 0) grid = g_debug_flags[5];
         if (grid > total_tiles) grid = total_tiles;
         conv_gemm_kernel<false><<<grid, 192, smem, st>>>(a0, a1, b, o, p);
         return check_cuda(cudaGetLastError(), "conv_gemm_kernel launch");
     }
-    const int total_tiles = ((m_tiles + 1) / 2) * p.n_blocks * p.nphase;
+    const int total_tiles = ((m_tiles + 1) / 2) * p.n_blocks * p.nphase * p.ksplit;
     int pairs = num_sms() / 2;
     if (g_debug_flags[5] > 0) pairs = g_debug_flags[5];
     if (pairs > total_tiles) pairs = total_tiles;
@@ -895,6 +899,21 @@ int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long lo
         Phase& ph = p.phase[0];
         for (int a = 0; a < 2; ++a)
             for (int bb = 0; bb < 2; ++bb) ph.seg[ph.nseg++] = mkseg(0, (int)(bb * ld_dy), 0, a, 0, a * 2 + bb, 0, Cout);
+    }
+    // Small-M convs (ConvLSTM recurrent dgrad: 8 pixel tiles x 4 column blocks = 16 work items for 74 CTA pairs) split K
+    // over the taps; the partial products meet in the fp32 output through TMA reduce-add (zero-filled first).
+    if (dx_f32 && !accumulate && p.nphase == 1 && dx_coff == 0 && dx_ld == Ci && g_debug_flags[0] != 1) {
+        const int m_work = (p.tiles_w * p.tiles_h * p.tiles_n + 1) / 2;
+        const int items = m_work * ((Ci + p.BN - 1) / p.BN);
+        const int nseg = p.phase[0].nseg, pairs = num_sms() / 2;
+        int ks = 1;
+        for (int cand = 1; cand <= nseg; ++cand)
+            if (nseg % cand == 0 && items * cand <= 2 * pairs) ks = cand;
+        if (ks > 1 && items <= pairs / 2) {
+            SNN_CUDA_OK(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)NB * H * W * Ci, st));
+            p.ksplit = ks;
+            p.accumulate = 1;
+        }
     }
     return launch_conv_gemm(a0, a0, wd, p, st);
 }

@@ -37,6 +37,21 @@ def _build(dev):
     return net.to(dev)
 
 
+def _backward_only(tr, frames, batch):
+    """Trainer.train_step without the optimizer: returns the (all-reduced) flat gradient and the loss items."""
+    tr.model.train()
+    tr.store.zero_grad()
+    if tr.bucketer is not None:
+        tr.bucketer.begin_step()
+    det, _ = tr.model.forward_sequence(frames)
+    loss, items = tr.loss_fn(det, {"padded": tuple(t.to(frames.device) for t in batch["padded"])})
+    loss.sum().backward()
+    if tr.bucketer is not None:
+        tr.bucketer.finish()
+    torch.cuda.synchronize()
+    return tr.store.flat_g.clone(), items.clone()
+
+
 def _worker(rank, world, port, mode, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -49,6 +64,16 @@ def _worker(rank, world, port, mode, out):
     assert tr.bucketer is not None and len(tr.bucketer.buckets) > 3
     B, T, HW = 2, 2, 128
     losses = []
+    if mode == "grad":
+        # ONE backward with the bucketed all-reduce, no optimizer step: the averaged gradient of identical per-rank batches
+        frames, labels = synthetic_batch(B, T, HW, HW, seed=100)
+        g, items = _backward_only(tr, frames.to(dev), tr.prepare_batch(labels, B, max_boxes=8))
+        launched = list(tr.bucketer.launch_order)
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank == 0:
+            out.put((True, g.cpu().numpy(), [items.cpu().numpy()], launched, False, len(tr.bucketer.buckets)))
+        return
     for step in range(4):
         seed = 100 + step + (0 if mode == "same" else 17 * rank)
         frames, labels = synthetic_batch(B, T, HW, HW, seed=seed)
@@ -90,23 +115,26 @@ needs2 = pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs"
 
 @needs2
 def test_ddp_same_batch_equals_single_process():
-    same, flat, losses, launched, _, nb = _run("same")
-    assert same
+    """Ranks fed the SAME batch: the bucketed, backward-overlapped all-reduce (AVG) must reproduce the single-process
+    gradient.  The backward is not bit-reproducible (fp32 atomics in split-K wgrad / BN reductions) and this tiny
+    geometry amplifies that noise, so the bound is the run-to-run noise of the single-process gradient itself; the
+    forward is deterministic, so the loss must match exactly."""
+    _, g_ddp, losses, launched, _, nb = _run("grad")
     assert len(launched) == nb and launched[0] == 0      # bucket 0 holds the LAST tensors: launched first, during backward
-    # single process, same data
     from snn_object_detectionddp_b200.data import synthetic_batch
     from snn_object_detectionddp_b200.trainer import Trainer
-    net = _build("cuda:0")
-    tr = Trainer(net, total_steps=20, device="cuda:0")
-    for step in range(4):
-        frames, labels = synthetic_batch(2, 2, 128, 128, seed=100 + step)
-        _, items = tr.train_step(frames.cuda(), tr.prepare_batch(labels, 2, max_boxes=8))
-        assert torch.allclose(items.cpu(), losses[step], rtol=2e-2, atol=1e-3), (step, items, losses[step])
-    ref = tr.store.flat_p.detach().cpu()
-    # wgrad accumulates with fp32 atomics (order varies run to run) and AdamW's first steps are +-lr per element, so
-    # compare the parameter movement statistically rather than bit-for-bit
-    diff = (flat - ref).abs()
-    assert float(diff.max()) <= 4 * 1e-4 and float((diff > 1e-6).float().mean()) < 0.02
+    from tests.gpu_util import rel_err
+    ref = []
+    for _ in range(2):
+        net = _build("cuda:0")
+        tr = Trainer(net, total_steps=20, device="cuda:0")
+        frames, labels = synthetic_batch(2, 2, 128, 128, seed=100)
+        ref.append(_backward_only(tr, frames.cuda(), tr.prepare_batch(labels, 2, max_boxes=8)))
+    (g1, it1), (g2, it2) = ref
+    assert torch.equal(it1, it2) and torch.equal(it1.cpu(), losses[0])
+    noise = float(rel_err(g1, g2))
+    err = float(rel_err(g_ddp.cuda(), g1))
+    assert float(g1.abs().max()) > 0 and err < 3 * noise + 1e-5, (err, noise)
 
 
 @needs2

@@ -194,7 +194,8 @@ def test_skipping_dead_frame_backward_changes_nothing():
     for e in st.entries:
         if e.name.startswith("detection_head.") or ".out_p" in e.name:
             sl = slice(e.offset, e.offset + e.numel)
-            assert float(rel_err(g_a[sl], g_b[sl])) < 3 * float(rel_err(g_b[sl], g_c[sl])) + 2e-4, e.name
+            # + bf16 rounding of dy (2^-9 per element) summed over as few as 32 pixels per channel
+            assert float(rel_err(g_a[sl], g_b[sl])) < 3 * float(rel_err(g_b[sl], g_c[sl])) + 3e-3, e.name
 
 
 def test_drop_in_forward_signature_and_eval_outputs():
