@@ -262,7 +262,6 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
-    clocks = sampler.stop() if rank == 0 else None
     last_loss = [float(v) for v in items]
 
     # ---------------- end to end through the public API with host buffers ----------------
@@ -315,6 +314,8 @@ def run_ours(args):
                "d2h_bytes_per_step": 12, "ms_per_step": float(ems) / args.steps,
                "api": ("Trainer.train_step_graphed" if graphed else "Trainer.train_step")
                       + " on double-buffered pinned host frames (fp32 [B,T,3,H,W]) + padded labels"}
+
+    clocks = sampler.stop() if rank == 0 else None          # sampled over both timed regions (device-resident + e2e)
 
     # ---------------- per-kernel accounting + roofline of the dominant kernel ----------------
     roofline, kernels_summary = None, None

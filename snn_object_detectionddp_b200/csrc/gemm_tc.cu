@@ -69,6 +69,7 @@ struct WgradParams {
     int bn, bh, bw;                   // pixel box (product == 64)
     int tiles_w, tiles_h, tiles_n, total_tiles;
     int ksplit, tiles_per_split;
+    int m_items;                      // work items along Cout (128 rows per CTA, 256 per CTA pair)
     int NT;                           // cin per CTA (multiple of 64, <= 256)
     int n_ci_tiles;
     int Cout, Ci;
@@ -433,49 +434,60 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 // wgrad kernel: dW[co, tap, ci] += sum_{pixels} dY[pix, co] * X[pix + tap, ci]
 // A = dY tile (M = 128 couts, K = 64 pixels), B = X tile (N = NT cins, K = 64 pixels), both MN-major.
 // ------------------------------------------------------------------------------------------
+// Persistent: a CTA (pair) walks work items (cout tile, tap x cin tile, pixel range); the accumulator is double-buffered
+// in TMEM so the epilogue of item i overlaps the K loop of item i+1 (v1 ran one item per CTA: TMEM allocation, barrier
+// set-up and a serialised row-wise red.global.add epilogue cost as much as the 64-stage K loop itself, profiles/r1).
+// Epilogue: 32 x 32 fp32 pieces through the 128B-swizzled staging tile, then ONE TMA reduce-add per piece into the flat
+// gradient buffer (split-K partial sums meet there; coalesced, asynchronous).
+// PAIR: two CTAs share one 256-cout x NT-cin accumulator tile (cta_group::2): each stages its own 128 couts of dY and HALF
+// of the X tile.
+template <bool PAIR>
 __global__ void __launch_bounds__(192, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
-                  const __grid_constant__ WgradParams p) {
+                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int stages = p.stages;
-    const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+    const uint32_t stage_bytes = (uint32_t)p.stage_bytes;   // per CTA
     constexpr uint32_t kBox = 64 * 128;  // one [64 pixels x 64 channels] bf16 box
-
-    const int co0 = blockIdx.x * 128;
-    const int tap_i = blockIdx.y / p.n_ci_tiles;
-    const int ci0 = (blockIdx.y % p.n_ci_tiles) * p.NT;
-    const WTap tp = p.taps[tap_i];
-    const int t_begin = blockIdx.z * p.tiles_per_split;
-    const int t_end = min(p.total_tiles, t_begin + p.tiles_per_split);
-    const int nxb = p.NT >> 6;  // X boxes per stage
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int ny = p.n_ci_tiles * p.ntaps;
+    const int total_items = p.m_items * ny * p.ksplit;        // item = (m, tap x cin tile, pixel range), m fastest
+    const int nxb = (PAIR ? p.NT >> 1 : p.NT) >> 6;           // X boxes staged by this CTA
+    const int tiles_hw = p.tiles_w * p.tiles_h;
 
     if (warp == 0) {
         if (lane == 0) {
             tma_prefetch_desc(&tmG);
             tma_prefetch_desc(&tmX);
+            tma_prefetch_desc(&tmW);
         }
         __syncwarp();
-        tmem_alloc<kTmemCols>(smem_u32(&tmem_base_s));
+        if (PAIR) tmem_alloc_pair<2 * kTmemCols>(smem_u32(&tmem_base_s)); else tmem_alloc<2 * kTmemCols>(smem_u32(&tmem_base_s));
     } else if (warp == 1 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
-        mbar_init(smem_u32(&tmem_full_bar), 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+            mbar_init(smem_u32(&tmem_empty_bar[a]), PAIR ? 8 : 4);
+        }
         mbar_fence_init();
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    const int total = max(0, t_end - t_begin);
 
     // warp-uniform role loops (see conv_gemm_kernel): one elected lane issues, loop state stays in uniform registers
     if (warp == 0) {
@@ -483,81 +495,133 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         int s = 0;
         uint32_t par = 0;
         uint32_t g_s = sbase;
-        int tw = t_begin % p.tiles_w, th = (t_begin / p.tiles_w) % p.tiles_h, tn = t_begin / (p.tiles_w * p.tiles_h);
-        const int gc0 = tp.g_dc + co0, xc0 = tp.x_dc + ci0;
-        for (int it = 0; it < total; ++it) {
-            const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-            mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
-            if (lead) {
-                const uint32_t fb = smem_u32(&full_bar[s]);
-                mbar_expect_tx(fb, stage_bytes);
-                tma_load_5d(g_s, &tmG, fb, gc0, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
-                tma_load_5d(g_s + kBox, &tmG, fb, gc0 + 64, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
-                const uint32_t x_s = g_s + 2 * kBox;
-                for (int b = 0; b < nxb; ++b)
-                    tma_load_5d(x_s + b * kBox, &tmX, fb, xc0 + b * 64, w0 + tp.x_dw, tp.x_dhp, h0 + tp.x_dh, n0);
+        for (int item = worker; item < total_items; item += nworkers) {
+            const int mi = item % p.m_items, y = (item / p.m_items) % ny, z = item / (p.m_items * ny);
+            const int co0 = PAIR ? mi * 256 + (int)rank * 128 : mi * 128;
+            const WTap tp = p.taps[y / p.n_ci_tiles];
+            const int ci0 = (y % p.n_ci_tiles) * p.NT + (PAIR ? (int)rank * (p.NT >> 1) : 0);
+            const int t_begin = z * p.tiles_per_split;
+            const int total = min(p.total_tiles, t_begin + p.tiles_per_split) - t_begin;
+            int tw = t_begin % p.tiles_w, th = (t_begin / p.tiles_w) % p.tiles_h, tn = t_begin / tiles_hw;
+            const int gc0 = tp.g_dc + co0, xc0 = tp.x_dc + ci0;
+            for (int it = 0; it < total; ++it) {
+                const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+                mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
+                if (lead) {
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    const uint32_t x_s = g_s + 2 * kBox;
+                    if (!PAIR) {
+                        mbar_expect_tx(fb, stage_bytes);
+                        tma_load_5d(g_s, &tmG, fb, gc0, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
+                        tma_load_5d(g_s + kBox, &tmG, fb, gc0 + 64, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
+                        for (int b = 0; b < nxb; ++b)
+                            tma_load_5d(x_s + b * kBox, &tmX, fb, xc0 + b * 64, w0 + tp.x_dw, tp.x_dhp, h0 + tp.x_dh, n0);
+                    } else {
+                        if (rank == 0) mbar_expect_tx(fb, 2u * stage_bytes);
+                        tma_load_5d_pair(g_s, &tmG, fb, gc0, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
+                        tma_load_5d_pair(g_s + kBox, &tmG, fb, gc0 + 64, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
+                        for (int b = 0; b < nxb; ++b)
+                            tma_load_5d_pair(x_s + b * kBox, &tmX, fb, xc0 + b * 64, w0 + tp.x_dw, tp.x_dhp, h0 + tp.x_dh, n0);
+                    }
+                }
+                g_s += stage_bytes;
+                if (++s == stages) { s = 0; par ^= 1u; g_s = sbase; }
+                if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
             }
-            g_s += stage_bytes;
-            if (++s == stages) { s = 0; par ^= 1u; g_s = sbase; }
-            if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
         }
     } else if (warp == 1) {
-        const bool lead = elect_one();
-        const uint32_t idesc = umma_idesc_bf16(128, p.NT, 1, 1);
-        const uint32_t desc_hi = ((uint32_t)p.sbo_bytes >> 4) | (1u << 14) | (2u << 29);
-        const uint32_t lo_c = (((uint32_t)p.lbo_bytes >> 4) & 0x3FFFu) << 16;
-        int s = 0;
-        uint32_t par = 0;
-        uint32_t g_s = sbase;
-        for (int it = 0; it < total; ++it) {
-            mbar_wait(smem_u32(&full_bar[s]), par);
-            tc_fence_after();
-            if (lead) {
-                const uint32_t a_lo = lo_c | ((g_s & 0x3FFFFu) >> 4);
-                const uint32_t b_lo = lo_c | (((g_s + 2 * kBox) & 0x3FFFFu) >> 4);
+        if (rank == 0) {
+            const bool lead = elect_one();
+            const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, p.NT, 1, 1);
+            const uint32_t desc_hi = ((uint32_t)p.sbo_bytes >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t lo_c = (((uint32_t)p.lbo_bytes >> 4) & 0x3FFFu) << 16;
+            int s = 0, li = 0;
+            uint32_t par = 0;
+            uint32_t g_s = sbase;
+            for (int item = worker; item < total_items; item += nworkers, ++li) {
+                const int t_begin = (item / (p.m_items * ny)) * p.tiles_per_split;
+                const int total = min(p.total_tiles, t_begin + p.tiles_per_split) - t_begin;
+                const int acc = li & 1;
+                mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((li >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(acc * kTmemCols);
+                for (int it = 0; it < total; ++it) {
+                    mbar_wait(smem_u32(&full_bar[s]), par);
+                    tc_fence_after();
+                    if (lead) {
+                        const uint32_t a_lo = lo_c | ((g_s & 0x3FFFFu) >> 4);
+                        const uint32_t b_lo = lo_c | (((g_s + 2 * kBox) & 0x3FFFFu) >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // 16 pixels (rows of 128 B) per MMA
-                    const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (2048u >> 4) * k);
-                    const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (2048u >> 4) * k);
-                    umma_bf16(tmem_base, adesc, bdesc, idesc, k ? 1u : (uint32_t)(it != 0));
+                        for (int k = 0; k < 4; ++k) {  // 16 pixels (rows of 128 B) per MMA
+                            const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (2048u >> 4) * k);
+                            const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (2048u >> 4) * k);
+                            if (PAIR) umma_bf16_pair(tacc, adesc, bdesc, idesc, k ? 1u : (uint32_t)(it != 0));
+                            else umma_bf16(tacc, adesc, bdesc, idesc, k ? 1u : (uint32_t)(it != 0));
+                        }
+                        if (PAIR) umma_commit_pair(smem_u32(&empty_bar[s])); else umma_commit(smem_u32(&empty_bar[s]));
+                        if (it == total - 1) {
+                            if (PAIR) umma_commit_pair(smem_u32(&tmem_full_bar[acc])); else umma_commit(smem_u32(&tmem_full_bar[acc]));
+                        }
+                    }
+                    g_s += stage_bytes;
+                    if (++s == stages) { s = 0; par ^= 1u; g_s = sbase; }
                 }
-                umma_commit(smem_u32(&empty_bar[s]));
-                if (it == total - 1) umma_commit(smem_u32(&tmem_full_bar));
             }
-            g_s += stage_bytes;
-            if (++s == stages) { s = 0; par ^= 1u; g_s = sbase; }
         }
-    } else if (total > 0) {
+    } else {
         const int q = warp & 3;
-        const int co = co0 + q * 32 + lane;
-        const bool valid = co < p.Cout;
-        mbar_wait(smem_u32(&tmem_full_bar), 0);
-        tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        float* drow = p.dw + (long long)co * p.dw_ld + (long long)tp.wtap * p.wK + p.w_coff;
-        const int nchunks = p.NT >> 4;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            uint32_t r[16];
-            tmem_ld16(trow + (uint32_t)(ch * 16), r);
-            tmem_ld_wait();
-            const int ci = ci0 + ch * 16;
-            if (!valid || ci >= p.Ci) continue;
-            const int nv = min(16, p.Ci - ci);
+        const uint32_t stg0 = sbase + (uint32_t)stages * stage_bytes + (uint32_t)q * 8192u;
+        uint32_t gcc = 0;
+        int li = 0;
+        for (int item = worker; item < total_items; item += nworkers, ++li) {
+            const int mi = item % p.m_items, y = (item / p.m_items) % ny;
+            const int co0 = (PAIR ? mi * 256 + (int)rank * 128 : mi * 128) + q * 32;
+            const int wtap = p.taps[y / p.n_ci_tiles].wtap;
+            const int ci0 = (y % p.n_ci_tiles) * p.NT;
+            const int acc = li & 1;
+            mbar_wait(smem_u32(&tmem_full_bar[acc]), (uint32_t)((li >> 1) & 1));
+            tc_fence_after();
+            const uint32_t trow = tmem_base + (uint32_t)(acc * kTmemCols) + ((uint32_t)(q * 32) << 16);
+            const int nch = (min(p.NT, p.Ci - ci0) + 31) >> 5;
+            for (int cc = 0; cc < nch; ++cc, ++gcc) {
+                const uint32_t buf = stg0 + (gcc & 1u) * 4096u;
+                uint32_t r[32];
+                tmem_ld16(trow + (uint32_t)(cc * 32), r);
+                tmem_ld16(trow + (uint32_t)(cc * 32 + 16), r + 16);
+                tmem_ld_wait();
+                if (gcc >= 2) {
+                    if (lane == 0) bulk_wait_group_read<1>();
+                    __syncwarp();
+                }
+                const uint32_t rowaddr = buf + (uint32_t)lane * 128u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j * 4 < nv) {
-                    float* d = drow + ci + j * 4;
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(__uint_as_float(r[4 * j])),
-                                 "f"(__uint_as_float(r[4 * j + 1])), "f"(__uint_as_float(r[4 * j + 2])),
-                                 "f"(__uint_as_float(r[4 * j + 3]))
-                                 : "memory");
+                for (int c = 0; c < 8; ++c)
+                    st_shared_v4(rowaddr + (uint32_t)((c ^ (lane & 7)) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && co0 < p.Cout) {   // rows >= Cout / columns >= wK are clipped by the tensor map
+                    tma_reduce_add_3d(&tmW, buf, p.w_coff + ci0 + cc * 32, wtap, co0);
+                    bulk_commit_group();
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[acc]) & kPeerBitMask);
+                else mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+            }
         }
+        if (lane == 0) bulk_wait_group<0>();
     }
+    __syncwarp();
     tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<kTmemCols>(tmem_base);
+    if (PAIR) {
+        cluster_sync_all();
+        if (warp == 0) { __syncwarp(); tmem_dealloc_pair<2 * kTmemCols>(tmem_base); }
+    } else {
+        __syncthreads();
+        if (warp == 0) tmem_dealloc<2 * kTmemCols>(tmem_base);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -926,7 +990,9 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        attr_err = cudaFuncSetAttribute(wgrad_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(wgrad_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     });
     SNN_CUDA_OK(attr_err);
     SNN_REQUIRE(Ci % 8 == 0 && Cout % 8 == 0 && w_K % 4 == 0 && w_coff % 4 == 0, "conv_wgrad: channel counts must be multiples of 8");
@@ -951,8 +1017,10 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
         p.n_ci_tiles = (Ci + p.NT - 1) / p.NT;
     }
     p.Cout = Cout; p.Ci = Ci; p.dw = dw; p.dw_ld = (long long)taps * w_K; p.wK = w_K; p.w_coff = w_coff;
-    p.stage_bytes = (2 + p.NT / 64) * 8192;
-    int stages = smem_budget() / p.stage_bytes;
+    const bool pair = Cout > 128 && p.NT % 128 == 0 && g_debug_flags[6] != 1;
+    p.stage_bytes = (2 + (pair ? p.NT / 2 : p.NT) / 64) * 8192;
+    const int stage_extra = 4 * 8192;      // epilogue staging: 4 warps x 2 tiles of 32 x 32 fp32
+    int stages = (smem_budget() - stage_extra) / p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
     p.lbo_bytes = g_debug_flags[2] ? g_debug_flags[2] : 8192;
@@ -968,24 +1036,55 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
             if (geom == GEOM_3x3_S2) { int pc; s2_tap(kh, &t.x_dhp, &t.x_dh); s2_tap(kw, &pc, &t.x_dw); t.x_dc = (int)(pc * ld_x); }
             if (geom == GEOM_T2x2_S2) { t.g_dhp = kh; t.g_dc = (int)(kw * ld_dy); }
         }
-    const int m_tiles = (Cout + 127) / 128;
-    const int base_ctas = m_tiles * p.n_ci_tiles * taps;
-    // split-K so that the grid is at most two FULL waves of one CTA per SM (rounding up gave 297 CTAs on 148 SMs:
-    // a third wave for one CTA, profiles/r1)
-    int ksplit = (num_sms() * 2) / base_ctas;
-    const int max_split = (p.total_tiles + 3) / 4;  // >= 4 pixel tiles per CTA
+    p.m_items = pair ? (Cout + 255) / 256 : (Cout + 127) / 128;
+    const int base = p.m_items * p.n_ci_tiles * taps;             // work items before splitting K
+    const int workers = pair ? num_sms() / 2 : num_sms();
+    // split K (pixel tiles) so that the item count is just below one or two full rounds of the persistent workers; every
+    // item keeps >= 16 pipeline stages when two rounds are used (more items = more reduce-add traffic into dW)
+    int ksplit = 1;
+    if (base < workers) {
+        const int k2 = (2 * workers) / base, k1 = workers / base;
+        ksplit = (k2 >= 1 && p.total_tiles / k2 >= 16) ? k2 : (k1 >= 1 ? k1 : 1);
+    }
+    const int max_split = (p.total_tiles + 3) / 4;  // >= 4 pixel tiles per item
     if (ksplit > max_split) ksplit = max_split;
     if (ksplit < 1) ksplit = 1;
     if (g_debug_flags[4] > 0) ksplit = g_debug_flags[4];
     p.tiles_per_split = (p.total_tiles + ksplit - 1) / ksplit;
     p.ksplit = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-    CUtensorMap mg, mx;
+    CUtensorMap mg, mx, mw;
     if (make_act_map(&mg, dy, NB, Hy, Wy, Cout, ld_dy, g_phase, p.bn, p.bh, p.bw)) return 2;
     if (make_act_map(&mx, x, NB, H, W, Ci, ld_x, x_phase, p.bn, p.bh, p.bw)) return 2;
-    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-    dim3 grid(m_tiles, p.n_ci_tiles * taps, p.ksplit);
-    wgrad_gemm_kernel<<<grid, 192, smem, st>>>(mg, mx, p);
-    return check_cuda(cudaGetLastError(), "wgrad_gemm_kernel launch");
+    {   // dW fp32 [Cout][taps][w_K] -> 3-D reduce-add map (k, tap, n), box 32 x 1 x 32
+        if (get_encode()) return 2;
+        SNN_REQUIRE(((uintptr_t)dw & 15) == 0, "conv_wgrad: dw must be 16-byte aligned");
+        cuuint64_t dims[3] = {(cuuint64_t)w_K, (cuuint64_t)taps, (cuuint64_t)Cout};
+        cuuint64_t strides[2] = {(cuuint64_t)w_K * 4, (cuuint64_t)taps * w_K * 4};
+        cuuint32_t box[3] = {32, 1, 32}, es[3] = {1, 1, 1};
+        CUresult r = g_encode(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dw, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SNN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(dw) failed: %d (Cout=%d taps=%d K=%d)", (int)r, Cout, taps, w_K);
+    }
+    const size_t smem = (size_t)p.stages * p.stage_bytes + stage_extra + 1024;
+    const int items = base * p.ksplit;
+    int nw = workers < items ? workers : items;
+    if (g_debug_flags[5] > 0 && nw > g_debug_flags[5]) nw = g_debug_flags[5];
+    if (!pair) {
+        wgrad_gemm_kernel<false><<<nw, 192, smem, st>>>(mg, mx, mw, p);
+        return check_cuda(cudaGetLastError(), "wgrad_gemm_kernel launch");
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * nw, 1, 1);
+    cfg.blockDim = dim3(192, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return check_cuda(cudaLaunchKernelEx(&cfg, wgrad_gemm_kernel<true>, mg, mx, mw, p), "wgrad_gemm_kernel<pair> launch");
 }
 
 }  // namespace snn

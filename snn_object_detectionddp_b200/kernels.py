@@ -311,10 +311,11 @@ def dw3x3_fprop(x, w9c):
     return y
 
 
-def dw3x3_dgrad(dy, w9c):
+def dw3x3_dgrad(dy, w9c, out=None):
     nb, h, w, c = dy.shape
     assert dy.is_contiguous() and dy.dtype == torch.bfloat16
-    dx = torch.empty((nb, h, w, c), device=dy.device, dtype=torch.bfloat16)
+    dx = torch.empty((nb, h, w, c), device=dy.device, dtype=torch.bfloat16) if out is None else out
+    assert dx.is_contiguous() and tuple(dx.shape) == (nb, h, w, c) and dx.dtype == torch.bfloat16
     call("snn_dw3x3_dgrad", ptr(dy), ptr(w9c), ptr(dx), nb, h, w, c, stream_ptr())
     return dx
 

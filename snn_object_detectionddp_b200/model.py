@@ -91,6 +91,7 @@ class ConvBlock(nn.Module):
                    want_state=rc.want_state, want_mask=rc.want_mask)
         if dead_frames_ok and rc.live_T is not None and self.neuron.kind == "silu" and rc.live_T < rc.T:
             cfg["live_T"] = rc.live_T
+            cfg["dead_grad_unread"] = getattr(rc, "dead_grad_unread", False)
         out, v = ConvBNActFn.apply(x0, x1, v_init, self.conv.weight, self.bn.weight, self.bn.bias, cfg)
         if rc.want_mask:
             self.last_mask = cfg.get("last_mask")
@@ -339,6 +340,9 @@ class YOLOTemporalUNet(nn.Module):
         st.refresh_operands()
         feats = self.feature_extractor.forward_seq(frames, B, T)
         rc = RunCtx(st, T, want_state=return_state, live_T=None if (all_steps or not self.skip_dead_backward) else 1)
+        # the head's inputs are produced by the U-Net output convs, which slice the dead frames' gradient away themselves:
+        # head-internal gradients of the dead frames are never read and need no zero fill
+        rc.dead_grad_unread = rc.live_T is not None
         outs, new_state = self.temporal_unet.forward_seq(rc, feats, _unpack_hidden(hidden_state))
         det = self.detection_head.forward_seq(rc, outs, B, last_only=not all_steps)
         hidden = _pack_hidden(new_state, self.temporal_unet.neuron.kind) if return_state else None

@@ -32,13 +32,12 @@ def _bf16c(g):
     return g.contiguous()
 
 
-def _pad_dead(g_live, x_full, live):
-    """Gradient of the live tail -> full-size gradient with zeros for the dead leading frames."""
-    if g_live is None or live is None or g_live.shape[0] == x_full.shape[0]:
-        return g_live
-    g = torch.zeros(x_full.shape, device=g_live.device, dtype=g_live.dtype)
-    g[x_full.shape[0] - g_live.shape[0]:] = g_live
-    return g
+def _dead_padded(x_full, n_live, zero):
+    """Full-size input-gradient buffer whose trailing n_live samples the caller fills.  The leading (dead) part is
+    zero-filled unless every consumer is known to slice it away (Detect-head internals: cfg['dead_grad_unread'])."""
+    alloc = torch.zeros if zero else torch.empty
+    g = alloc(x_full.shape, device=x_full.device, dtype=torch.bfloat16)
+    return g, g[x_full.shape[0] - n_live:]
 
 
 class ConvBNActFn(Function):
@@ -119,23 +118,35 @@ class ConvBNActFn(Function):
             c = weight.shape[0]
             K.dw3x3_wgrad(x0, dy, gw3.view(9, c))
             st.grad_done(weight)
-            gx0 = K.dw3x3_dgrad(dy, st.w_master3(weight).view(9, c)) if ctx.needs_input_grad[0] else None
-            return _pad_dead(gx0, x0_full, live_T), None, (None if gv0 is None else gv0.view(v_init.shape)), None, None, None, None
+            gx0 = None
+            if ctx.needs_input_grad[0]:
+                if live_T is None:
+                    gx0 = K.dw3x3_dgrad(dy, st.w_master3(weight).view(9, c))
+                else:
+                    gx0, tail = _dead_padded(x0_full, x0.shape[0], not cfg.get("dead_grad_unread", False))
+                    K.dw3x3_dgrad(dy, st.w_master3(weight).view(9, c), out=tail)
+            return gx0, None, (None if gv0 is None else gv0.view(v_init.shape)), None, None, None, None
         K.conv_wgrad(geom, x0, dy, gw3, w_coff=0)
         if ctx.has_x1:
             K.conv_wgrad(geom, x1, dy, gw3, w_coff=x0.shape[3])
         st.grad_done(weight)
         gx0 = gx1 = None
         in_hw = (x0.shape[1], x0.shape[2])
+        zero = not cfg.get("dead_grad_unread", False)
         if ctx.needs_input_grad[0]:
-            gx0 = K.conv_dgrad(geom, dy, st.w_fprop(weight), in_hw, x0.shape[3], ci_off=0)
+            tail = None
+            if live_T is not None:
+                gx0, tail = _dead_padded(x0_full, x0.shape[0], zero)
+            r = K.conv_dgrad(geom, dy, st.w_fprop(weight), in_hw, x0.shape[3], ci_off=0, out=tail)
+            gx0 = r if live_T is None else gx0
         if ctx.has_x1 and ctx.needs_input_grad[1]:
-            gx1 = K.conv_dgrad(geom, dy, st.w_fprop(weight), in_hw, x1.shape[3], ci_off=x0.shape[3])
+            tail = None
+            if live_T is not None:
+                gx1, tail = _dead_padded(ctx.saved_tensors[1], x1.shape[0], zero)
+            r = K.conv_dgrad(geom, dy, st.w_fprop(weight), in_hw, x1.shape[3], ci_off=x0.shape[3], out=tail)
+            gx1 = r if live_T is None else gx1
         if gv0 is not None:
             gv0 = gv0.view(v_init.shape)
-        if live_T is not None:
-            gx0 = _pad_dead(gx0, x0_full, live_T)
-            gx1 = None if gx1 is None else _pad_dead(gx1, ctx.saved_tensors[1], live_T)
         return gx0, gx1, gv0, None, None, None, None
 
 

@@ -150,5 +150,48 @@ class Trainer:
         st.opt_epoch += 1
         return self._static_out
 
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def validate_step(self, frames, batch):
+        """validate_one_epoch's inner step (reference train.py:106-131): eval mode (BatchNorm running statistics, state
+        reset per window), loss on the last frame, no gradient.  Returns loss.detach() [3] as a DEVICE tensor."""
+        model = self.model
+        was_training = model.training
+        model.eval()
+        try:
+            det, _ = model.forward_sequence(frames)
+            _, items = self.loss_fn(det, batch)
+        finally:
+            model.train(was_training)
+        return items
+
+    # ------------------------------------------------------------------------------------------
+    def save_checkpoint(self, path, epoch=0, best_val_loss=float("inf")):
+        """The reference's checkpoint dict (train.py:204-209: 'epoch', 'model_state_dict', 'best_val_loss') -- loadable
+        by the reference's own `model.load_state_dict(ckpt['model_state_dict'])` for the temporal_unet / detection_head
+        keys -- plus what the reference forgets (optimizer moments, schedule position) under 'trainer_state'."""
+        st = self.store
+        torch.save({"epoch": epoch, "model_state_dict": {k: v.detach().cpu().contiguous() for k, v in self.model.state_dict().items()},
+                    "best_val_loss": best_val_loss,
+                    "trainer_state": {"step_idx": self.step_idx, "total_steps": self.total_steps,
+                                      "exp_avg": st.flat_m.cpu(), "exp_avg_sq": st.flat_v.cpu(),
+                                      "layout": [(e.name, e.offset, e.numel) for e in st.entries]}}, path)
+
+    def load_checkpoint(self, path, strict=True):
+        """Accepts both this class's files and plain reference checkpoints (no 'trainer_state': moments restart at 0)."""
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        self.model.load_state_dict(ck["model_state_dict"], strict=strict)
+        st = self.store.ensure(self.device)
+        st._versions = None
+        st.refresh_operands()
+        ts = ck.get("trainer_state")
+        if ts is not None and [(e.name, e.offset, e.numel) for e in st.entries] == [tuple(x) for x in ts["layout"]]:
+            st.flat_m.copy_(ts["exp_avg"])
+            st.flat_v.copy_(ts["exp_avg_sq"])
+            self.step_idx = int(ts["step_idx"])
+            self._step_dev.fill_(self.step_idx)
+        self._graph = None                       # captured graphs hold the old buffers' contents only by address: still valid, but re-capture is cheap and safe
+        return ck.get("epoch", 0), ck.get("best_val_loss", float("inf"))
+
     def lr(self):
         return float(self.hp[min(self.step_idx, self.total_steps - 1), 0])

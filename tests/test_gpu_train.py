@@ -194,8 +194,9 @@ def test_skipping_dead_frame_backward_changes_nothing():
     for e in st.entries:
         if e.name.startswith("detection_head.") or ".out_p" in e.name:
             sl = slice(e.offset, e.offset + e.numel)
-            # + bf16 rounding of dy (2^-9 per element) summed over as few as 32 pixels per channel
-            assert float(rel_err(g_a[sl], g_b[sl])) < 3 * float(rel_err(g_b[sl], g_c[sl])) + 3e-3, e.name
+            # + bf16 rounding of dy (2^-9 per element): bias gradients are sums of as few as 32 such values per channel and
+            # cancel heavily, so a handful of rounding flips shows at the percent level; a missing contribution would be O(1)
+            assert float(rel_err(g_a[sl], g_b[sl])) < 3 * float(rel_err(g_b[sl], g_c[sl])) + 2e-2, e.name
 
 
 def test_drop_in_forward_signature_and_eval_outputs():
@@ -215,3 +216,36 @@ def test_drop_in_forward_signature_and_eval_outputs():
     assert dec.shape == (2, 12, 336) and len(maps) == 3
     assert net.model[0] is net.detection_head and net.nc == 8 and net.args.box == 7.5
     assert torch.equal(net.strides.cpu(), torch.tensor([8.0, 16.0, 32.0]))
+
+
+def test_checkpoint_roundtrip_and_validation_step(tmp_path):
+    """Reference checkpoint format (train.py:204-209) + validation step (train.py:106-131): a reloaded trainer
+    reproduces the eval-mode loss exactly and continues with the same optimizer state; a reference-style file that also
+    carries frozen-extractor keys loads."""
+    setup_exact()
+    from snn_object_detectionddp_b200.trainer import Trainer
+    _, net = _models("lif", seed=8)
+    tr = Trainer(net, total_steps=20, device=DEV)
+    frames, labels = MO.synthetic_batch(2, 2, 128, 128, seed=14)
+    frames, labels = frames.to(DEV), labels.to(DEV)
+    batch = {"batch_idx": labels[:, 0], "cls": labels[:, 1], "bboxes": labels[:, 2:]}
+    for _ in range(2):
+        tr.train_step(frames, batch)
+    v0 = tr.validate_step(frames, batch).clone()
+    assert net.training and torch.isfinite(v0).all()
+    path = str(tmp_path / "latest.pt")
+    tr.save_checkpoint(path, epoch=3, best_val_loss=1.5)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert {"epoch", "model_state_dict", "best_val_loss"} <= set(ck) and ck["epoch"] == 3
+    assert all(k.startswith(("temporal_unet.", "detection_head.", "feature_extractor.")) for k in ck["model_state_dict"])
+    _, net2 = _models("lif", seed=9)                 # different init
+    tr2 = Trainer(net2, total_steps=20, device=DEV)
+    ck["model_state_dict"]["feature_extractor.model.model.0.conv.weight"] = torch.zeros(3)    # reference files carry these
+    torch.save(ck, path)
+    epoch, best = tr2.load_checkpoint(path)
+    assert (epoch, best) == (3, 1.5) and tr2.step_idx == tr.step_idx
+    assert torch.equal(tr2.validate_step(frames, batch), v0)
+    assert torch.equal(tr2.store.flat_p, tr.store.flat_p) and torch.equal(tr2.store.flat_m, tr.store.flat_m)
+    l1, i1 = tr.train_step(frames, batch)
+    l2, i2 = tr2.train_step(frames, batch)
+    assert torch.equal(i1, i2)                       # deterministic forward on identical parameters
