@@ -458,7 +458,9 @@ bn_act_bwd2_kernel(const float* __restrict__ y, const float* __restrict__ scale,
         }
         const float4* tA = tabA + cg * PITCH;
         const float4* tB = tabB + cg * PITCH;
-        const int p0 = blockIdx.x * pix_per_block, p1 = min(P, p0 + pix_per_block);
+        // pass 2 walks the pixel ranges in the REVERSE order of pass 1: the tail pass 1 read last is still in L2 (LRU)
+        const int xb = REDUCE ? (int)blockIdx.x : (int)(gridDim.x - 1 - blockIdx.x);
+        const int p0 = xb * pix_per_block, p1 = min(P, p0 + pix_per_block);
         size_t e2 = (size_t)(p0 + row) * C2 + (c_base >> 1) + cg;
         const size_t e2_step = (size_t)rows * C2;
         for (int p = p0 + row; p < p1; p += rows, e2 += e2_step) {

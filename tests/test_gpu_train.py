@@ -237,7 +237,7 @@ def test_checkpoint_roundtrip_and_validation_step(tmp_path):
     tr.save_checkpoint(path, epoch=3, best_val_loss=1.5)
     ck = torch.load(path, map_location="cpu", weights_only=False)
     assert {"epoch", "model_state_dict", "best_val_loss"} <= set(ck) and ck["epoch"] == 3
-    assert all(k.startswith(("temporal_unet.", "detection_head.", "feature_extractor.")) for k in ck["model_state_dict"])
+    assert all(k.startswith(("temporal_unet.", "detection_head.", "model.0.", "feature_extractor.")) for k in ck["model_state_dict"])
     _, net2 = _models("lif", seed=9)                 # different init
     tr2 = Trainer(net2, total_steps=20, device=DEV)
     ck["model_state_dict"]["feature_extractor.model.model.0.conv.weight"] = torch.zeros(3)    # reference files carry these
