@@ -70,10 +70,9 @@ def _worker(rank, world, port, mode, out):
         g, items = _backward_only(tr, frames.to(dev), tr.prepare_batch(labels, B, max_boxes=8))
         launched = list(tr.bucketer.launch_order)
         dist.barrier()
-        dist.destroy_process_group()
         if rank == 0:
             out.put((True, g.cpu().numpy(), [items.cpu().numpy()], launched, False, len(tr.bucketer.buckets)))
-        return
+        os._exit(0)
     for step in range(4):
         seed = 100 + step + (0 if mode == "same" else 17 * rank)
         frames, labels = synthetic_batch(B, T, HW, HW, seed=seed)
@@ -87,12 +86,16 @@ def _worker(rank, world, port, mode, out):
     dist.all_gather(gathered, flat)
     same = all(torch.equal(gathered[0], g) for g in gathered[1:])
     launched = list(tr.bucketer.launch_order)
+    graphed = bool(tr._graph is not None)
+    torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
     if rank == 0:
         # plain numpy payloads: torch tensors travel through mp queues as shared-memory handles that die with this process
-        out.put((same, flat.cpu().numpy(), [l.cpu().numpy() for l in losses], launched, bool(tr._graph is not None),
-                 len(tr.bucketer.buckets)))
+        out.put((same, flat.cpu().numpy(), [l.cpu().numpy() for l in losses], launched, graphed, len(tr.bucketer.buckets)))
+    # leave without NCCL teardown: destroy_process_group() can block for minutes while a captured graph still references the
+    # communicator's kernels (seen on the 2-GPU box); SimpleQueue.put is synchronous, so the payload is already in the pipe
+    os._exit(0)
 
 
 def _run(mode):
@@ -102,9 +105,20 @@ def _run(mode):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = q.get()            # read before join: a child blocks in exit until its queue payload is consumed
+    import time
+    t0 = time.time()
+    while q.empty():         # poll instead of a blocking get(): a crashed worker must fail the test, not hang it
+        if any(p.exitcode not in (None, 0) for p in procs) or time.time() - t0 > 240:
+            for p in procs:
+                if p.is_alive():
+                    p.kill()
+            raise AssertionError(f"DDP worker failed or timed out: exit codes {[p.exitcode for p in procs]}")
+        time.sleep(0.2)
+    res = q.get()
     for p in procs:
-        p.join(600)
+        p.join(60)
+        if p.is_alive():
+            p.kill()
         assert p.exitcode == 0
     same, flat, losses, launched, graphed, nb = res
     return same, torch.from_numpy(flat), [torch.from_numpy(l) for l in losses], launched, graphed, nb
