@@ -267,12 +267,15 @@ def run_ours(args):
     # ---------------- end to end through the public API with host buffers ----------------
     e2e = None
     if not args.no_e2e:
-        pin = [frames_cpu.clone().pin_memory() for _ in range(2)]
+        # host frames as the dataset decodes them: uint8 RGB (reference dataset.py:139-152 converts to fp32 / 255 on the HOST and
+        # ships 4x the bytes); the division runs in the frame packer kernel, bit-identical to the host's
+        frames_u8 = (frames_cpu * 255.0).round().clamp_(0, 255).to(torch.uint8)
+        pin = [frames_u8.clone().pin_memory() for _ in range(2)]
         lab_pin = [tuple(t.pin_memory() for t in trainer.prepare_batch(labels_cpu, B, max_boxes=MAXB)["padded"]) for _ in range(2)]
         loss_host = torch.zeros(args.steps + args.warmup, 3).pin_memory()
         copy_stream = torch.cuda.Stream(dev)
         main_stream = torch.cuda.current_stream(dev)
-        dbuf = [torch.empty_like(frames) for _ in range(2)]
+        dbuf = [torch.empty(frames.shape, device=dev, dtype=torch.uint8) for _ in range(2)]
         lbuf = [tuple(torch.empty_like(t, device=dev) for t in lab_pin[0]) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
@@ -309,11 +312,11 @@ def run_ours(args):
         ems = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        h2d_bytes = frames_cpu.numel() * frames_cpu.element_size() + sum(t.numel() * t.element_size() for t in lab_pin[0])
+        h2d_bytes = frames_u8.numel() * frames_u8.element_size() + sum(t.numel() * t.element_size() for t in lab_pin[0])
         e2e = {"value": world * B * args.steps / (float(ems) * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": 12, "ms_per_step": float(ems) / args.steps,
                "api": ("Trainer.train_step_graphed" if graphed else "Trainer.train_step")
-                      + " on double-buffered pinned host frames (fp32 [B,T,3,H,W]) + padded labels"}
+                      + " on double-buffered pinned host frames (uint8 [B,T,3,H,W], /255 on the device) + padded labels"}
 
     clocks = sampler.stop() if rank == 0 else None          # sampled over both timed regions (device-resident + e2e)
 

@@ -125,6 +125,9 @@ int snn_dw3x3_wgrad(const void* x_bf16, const void* dy_bf16, float* dw, int NB, 
 /* ---- frame packer of the stand-in feature pyramid (the frozen YOLO11m of model.py:74-98 cannot exist
  *      offline): fp32 frames [B][T][3][H][W] -> bf16 NHWC [T*B][H/8][W/8][192] ---- */
 int snn_space_to_depth8(const float* frames, void* out_bf16, int B, int T, int H, int W, void* stream);
+/* same packer for uint8 frames [B][T][3][H][W] (what dataset.py:139-152 decodes before its host-side `/ 255.0`): the division
+ * runs on the device, bit-identical to the host's, and the host->device copy shrinks 4x */
+int snn_space_to_depth8_u8(const unsigned char* frames, void* out_bf16, int B, int T, int H, int W, void* stream);
 
 /* ---- bias gradient of the biased convs (ConvLSTM2d.conv, UpBlock.up, out_p*): acc[c] += sum_p dy[p][c] ---- */
 int snn_colsum_bf16(const void* dy_bf16, float* acc, long long P, int C, void* stream);

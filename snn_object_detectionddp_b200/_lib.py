@@ -39,6 +39,7 @@ _SIGNATURES = {
     "snn_dw3x3_dgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
     "snn_dw3x3_wgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
     "snn_space_to_depth8": [_P, _P, _I, _I, _I, _I, _P],
+    "snn_space_to_depth8_u8": [_P, _P, _I, _I, _I, _I, _P],
     "snn_detect_decode": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "snn_detect_loss_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     "snn_detect_loss_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P],

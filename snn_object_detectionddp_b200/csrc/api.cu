@@ -68,6 +68,7 @@ int launch_dw3x3_fwd(const __nv_bfloat16*, const float*, float*, int, int, int, 
 int launch_dw3x3_dgrad(const __nv_bfloat16*, const float*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 int launch_dw3x3_wgrad(const __nv_bfloat16*, const __nv_bfloat16*, float*, int, int, int, int, cudaStream_t);
 int launch_s2d8(const float*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
+int launch_s2d8_u8(const uint8_t*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 int launch_adamw(float*, const float*, float*, float*, __nv_bfloat16*, long long, const float*, const double*, float*,
                  int*, int, cudaStream_t);
 int launch_detect_decode(const float*, const float*, const float*, const float*, int, int, int, int, int, float*, float*,
@@ -186,6 +187,9 @@ int snn_dw3x3_wgrad(const void* x, const void* dy, float* dw, int NB, int H, int
 }
 int snn_space_to_depth8(const float* frames, void* out, int B, int T, int H, int W, void* stream) {
     return launch_s2d8(frames, (__nv_bfloat16*)out, B, T, H, W, ST);
+}
+int snn_space_to_depth8_u8(const unsigned char* frames, void* out, int B, int T, int H, int W, void* stream) {
+    return launch_s2d8_u8(frames, (__nv_bfloat16*)out, B, T, H, W, ST);
 }
 int snn_colsum_bf16(const void* dy, float* acc, long long P, int C, void* stream) {
     return launch_colsum_bf16((const __nv_bfloat16*)dy, acc, P, C, ST);

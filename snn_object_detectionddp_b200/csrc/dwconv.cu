@@ -161,6 +161,38 @@ int launch_dw3x3_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* d
     dw3x3_wgrad_kernel<<<(unsigned)((P + ppb - 1) / ppb), 256, sizeof(float) * 9 * C, st>>>(x, dy, dw, NB, H, W, C, (int)ppb);
     return check_cuda(cudaGetLastError(), "dw3x3_wgrad_kernel");
 }
+// uint8 frames (what the dataset decodes, dataset.py:139-152) -> /255 on the device (the reference divides on the host and
+// ships fp32: 4x the PCIe bytes); `v / 255.0f` in IEEE fp32 is bit-identical to torch's `.float() / 255.0`
+__global__ void __launch_bounds__(256)
+s2d8_u8_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int T, int H, int W) {
+    const int H8 = H >> 3, W8 = W >> 3;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long total = (long long)B * T * 3 * 8 * H8 * W8;
+    if (idx >= total) return;
+    const int j = (int)(idx % W8);
+    const int i = (int)((idx / W8) % H8);
+    const int dy = (int)((idx / ((long long)W8 * H8)) % 8);
+    const int c = (int)((idx / ((long long)W8 * H8 * 8)) % 3);
+    const long long n = idx / ((long long)W8 * H8 * 24);
+    const int t = (int)(n / B), b = (int)(n % B);
+    const uint8_t* src = in + ((((long long)b * T + t) * 3 + c) * H + (i * 8 + dy)) * W + j * 8;
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(src));
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = __fdiv_rn((float)((raw.x >> (8 * k)) & 0xFFu), 255.0f);
+        v[4 + k] = __fdiv_rn((float)((raw.y >> (8 * k)) & 0xFFu), 255.0f);
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]); pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + ((n * H8 + i) * W8 + j) * 192 + c * 64 + dy * 8) = pk;
+}
+int launch_s2d8_u8(const uint8_t* in, __nv_bfloat16* out, int B, int T, int H, int W, cudaStream_t st) {
+    SNN_REQUIRE(H % 8 == 0 && W % 8 == 0, "space_to_depth8: H, W must be multiples of 8");
+    const long long total = (long long)B * T * 3 * 8 * (H / 8) * (W / 8);
+    s2d8_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, B, T, H, W);
+    return check_cuda(cudaGetLastError(), "s2d8_u8_kernel");
+}
 int launch_s2d8(const float* in, __nv_bfloat16* out, int B, int T, int H, int W, cudaStream_t st) {
     SNN_REQUIRE(H % 8 == 0 && W % 8 == 0, "space_to_depth8: H, W must be multiples of 8");
     const long long total = (long long)B * T * 3 * 8 * (H / 8) * (W / 8);

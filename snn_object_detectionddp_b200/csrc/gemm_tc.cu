@@ -54,6 +54,9 @@ struct ConvGemmParams {
     int b_boxes;                      // b_mn: number of 64-column boxes per stage
     float* stats;                     // tma_out + fp32: per-(32-row group, column) sum / sum-of-squares partials [4*m_tiles][2][n_store]
     int tma_out;                      // epilogue through swizzled smem staging + TMA tensor stores (coalesced) instead of per-thread rows
+    int cps, chunk_bytes;             // 64-wide K chunks per pipeline stage (1, 2 or 4: narrow-N tiles need more MMA work per
+                                      // mbarrier round trip) and bytes of one chunk (A 16 KB + this CTA's B slice)
+    int nbuf;                         // epilogue staging tiles per warp (2, or 4 for small-K convs: TMA-store latency bound)
     int ksplit;                       // K split over the tap segments (fp32 output, TMA reduce-add): fills the GPU on small-M convs
     int dbg;                          // timing experiments only: bit 0 = producer skips the TMA loads, bit 1 = no MMA issue
     Phase phase[4];
@@ -169,32 +172,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const CUtensorMap* tmA = g.src ? &tmA1 : &tmA0;
                 const int cw = w0 + g.dw, chh = h0 + g.dh;
                 int ca = g.dc, cb = g.wc0;
-                for (int kc = 0; kc < g.nchunk; ++kc, ca += 64, cb += 64) {
+                for (int kc = 0; kc < g.nchunk; kc += p.cps) {
+                    const int nsub = min(p.cps, g.nchunk - kc);       // K chunks carried by this stage
                     mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
                     if (lead) {
                         const uint32_t fb = smem_u32(&full_bar[s]);
                         if (p.dbg & 1) {
                             if (rank == 0) mbar_arrive(fb);
                         } else if (!PAIR) {
-                            mbar_expect_tx(fb, stage_bytes);
-                            tma_load_5d(a_s, tmA, fb, ca, cw, g.dhp, chh, n0);
-                            if (!p.b_mn) {
-                                tma_load_3d(a_s + 16384u, &tmB, fb, cb, g.wtap, ncol0);
-                            } else {  // [64 K rows] x [64 N] boxes, one per 64 output columns
-                                for (int nb = 0; nb < p.b_boxes; ++nb)
-                                    tma_load_3d(a_s + 16384u + (uint32_t)nb * 8192u, &tmB, fb, ncol0 + nb * 64, g.wtap, cb);
+                            mbar_expect_tx(fb, (uint32_t)(nsub * p.chunk_bytes));
+                            for (int j = 0; j < nsub; ++j) {
+                                const uint32_t c_s = a_s + (uint32_t)(j * p.chunk_bytes);
+                                tma_load_5d(c_s, tmA, fb, ca + 64 * j, cw, g.dhp, chh, n0);
+                                if (!p.b_mn) {
+                                    tma_load_3d(c_s + 16384u, &tmB, fb, cb + 64 * j, g.wtap, ncol0);
+                                } else {  // [64 K rows] x [64 N] boxes, one per 64 output columns
+                                    for (int nb = 0; nb < p.b_boxes; ++nb)
+                                        tma_load_3d(c_s + 16384u + (uint32_t)nb * 8192u, &tmB, fb, ncol0 + nb * 64, g.wtap, cb + 64 * j);
+                                }
                             }
                         } else {
-                            if (rank == 0) mbar_expect_tx(fb, 2u * stage_bytes);      // both CTAs' bytes land on the leader's barrier
-                            tma_load_5d_pair(a_s, tmA, fb, ca, cw, g.dhp, chh, n0);
-                            if (!p.b_mn) {
-                                tma_load_3d_pair(a_s + 16384u, &tmB, fb, cb, g.wtap, ncol0);
-                            } else {
-                                for (int nb = 0; nb < p.b_boxes; ++nb)
-                                    tma_load_3d_pair(a_s + 16384u + (uint32_t)nb * 8192u, &tmB, fb, ncol0 + nb * 64, g.wtap, cb);
+                            if (rank == 0) mbar_expect_tx(fb, 2u * (uint32_t)(nsub * p.chunk_bytes));   // both CTAs' bytes land on the leader's barrier
+                            for (int j = 0; j < nsub; ++j) {
+                                const uint32_t c_s = a_s + (uint32_t)(j * p.chunk_bytes);
+                                tma_load_5d_pair(c_s, tmA, fb, ca + 64 * j, cw, g.dhp, chh, n0);
+                                if (!p.b_mn) {
+                                    tma_load_3d_pair(c_s + 16384u, &tmB, fb, cb + 64 * j, g.wtap, ncol0);
+                                } else {
+                                    for (int nb = 0; nb < p.b_boxes; ++nb)
+                                        tma_load_3d_pair(c_s + 16384u + (uint32_t)nb * 8192u, &tmB, fb, ncol0 + nb * 64, g.wtap, cb + 64 * j);
+                                }
                             }
                         }
                     }
+                    ca += 64 * p.cps; cb += 64 * p.cps;
                     a_s += stage_bytes;
                     if (++s == stages) { s = 0; par ^= 1u; a_s = sbase; }
                 }
@@ -218,35 +229,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const int pk = (tile / m_work) / p.n_blocks;
                 const Phase& ph = p.phase[pk % p.nphase];
                 const int spp = ph.nseg / p.ksplit, sg0 = (pk / p.nphase) * spp;
-                int total = 0;
-                for (int i = sg0; i < sg0 + spp; ++i) total += ph.seg[i].nchunk;
                 const int acc = lt & 1;
                 mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((lt >> 1) & 1) ^ 1));   // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(acc * kAccCols);
-                for (int j = 0; j < total; ++j) {
-                    mbar_wait(smem_u32(&full_bar[s]), par);
-                    tc_fence_after();
-                    if (lead) {
-                        const uint32_t a_lo = a_lo_c | ((a_s & 0x3FFFFu) >> 4);
-                        const uint32_t b_lo = b_lo_c | (((a_s + 16384u) & 0x3FFFFu) >> 4);
-                        if (!dbg_nomma) {
+                uint32_t first = 1u;                                   // first MMA of the tile overwrites the accumulator
+                for (int sg = sg0; sg < sg0 + spp; ++sg) {
+                    const int nchunk = ph.seg[sg].nchunk;
+                    const bool last_seg = sg == sg0 + spp - 1;
+                    for (int kc = 0; kc < nchunk; kc += p.cps) {
+                        const int nsub = min(p.cps, nchunk - kc);
+                        mbar_wait(smem_u32(&full_bar[s]), par);
+                        tc_fence_after();
+                        if (lead) {
+                            if (!dbg_nomma) {
+                                for (int j = 0; j < nsub; ++j) {
+                                    const uint32_t c_s = a_s + (uint32_t)(j * p.chunk_bytes);
+                                    const uint32_t a_lo = a_lo_c | ((c_s & 0x3FFFFu) >> 4);
+                                    const uint32_t b_lo = b_lo_c | (((c_s + 16384u) & 0x3FFFFu) >> 4);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
-                                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + b_kstep * k);
-                                const uint32_t accf = k ? 1u : (uint32_t)(j != 0);
-                                if (PAIR) umma_bf16_pair(tacc, adesc, bdesc, idesc, accf);
-                                else umma_bf16(tacc, adesc, bdesc, idesc, accf);
+                                    for (int k = 0; k < 4; ++k) {
+                                        const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
+                                        const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + b_kstep * k);
+                                        const uint32_t accf = (k | j) ? 1u : (first ^ 1u);
+                                        if (PAIR) umma_bf16_pair(tacc, adesc, bdesc, idesc, accf);
+                                        else umma_bf16(tacc, adesc, bdesc, idesc, accf);
+                                    }
+                                }
+                            }
+                            if (PAIR) umma_commit_pair(smem_u32(&empty_bar[s])); else umma_commit(smem_u32(&empty_bar[s]));
+                            if (last_seg && kc + p.cps >= nchunk) {
+                                if (PAIR) umma_commit_pair(smem_u32(&tmem_full_bar[acc])); else umma_commit(smem_u32(&tmem_full_bar[acc]));
                             }
                         }
-                        if (PAIR) umma_commit_pair(smem_u32(&empty_bar[s])); else umma_commit(smem_u32(&empty_bar[s]));
-                        if (j == total - 1) {
-                            if (PAIR) umma_commit_pair(smem_u32(&tmem_full_bar[acc])); else umma_commit(smem_u32(&tmem_full_bar[acc]));
-                        }
+                        first = 0u;
+                        a_s += stage_bytes;
+                        if (++s == stages) { s = 0; par ^= 1u; a_s = sbase; }
                     }
-                    a_s += stage_bytes;
-                    if (++s == stages) { s = 0; par ^= 1u; a_s = sbase; }
                 }
             }
         }
@@ -280,10 +299,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const int cw = tw * bw_ + row0 % bw_, chh = th * bh_ + (row0 / bw_) % bh_, cn = tn * p.bn + row0 / (bw_ * bh_);
                 const int cbase = (p.os == 2 ? ph.opw * (int)p.out_ld : 0);
                 const int cph = (p.os == 2 ? ph.oph : 0);
-                const uint32_t stg0 = sbase + (uint32_t)stages * stage_bytes + (uint32_t)q * 8192u;
+                const uint32_t stg0 = sbase + (uint32_t)stages * stage_bytes + (uint32_t)(q * p.nbuf) * 4096u;
                 const int nch = (min(p.BN, p.n_store - ncol0) + CH - 1) / CH;
                 for (int cc = 0; cc < nch; ++cc, ++gcc) {
-                    const uint32_t buf = stg0 + (gcc & 1u) * 4096u;
+                    const uint32_t buf = stg0 + (gcc % (uint32_t)p.nbuf) * 4096u;
                     uint32_t r[32];
                     if (p.out_f32) {
                         tmem_ld16(trow + (uint32_t)(cc * 32), r);
@@ -314,8 +333,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             }
                         }
                     }
-                    if (gcc >= 2) {                      // the store that read this buffer two chunks ago has drained it
-                        if (lane == 0) bulk_wait_group_read<1>();
+                    if (gcc >= (uint32_t)p.nbuf) {       // the store that read this buffer nbuf chunks ago has drained it
+                        if (lane == 0) { if (p.nbuf == 4) bulk_wait_group_read<3>(); else bulk_wait_group_read<1>(); }
                         __syncwarp();
                     }
                     const uint32_t rowaddr = buf + (uint32_t)lane * 128u;
@@ -758,16 +777,30 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     // MN-major 64-column boxes; g_debug_flags[6] == 1 forces the single-CTA kernel (tests / A-B timing)
     bool pair = m_tiles >= 2 && g_debug_flags[6] != 1;
     if (pair) pair = p.b_mn ? (p.BN % 128 == 0) : (p.BN % 16 == 0);
+    // K chunks per work item: small-K convs (1x1, transposed) are bound by per-tile latencies, not by operand traffic:
+    // single-CTA tiles (no cluster handshakes) and four epilogue staging tiles instead of two
+    if (p.ksplit < 1) p.ksplit = 1;
+    int chunks_per_item = 0;
+    for (int i = 0; i < p.phase[0].nseg; ++i) chunks_per_item += p.phase[0].seg[i].nchunk;
+    chunks_per_item /= p.ksplit;
+    const bool small_k = chunks_per_item <= 8;
+    if (small_k && g_debug_flags[6] != 2) pair = false;
     const int bn_cta = pair ? p.BN / 2 : p.BN;
     p.b_boxes = (bn_cta + 63) / 64;
-    p.stage_bytes = p.b_mn ? 16384 + p.b_boxes * 8192 : 16384 + bn_cta * 128;
+    p.chunk_bytes = p.b_mn ? 16384 + p.b_boxes * 8192 : 16384 + bn_cta * 128;
+    // chunks per stage: keep >= ~512 MMA cycles behind every mbarrier round trip (N = 256: 1 chunk, 128: 2, <= 64: 4)
+    p.cps = small_k ? 1 : (p.BN > 128 ? 1 : (p.BN > 64 ? 2 : 4));
+    if (g_debug_flags[2] > 0) p.cps = g_debug_flags[2];
     // coalesced TMA-store epilogue whenever the output view is expressible as a tensor map
     const int es = p.out_f32 ? 4 : 2, CH = p.out_f32 ? 32 : 64;
     char* obase = reinterpret_cast<char*>(p.out) + (long long)p.out_coff * es;
     p.tma_out = g_debug_flags[0] != 1 && !(p.accumulate && !p.out_f32) && ((uintptr_t)obase % 16 == 0) && ((p.out_ld * es) % 16 == 0) &&
                 (p.os == 1 || (p.n_store % CH == 0 && p.Ho % 2 == 0 && p.Wo % 2 == 0));
     SNN_REQUIRE(!p.stats || p.tma_out, "conv_fprop: fused statistics need the TMA-store epilogue (output alignment)");
-    const int stage_extra = p.tma_out ? 4 * 8192 : 0;     // 4 epilogue warps x 2 staging tiles of 32 rows x 128 B
+    p.nbuf = small_k ? 4 : 2;
+    const int stage_extra = p.tma_out ? 4 * p.nbuf * 4096 : 0;     // 4 epilogue warps x nbuf staging tiles of 32 rows x 128 B
+    while (p.cps > 1 && (smem_budget() - stage_extra) / (p.cps * p.chunk_bytes) < 3) p.cps >>= 1;   // keep >= 3 stages
+    p.stage_bytes = p.cps * p.chunk_bytes;
     int stages = (smem_budget() - stage_extra) / p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (g_debug_flags[1] > 0 && stages > g_debug_flags[1]) stages = g_debug_flags[1];
@@ -776,7 +809,6 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     const size_t smem = (size_t)stages * p.stage_bytes + stage_extra + 1024;
     p.n_blocks = (p.n_store + p.BN - 1) / p.BN;
     p.dbg = g_debug_flags[7];
-    if (p.ksplit < 1) p.ksplit = 1;
     CUtensorMap b, o;
     if (make_w_map(&b, wd.ptr, wd.wN, wd.wT, wd.wK, p.b_mn ? 64 : bn_cta)) return 2;
     if (p.tma_out) {
@@ -1023,8 +1055,8 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
     int stages = (smem_budget() - stage_extra) / p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
-    p.lbo_bytes = g_debug_flags[2] ? g_debug_flags[2] : 8192;
-    p.sbo_bytes = g_debug_flags[3] ? g_debug_flags[3] : 1024;
+    p.lbo_bytes = 8192;     // MN-major operands: 64-channel blocks 8192 B apart, 8-row (pixel) groups 1024 B apart
+    p.sbo_bytes = 1024;
     p.ntaps = taps;
     const int k = geom == GEOM_1x1 ? 1 : (geom == GEOM_T2x2_S2 ? 2 : 3);
     for (int kh = 0; kh < k; ++kh)

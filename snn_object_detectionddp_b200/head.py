@@ -116,14 +116,16 @@ class Detect(nn.Module):
             dead = dict(dead_frames_ok=last_only)
             b, _ = self.cv2[i][0].forward_seq(rc, x, **dead)
             b, _ = self.cv2[i][1].forward_seq(rc, b, **dead)
-            b = ConvBiasFn.apply(b, self.cv2[i][2].weight, self.cv2[i][2].bias, f32)
             c, _ = self.cv3[i][0][0].forward_seq(rc, x, **dead)
             c, _ = self.cv3[i][0][1].forward_seq(rc, c, **dead)
             c, _ = self.cv3[i][1][0].forward_seq(rc, c, **dead)
             c, _ = self.cv3[i][1][1].forward_seq(rc, c, **dead)
-            c = ConvBiasFn.apply(c, self.cv3[i][2].weight, self.cv3[i][2].bias, f32)
             if last_only:
+                # the closing 1x1 convs have no BatchNorm (no per-frame side effect): only the frames that are returned
                 b, c = b[-B:], c[-B:]
+                f32 = dict(store=rc.store, geom=GEOM_1x1, out_dtype=torch.float32)
+            b = ConvBiasFn.apply(b, self.cv2[i][2].weight, self.cv2[i][2].bias, f32)
+            c = ConvBiasFn.apply(c, self.cv3[i][2].weight, self.cv3[i][2].bias, f32)
             boxes.append(b)
             clss.append(c)
         return HeadOut(boxes, clss, self.training)

@@ -327,12 +327,14 @@ def dw3x3_wgrad(x, dy, dw9c):
 
 
 def space_to_depth8(frames, B, T):
-    """fp32 frames [B,T,3,H,W] (contiguous) -> bf16 NHWC [T*B, H/8, W/8, 192] (timestep-major folded batch)."""
+    """fp32 frames in [0,1] or uint8 frames (divided by 255 on the device) [B,T,3,H,W] (contiguous) -> bf16 NHWC
+    [T*B, H/8, W/8, 192] (timestep-major folded batch)."""
     require_cuda(frames)
-    assert frames.is_contiguous() and frames.dtype == torch.float32
+    assert frames.is_contiguous() and frames.dtype in (torch.float32, torch.uint8)
     h, w = frames.shape[-2:]
     out = torch.empty((T * B, h // 8, w // 8, 192), device=frames.device, dtype=torch.bfloat16)
-    call("snn_space_to_depth8", ptr(frames), ptr(out), B, T, h, w, stream_ptr())
+    name = "snn_space_to_depth8" if frames.dtype == torch.float32 else "snn_space_to_depth8_u8"
+    call(name, ptr(frames), ptr(out), B, T, h, w, stream_ptr())
     return out
 
 

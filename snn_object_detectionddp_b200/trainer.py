@@ -113,7 +113,7 @@ class Trainer:
         The first `warmup_calls` calls run eagerly (they are real steps); the next call captures, then replays.
         Returned tensors are the graph's static outputs: read them before the next call."""
         padded = batch["padded"]
-        key = (tuple(frames.shape), tuple(tuple(t.shape) for t in padded))
+        key = (tuple(frames.shape), frames.dtype, tuple(tuple(t.shape) for t in padded))
         if self._graph_failed:
             return self.train_step(frames, {"padded": tuple(t.to(self.device) for t in padded)})
         if self._graph is not None and self._graph_key != key:

@@ -249,3 +249,22 @@ def test_checkpoint_roundtrip_and_validation_step(tmp_path):
     l1, i1 = tr.train_step(frames, batch)
     l2, i2 = tr2.train_step(frames, batch)
     assert torch.equal(i1, i2)                       # deterministic forward on identical parameters
+
+
+def test_uint8_frames_equal_host_side_division():
+    """uint8 frames divided by 255 on the device (snn_space_to_depth8_u8) == the reference's host-side
+    `.float() / 255.0` (dataset.py:152) fed as fp32: bit-identical features, hence identical losses."""
+    from snn_object_detectionddp_b200 import kernels as K
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (3, 2, 3, 64, 128), generator=g, dtype=torch.uint8)
+    f32 = u8.float() / 255.0
+    a = K.space_to_depth8(u8.to(DEV), 3, 2)
+    b = K.space_to_depth8(f32.to(DEV), 3, 2)
+    assert torch.equal(a, b)
+    _, net = _models("lif", seed=10)
+    net.eval()
+    with torch.no_grad():
+        da, _ = net.forward_sequence(u8.to(DEV))
+        db, _ = net.forward_sequence(f32.to(DEV))
+    for x, y in zip(da.box + da.cls, db.box + db.cls):
+        assert torch.equal(x, y)

@@ -21,16 +21,5 @@ try:
 except Exception as e:
     print("bench parse failed", e)
 PY
-timeout -s KILL 600 python bench.py --config 3 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r6/bench_cfg3.json 2> gpurun_out/r6/bench_cfg3.err
-echo "bench cfg3 rc=$?"; tail -n 3 gpurun_out/r6/bench_cfg3.err
-python - <<'PY'
-import json
-try:
-    d = json.loads(open("gpurun_out/r6/bench_cfg3.json").read().strip().splitlines()[-1])
-    print("cfg3 (T=8, 512x512, B=16/GPU)", d["value"], "img/s", d["ms_per_step"], "ms; e2e", d["e2e"]["value"])
-    for k, v in d["kernels"].items():
-        if v["ms_per_step"] > 0.3:
-            print("  %-28s %7.3f ms %5.0f calls %s" % (k, v["ms_per_step"], v["calls_per_step"], {a: round(b, 1) for a, b in v.items() if a in ("tflops", "gbs")}))
-except Exception as e:
-    print("cfg3 parse failed", e)
-PY
+timeout -s KILL 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 2
+timeout -s KILL 200 python tools/conv_probe2.py 2>&1 | grep -E "single=0 rows_epi=0|single=1 rows_epi=0" | tail -n 12
