@@ -95,6 +95,90 @@ __global__ void __launch_bounds__(kRL * 8) bn_stats_from_partials_kernel(const f
     }
 }
 
+// Fused tail of the train-mode BatchNorm statistics: partial reduce (as above) + per-(t,c) scale/shift/mean/invstd + the
+// T sequential running-stat updates + num_batches_tracked += T, one launch instead of three.  The block that finishes
+// LAST for a channel group (atomic ticket; the result does not depend on which block that is) walks t = 0..T-1 in order.
+// `counters` is a caller-owned, zero-initialised array of ceil(C/8) unsigned ints that the kernel leaves zeroed again.
+__global__ void __launch_bounds__(kRL * 8)
+bn_finalize_partials_kernel(const float* __restrict__ part, double* __restrict__ sums, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, float* running_mean, float* running_var, long long* nbt,
+                            float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
+                            float* __restrict__ invstd_o, unsigned int* counters, int T, int C, int P, int groups_per_t,
+                            float eps, float momentum) {
+    __shared__ double sh[2][kRL][8];
+    __shared__ unsigned int s_ticket;
+    const int t = blockIdx.y;
+    const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int c = blockIdx.x * 8 + cl;
+    double s = 0.0, q = 0.0;
+    if (c < C) {
+        const float* base = part + ((size_t)t * groups_per_t * 2) * C + c;
+        int r = rl;
+        for (; r + 3 * kRL < groups_per_t; r += 4 * kRL) {
+            const float* r0 = base + (size_t)r * 2 * C;
+            const float* r1 = base + (size_t)(r + kRL) * 2 * C;
+            const float* r2 = base + (size_t)(r + 2 * kRL) * 2 * C;
+            const float* r3 = base + (size_t)(r + 3 * kRL) * 2 * C;
+            const float a0 = __ldg(r0), b0 = __ldg(r0 + C), a1 = __ldg(r1), b1 = __ldg(r1 + C);
+            const float a2 = __ldg(r2), b2 = __ldg(r2 + C), a3 = __ldg(r3), b3 = __ldg(r3 + C);
+            s += (double)a0; q += (double)b0; s += (double)a1; q += (double)b1;
+            s += (double)a2; q += (double)b2; s += (double)a3; q += (double)b3;
+        }
+        for (; r < groups_per_t; r += kRL) {
+            const float* r0 = base + (size_t)r * 2 * C;
+            s += (double)__ldg(r0); q += (double)__ldg(r0 + C);
+        }
+    }
+    sh[0][rl][cl] = s; sh[1][rl][cl] = q;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const int co = blockIdx.x * 8 + threadIdx.x;
+        if (co < C) {
+            double a = 0.0, b = 0.0;
+            for (int i = 0; i < kRL; ++i) { a += sh[0][i][threadIdx.x]; b += sh[1][i][threadIdx.x]; }
+            sums[((size_t)t * 2 + 0) * C + co] = a;
+            sums[((size_t)t * 2 + 1) * C + co] = b;
+            const double md = a / P;
+            double vd = b / P - md * md;
+            if (vd < 0) vd = 0;
+            const float m = (float)md, var = (float)vd;
+            const float inv = 1.0f / sqrtf(var + eps);
+            const float g = gamma ? gamma[co] : 1.f, bb = beta ? beta[co] : 0.f;
+            const float sc = g * inv;
+            scale[t * C + co] = sc; shift[t * C + co] = bb - m * sc;
+            mean_o[t * C + co] = m; invstd_o[t * C + co] = inv;
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&counters[blockIdx.x], 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(T - 1)) return;
+    // last block of this channel group: every timestep's sums are visible
+    __threadfence();
+    if (threadIdx.x < 8) {
+        const int co = blockIdx.x * 8 + threadIdx.x;
+        if (co < C && running_mean && running_var) {
+            float rm = running_mean[co], rv = running_var[co];
+            for (int tt = 0; tt < T; ++tt) {
+                const double a = __ldcg(&sums[((size_t)tt * 2 + 0) * C + co]), b = __ldcg(&sums[((size_t)tt * 2 + 1) * C + co]);
+                const double md = a / P;
+                double vd = b / P - md * md;
+                if (vd < 0) vd = 0;
+                const float m = (float)md, var = (float)vd;
+                const float unb = (P > 1) ? (float)(vd * ((double)P / (double)(P - 1))) : var;
+                rm = (1.f - momentum) * rm + momentum * m;
+                rv = (1.f - momentum) * rv + momentum * unb;
+            }
+            running_mean[co] = rm; running_var[co] = rv;
+        }
+    }
+    if (threadIdx.x == 0) {
+        counters[blockIdx.x] = 0u;
+        if (blockIdx.x == 0 && nbt) *nbt += T;
+    }
+}
+
 // scale/shift per (t,c); running-stat update applied T times in order (the reference calls the
 // module once per timestep, model.py:14 via train.py:64-66).
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
@@ -607,6 +691,16 @@ int launch_bn_stats_from_partials(const float* part, double* sums, int T, int C,
     dim3 grid((C + 7) / 8, T);
     bn_stats_from_partials_kernel<<<grid, kRL * 8, 0, st>>>(part, sums, C, groups_per_t);
     return check_cuda(cudaGetLastError(), "bn_stats_from_partials_kernel");
+}
+
+int launch_bn_finalize_partials(const float* part, double* sums, const float* gamma, const float* beta, float* rm, float* rv,
+                                long long* nbt, float* scale, float* shift, float* mean, float* invstd, unsigned int* counters,
+                                int T, int C, int P, int groups_per_t, float eps, float momentum, cudaStream_t st) {
+    SNN_REQUIRE(T >= 1 && C >= 1 && groups_per_t >= 1 && counters != nullptr, "bn_finalize_partials: bad arguments");
+    dim3 grid((C + 7) / 8, T);
+    bn_finalize_partials_kernel<<<grid, kRL * 8, 0, st>>>(part, sums, gamma, beta, rm, rv, nbt, scale, shift, mean, invstd, counters,
+                                                          T, C, P, groups_per_t, eps, momentum);
+    return check_cuda(cudaGetLastError(), "bn_finalize_partials_kernel");
 }
 
 int launch_bn_finalize(const double* sums, const float* gamma, const float* beta, float* rm, float* rv, float* scale,

@@ -63,10 +63,10 @@ def conv_fprop(geom, x0, w_bf16, cout, x1=None, bias=None, out=None, out_dtype=t
 _STATS_GROUPS = {}
 
 
-def conv_fprop_stats(geom, x0, w_bf16, cout, T, x1=None):
-    """ConvBlock conv with the per-timestep BatchNorm sums fused into its epilogue.
-    Returns (y fp32 [NB,Ho,Wo,cout], sums fp64 [T][2][cout]); sums is None when the geometry cannot keep every 128-pixel
-    tile inside one timestep (then the caller runs bn_stats on y)."""
+def conv_fprop_partials(geom, x0, w_bf16, cout, T, x1=None):
+    """ConvBlock conv whose epilogue also emits the per-(32-pixel group, channel) BatchNorm partial sums.
+    Returns (y fp32 [NB,Ho,Wo,cout], partials fp32 [groups][2][cout] | None, groups_per_timestep); partials is None when
+    the geometry cannot keep every 128-pixel tile inside one timestep (then the caller runs bn_stats on y)."""
     require_cuda(x0, x1, w_bf16)
     nb, h, w, c0 = x0.shape
     key = (geom, nb, h, w, T)
@@ -76,7 +76,7 @@ def conv_fprop_stats(geom, x0, w_bf16, cout, T, x1=None):
         _STATS_GROUPS[key] = (int(n), int(gpt.value))
     groups, gpt = _STATS_GROUPS[key]
     if groups == 0:
-        return conv_fprop(geom, x0, w_bf16, cout, x1=x1), None
+        return conv_fprop(geom, x0, w_bf16, cout, x1=x1), None, 0
     ho, wo = out_hw(geom, h, w)
     out = torch.empty((nb, ho, wo, cout), device=x0.device, dtype=torch.float32)
     rows, taps, wk = w_bf16.shape
@@ -87,9 +87,31 @@ def conv_fprop_stats(geom, x0, w_bf16, cout, T, x1=None):
     call("snn_conv_fprop_stats", geom, nb, h, w, ptr(x0), c0, _nhwc_ld(x0), ptr(x1), c1, 0 if x1 is None else _nhwc_ld(x1),
          ptr(w_bf16), rows, wk, 0, cout, 0, ptr(out), nb // T, ptr(part), stream_ptr(),
          work=("flop", _conv_flops(geom, nb, h, w, c0 + c1, cout), f"g{geom} nb{nb} {h}x{w} {c0 + c1}->{cout}"))
+    return out, part, gpt
+
+
+def conv_fprop_stats(geom, x0, w_bf16, cout, T, x1=None):
+    """conv_fprop_partials + the fixed-order reduce: returns (y, sums fp64 [T][2][cout] | None)."""
+    out, part, gpt = conv_fprop_partials(geom, x0, w_bf16, cout, T, x1=x1)
+    if part is None:
+        return out, None
     sums = torch.empty((T, 2, cout), device=x0.device, dtype=torch.float64)
     call("snn_bn_stats_from_partials", ptr(part), ptr(sums), T, cout, gpt, stream_ptr(), work=("byte", 4.0 * part.numel()))
     return out, sums
+
+
+def bn_finalize_partials(part, gpt, gamma, beta, running_mean, running_var, num_batches_tracked, counters, T, C, P, eps, momentum):
+    """Partials -> (scale, shift, mean, invstd) [T][C] + the T running-statistics updates + num_batches_tracked += T,
+    in one launch.  `counters`: persistent zeroed uint32 [ceil(C/8)] (the kernel leaves it zeroed)."""
+    dev = part.device
+    scale, shift, mean, invstd = (torch.empty((T, C), device=dev, dtype=torch.float32) for _ in range(4))
+    sums = torch.empty((T, 2, C), device=dev, dtype=torch.float64)
+    assert counters.dtype == torch.int32 and counters.numel() >= (C + 7) // 8
+    assert num_batches_tracked is None or num_batches_tracked.dtype == torch.int64
+    call("snn_bn_finalize_partials", ptr(part), ptr(sums), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+         ptr(num_batches_tracked), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(counters), T, C, P, gpt, float(eps),
+         float(momentum), stream_ptr(), work=("byte", 4.0 * part.numel()))
+    return scale, shift, mean, invstd
 
 
 def conv_dgrad(geom, dy, w_bf16, in_hw, ci, ci_off=0, out=None, out_dtype=torch.bfloat16, accumulate=False):

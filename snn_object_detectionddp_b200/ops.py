@@ -47,18 +47,25 @@ class ConvBNActFn(Function):
     def forward(ctx, x0, x1, v_init, weight, gamma, beta, cfg):
         st, geom, T, bn, neuron, training = cfg["store"], cfg["geom"], cfg["T"], cfg["bn"], cfg["neuron"], cfg["training"]
         cout = weight.shape[0]
-        sums = None
+        sums = part = None
+        gpt = 0
         if geom == K.GEOM_DW3x3:
             y = K.dw3x3_fprop(x0, st.w_master3(weight).view(9, cout))
         elif training:
-            y, sums = K.conv_fprop_stats(geom, x0, st.w_fprop(weight), cout, T, x1=x1)    # BN sums fused into the epilogue
+            y, part, gpt = K.conv_fprop_partials(geom, x0, st.w_fprop(weight), cout, T, x1=x1)    # BN partial sums from the epilogue
         else:
             y = K.conv_fprop(geom, x0, st.w_fprop(weight), cout, x1=x1)
         nb, ho, wo, _ = y.shape
         P = (nb // T) * ho * wo
-        if training:
-            if sums is None:
-                sums = K.bn_stats(y, T)
+        if training and part is not None:
+            ctr = getattr(bn, "_snn_counters", None)
+            if ctr is None or ctr.device != y.device:
+                ctr = torch.zeros(((cout + 7) // 8,), device=y.device, dtype=torch.int32)
+                bn._snn_counters = ctr            # plain attribute: not a buffer, never in state_dict
+            scale, shift, mean, invstd = K.bn_finalize_partials(part, gpt, gamma, beta, bn.running_mean, bn.running_var,
+                                                                bn.num_batches_tracked, ctr, T, cout, P, bn.eps, bn.momentum)
+        elif training:
+            sums = K.bn_stats(y, T)
             scale, shift, mean, invstd = K.bn_finalize(sums, gamma, beta, bn.running_mean, bn.running_var, T, cout, P,
                                                        bn.eps, bn.momentum, True)
             if bn.num_batches_tracked is not None:

@@ -145,3 +145,57 @@ def test_streaming_detector_carries_state():
     for t in range(3):
         out = det(frames[:, t])
     assert len(out) == 2
+
+
+@pytest.mark.parametrize("B", [1, 32])
+def test_eval_spikes_teacher_forced_bit_compare(B):
+    """configs[4]: batch-1 / batch-32 streaming windows, T=4, eval mode (BatchNorm running statistics).  Every spiking
+    ConvBlock of the product is fed the ORACLE's input of that layer (teacher forcing, so one layer's flips cannot
+    cascade): spikes must agree exactly, except neurons whose oracle membrane lies within 1e-5 of threshold -- those are
+    counted and reported as the flip rate (SURVEY.md 7.2 protocol)."""
+    setup_exact()
+    from oracle import snn_oracle as O
+    from snn_object_detectionddp_b200.model import RunCtx
+    from snn_object_detectionddp_b200.params import store_for
+    orc, net = _models(seed=23)
+    with torch.no_grad():                       # non-trivial running statistics
+        for m in orc.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.uniform_(-0.2, 0.2); m.running_var.uniform_(0.5, 2.0)
+    net.load_state_dict(orc.state_dict())
+    orc.eval(); net.eval()
+    T, HW = 4, 128
+    frames, _ = MO.synthetic_batch(B, T, HW, HW, seed=33)
+    frames = frames.to(DEV)
+    names = {m: n for n, m in orc.temporal_unet.named_modules() if isinstance(m, O.OracleConvBlock)}
+    rec_x, rec_s, rec_u = {}, {}, {}
+
+    def hook(m, inp, outp):
+        rec_x.setdefault(names[m], []).append(inp[0].detach())
+        rec_s.setdefault(names[m], []).append(outp[0].detach())
+        rec_u.setdefault(names[m], []).append(m.last_u)
+
+    hs = [m.register_forward_hook(hook) for m in names]
+    with torch.no_grad():
+        hid = None
+        for t in range(T):
+            _, hid = orc(frames[:, t], hid)
+    for h in hs:
+        h.remove()
+    st = store_for(net, DEV)
+    st.refresh_operands()
+    blocks = dict(net.temporal_unet.named_modules())
+    report, n_tot, flips, far = [], 0, 0, 0
+    with torch.no_grad():
+        for name, xs in rec_x.items():
+            x = torch.cat(xs, 0).permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()          # folded [T*B,h,w,C]
+            out, _ = blocks[name].forward_seq(RunCtx(st, T), x)
+            s_p = out.reshape(T, B, *out.shape[1:]).permute(0, 1, 4, 2, 3).float()
+            s_o, u_o = torch.stack(rec_s[name]), torch.stack(rec_u[name])
+            d = s_p != s_o
+            near = (u_o - 1.0).abs() < 1e-5
+            report.append((name, int(d.sum()), int((d & ~near).sum()), float(s_o.mean())))
+            n_tot += s_o.numel(); flips += int(d.sum()); far += int((d & ~near).sum())
+    print(f"B={B}: eval spike flip report (layer, flips, far-from-threshold flips, spike rate):", *report, sep="\n  ")
+    print(f"B={B}: flip rate {flips}/{n_tot} = {flips / n_tot:.2e}")
+    assert len(report) == 16 and far == 0 and flips <= max(4, int(2e-6 * n_tot)), report

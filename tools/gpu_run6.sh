@@ -22,4 +22,3 @@ except Exception as e:
     print("bench parse failed", e)
 PY
 timeout -s KILL 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 2
-timeout -s KILL 200 python tools/conv_probe2.py 2>&1 | grep -E "single=0 rows_epi=0|single=1 rows_epi=0" | tail -n 12
