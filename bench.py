@@ -63,6 +63,11 @@ def workload(args):
     return B, T, HW
 
 
+def workload_name(args, B, T, HW):
+    return (f"BASELINE.json configs[{args.config - 1}]: default SNN detector ({args.neuron} neurons), T={T}, batch {B}/GPU, "
+            f"synthetic {HW}x{HW} RGB frames, one train step (fwd + loss + bwd + clip + AdamW + OneCycle)")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -151,8 +156,7 @@ def run_reference(args):
         "impl": "reference", "metric": "train images/sec", "value": r["value"], "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE.json configs[{args.config - 1}]: SNN detector ({args.neuron}) T={T} batch {B}/GPU "
-                               f"{HW}x{HW}, one train step", "cpu_sample_batch": args.ref_batch},
+        "config": {"workload": workload_name(args, B, T, HW), "per_gpu_batch": B, "T": T, "cpu_sample_batch": args.ref_batch},
         "cpu_baseline": {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -382,9 +386,7 @@ def run_ours(args):
         "metric": "train images/sec", "value": world * B * args.steps / (ms_total * 1e-3), "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"BASELINE.json configs[{args.config - 1}]: default SNN detector ({args.neuron} neurons), T={T}, "
-                               f"batch {B}/GPU, synthetic {HW}x{HW} RGB frames, one train step "
-                               f"(fwd + loss + bwd + clip + AdamW + OneCycle)",
+        "config": {"workload": workload_name(args, B, T, HW),
                    "per_gpu_batch": B, "T": T, "frames_per_s": world * B * T * args.steps / (ms_total * 1e-3),
                    "l2": "per-step working set (240 MB bf16 weights + GBs of activations) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world}", "feature_extractor": "stand-in frozen pyramid (YOLO11m weights unobtainable offline)"},
