@@ -268,3 +268,44 @@ def test_uint8_frames_equal_host_side_division():
         db, _ = net.forward_sequence(f32.to(DEV))
     for x, y in zip(da.box + da.cls, db.box + db.cls):
         assert torch.equal(x, y)
+
+
+def test_reference_training_loop_runs_unchanged_on_the_drop_in_modules():
+    """The body of the reference's train_one_epoch (train.py:58-80) verbatim -- per-frame loop threading `hidden`, loss on
+    the last predictions, `.sum().backward()`, `clip_grad_norm_(10)`, torch `AdamW` + `OneCycleLR` -- on the drop-in
+    modules, next to the fused Trainer path on a twin model: same losses step after step (the fused optimizer and the
+    torch optimizer implement the same update; the two forward paths are bit-identical)."""
+    setup_exact()
+    from snn_object_detectionddp_b200.loss import v8DetectionLoss
+    from snn_object_detectionddp_b200.trainer import Trainer
+    _, model = _models("lif", seed=12)
+    _, twin = _models("lif", seed=12)
+    B, T, HW = 2, 3, 128
+    image_tensor, labels_tensor = MO.synthetic_batch(B, T, HW, HW, seed=15)
+    image_tensor, labels_tensor = image_tensor.to(DEV), labels_tensor.to(DEV)
+    total_steps = 10
+    # --- reference code path (train.py:155-169 + 58-80) ---
+    loss_fn = v8DetectionLoss(model)
+    optimizer = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=5e-4)
+    scheduler = torch.optim.lr_scheduler.OneCycleLR(optimizer, max_lr=1e-4, total_steps=total_steps)
+    tr = Trainer(twin, max_lr=1e-4, weight_decay=5e-4, total_steps=total_steps, device=DEV)
+    model.train()
+    for step in range(3):
+        optimizer.zero_grad()
+        hidden_state = None
+        for t in range(T):
+            frame = image_tensor[:, t, :, :, :]
+            preds, hidden_state = model(frame, hidden_state)
+        batch_dict = {'batch_idx': labels_tensor[:, 0], 'cls': labels_tensor[:, 1], 'bboxes': labels_tensor[:, 2:]}
+        loss, loss_components_detached = loss_fn(preds, batch_dict)
+        loss.sum().backward()
+        gn = torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
+        optimizer.step()
+        scheduler.step()
+        _, items = tr.train_step(image_tensor, batch_dict)
+        print(step, loss_components_detached.tolist(), items.tolist(), float(gn), float(tr.grad_norm))
+        if step == 0:
+            assert torch.equal(items, loss_components_detached)          # identical parameters, deterministic forward
+            assert abs(float(gn) - float(tr.grad_norm)) < 2e-2 * float(gn)
+        assert torch.allclose(items, loss_components_detached, rtol=0.2, atol=1e-2)
+    assert all(p.grad is not None for p in model.temporal_unet.parameters())
