@@ -790,6 +790,9 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     p.chunk_bytes = p.b_mn ? 16384 + p.b_boxes * 8192 : 16384 + bn_cta * 128;
     // chunks per stage: keep >= ~512 MMA cycles behind every mbarrier round trip (N = 256: 1 chunk, 128: 2, <= 64: 4)
     p.cps = small_k ? 1 : (p.BN > 128 ? 1 : (p.BN > 64 ? 2 : 4));
+    for (int ph = 0; ph < p.nphase && p.cps > 1; ++ph)          // ragged segments (e.g. 144 channels = 3 chunks) would leave
+        for (int i = 0; i < p.phase[ph].nseg; ++i)               // half-empty stages behind: fall back to one chunk per stage
+            while (p.cps > 1 && p.phase[ph].seg[i].nchunk % p.cps != 0) p.cps >>= 1;
     if (g_debug_flags[2] > 0) p.cps = g_debug_flags[2];
     // coalesced TMA-store epilogue whenever the output view is expressible as a tensor map
     const int es = p.out_f32 ? 4 : 2, CH = p.out_f32 ? 32 : 64;
