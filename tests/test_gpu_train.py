@@ -309,3 +309,30 @@ def test_reference_training_loop_runs_unchanged_on_the_drop_in_modules():
             assert abs(float(gn) - float(tr.grad_norm)) < 2e-2 * float(gn)
         assert torch.allclose(items, loss_components_detached, rtol=0.2, atol=1e-2)
     assert all(p.grad is not None for p in model.temporal_unet.parameters())
+
+
+def test_device_prefetcher_pageable_and_pinned_sources():
+    """data.DevicePrefetcher: batches arrive intact and in order whether the host tensors are pageable (staged through
+    pinned memory) or already pinned, with the copy of batch i+1 queued while batch i is in use."""
+    from snn_object_detectionddp_b200.data import DevicePrefetcher
+    pf = DevicePrefetcher(DEV)
+    g = torch.Generator().manual_seed(4)
+    batches = []
+    for i in range(5):
+        fr = torch.randint(0, 256, (2, 2, 3, 64, 64), generator=g, dtype=torch.uint8)
+        pad = (torch.full((2, 8), float(i)), torch.rand(2, 8, 4, generator=g), torch.ones(2, 8, dtype=torch.bool))
+        if i % 2:
+            fr, pad = fr.pin_memory(), tuple(t.pin_memory() for t in pad)
+        batches.append((fr, pad))
+    pf.stage(*batches[0])
+    for i in range(5):
+        fr_d, pad_d = pf.take()
+        if i + 1 < 5:
+            pf.stage(*batches[i + 1])
+        got = (fr_d.clone(), tuple(t.clone() for t in pad_d))
+        pf.release()
+        torch.cuda.synchronize()
+        assert torch.equal(got[0].cpu(), batches[i][0])
+        for a, b in zip(got[1], batches[i][1]):
+            assert torch.equal(a.cpu(), b)
+    assert pf.bytes_per_batch() == sum(t.numel() * t.element_size() for t in (batches[4][0],) + batches[4][1])
