@@ -60,3 +60,30 @@ class StreamingDetector:
             frames = frames[:, None]
         out, self.hidden = detect_sequence(self.model, frames, hidden_state=self.hidden, return_state=True, **self.kw)
         return out
+
+
+class GraphedWindowDetector:
+    """`detect_sequence(..., padded=True)` replayed from ONE CUDA graph (static window shape): the ~250 launches of an
+    eval window cost ~6 ms of host time eagerly whatever the batch size, a replay is bounded by the GPU.  Returns the
+    graph's static (rows [B,max_det,6], kept [B,max_det], counts [B]) device tensors: read them before the next call."""
+
+    def __init__(self, model, conf_thres=0.3, iou_thres=0.45, multi_label=True, agnostic=False, max_det=300, warmup=2):
+        self.model, self.warmup = model, warmup
+        self.kw = dict(conf_thres=conf_thres, iou_thres=iou_thres, multi_label=multi_label, agnostic=agnostic, max_det=max_det)
+        self._graph = self._key = self._in = self._out = None
+
+    @torch.no_grad()
+    def __call__(self, frames):
+        key = (tuple(frames.shape), frames.dtype, frames.device)
+        if self._graph is None or key != self._key:
+            for _ in range(self.warmup):
+                detect_sequence(self.model, frames, padded=True, **self.kw)
+            self._in = frames.clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._out = detect_sequence(self.model, self._in, padded=True, **self.kw)
+            self._graph, self._key = g, key
+        self._in.copy_(frames, non_blocking=True)
+        self._graph.replay()
+        return self._out

@@ -199,3 +199,20 @@ def test_eval_spikes_teacher_forced_bit_compare(B):
     print(f"B={B}: eval spike flip report (layer, flips, far-from-threshold flips, spike rate):", *report, sep="\n  ")
     print(f"B={B}: flip rate {flips}/{n_tot} = {flips / n_tot:.2e}")
     assert len(report) == 16 and far == 0 and flips <= max(4, int(2e-6 * n_tot)), report
+
+
+def test_graphed_window_detector_equals_eager():
+    """CUDA-graph replay of the eval window (unroll -> decode -> NMS) == the eager calls, on changing inputs."""
+    setup_exact()
+    from snn_object_detectionddp_b200.infer import GraphedWindowDetector, detect_sequence
+    _, net = _models(seed=24)
+    det = GraphedWindowDetector(net, conf_thres=0.3)
+    for seed in (41, 42, 43):
+        frames, _ = MO.synthetic_batch(2, 3, 128, 128, seed=seed)
+        frames = frames.to(DEV)
+        rows_g, kept_g, counts_g = (t.clone() for t in det(frames))
+        rows_e, kept_e, counts_e = detect_sequence(net, frames, conf_thres=0.3, padded=True)
+        assert torch.equal(counts_g, counts_e)
+        for b in range(2):
+            n = int(counts_e[b])
+            assert torch.equal(rows_g[b, :n], rows_e[b, :n]) and torch.equal(kept_g[b, :n], kept_e[b, :n])
