@@ -755,7 +755,8 @@ static void pick_box(int NB, int H, int W, int npix, int* bn, int* bh, int* bw) 
 enum { GEOM_3x3_S1 = 0, GEOM_3x3_S2 = 1, GEOM_1x1 = 2, GEOM_T2x2_S2 = 3 };
 
 static int g_debug_flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-void debug_set(int k, int v) { if (k >= 0 && k < 8) g_debug_flags[k] = v; }
+void neuron_debug_set(int k, int v);
+void debug_set(int k, int v) { if (k >= 0 && k < 8) g_debug_flags[k] = v; else if (k >= 8 && k < 12) neuron_debug_set(k - 8, v); }
 
 static int smem_budget() { return 220 * 1024; }
 

@@ -648,6 +648,109 @@ bn_act_bwd2_kernel(const float* __restrict__ y, const float* __restrict__ scale,
 }
 
 // ------------------------------------------------------------------------------------------
+// T == 1 SiLU layers (Detect head: only the last frame carries gradient): no scan, so the generic kernel would keep a
+// single 12-byte operand pair in flight per thread (1.4 TB/s measured).  Same two passes, four pixels per thread and
+// iteration.  Arithmetic identical to bn_act_bwd2_kernel<ACT_SILU, 1, ...>.
+// ------------------------------------------------------------------------------------------
+template <bool REDUCE>
+__global__ void __launch_bounds__(256, 4)
+silu_t1_bwd2_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ beta_bn,
+                    const float* __restrict__ red_in, const __nv_bfloat16* __restrict__ gs, __nv_bfloat16* __restrict__ dy_out,
+                    float* __restrict__ red_out, float* dgamma, float* dbeta, int P, int C, int Cb, int pix_per_block, float invP) {
+    extern __shared__ float4 sht[];
+    constexpr int PU = 4;
+    const int c_base = blockIdx.y * Cb;
+    const int tpp = Cb >> 1, rows = 256 / tpp;
+    const int cg = threadIdx.x % tpp, row = threadIdx.x / tpp;
+    float4* tabA = sht;                                            // {scale.xy, shift.xy}
+    float4* tabB = sht + tpp;                                      // REDUCE {-mean.xy,0,0} ; DX {-scale*mean(gx).xy, -mean(gx*xhat)*invstd.xy}
+    float* accum = reinterpret_cast<float*>(tabB + tpp);           // REDUCE [2][Cb]
+    for (int j = threadIdx.x; j < tpp; j += 256) {
+        const int gc = c_base + 2 * j;
+        const float2 sc = *reinterpret_cast<const float2*>(scale + gc), sh = *reinterpret_cast<const float2*>(shift + gc);
+        tabA[j] = make_float4(sc.x, sc.y, sh.x, sh.y);
+        if (REDUCE) {
+            const float2 m = *reinterpret_cast<const float2*>(mean + gc);
+            tabB[j] = make_float4(-m.x, -m.y, 0.f, 0.f);
+        } else {
+            const float2 r0 = *reinterpret_cast<const float2*>(red_in + gc), r1 = *reinterpret_cast<const float2*>(red_in + C + gc);
+            const float2 is = *reinterpret_cast<const float2*>(invstd + gc);
+            tabB[j] = make_float4(-(sc.x * (r0.x * invP)), -(sc.y * (r0.y * invP)), -(r1.x * invP * is.x), -(r1.y * invP * is.y));
+        }
+    }
+    if (REDUCE) {
+        for (int i = threadIdx.x; i < 2 * Cb; i += 256) accum[i] = 0.f;
+    } else if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < Cb; c += 256) {
+            if (dbeta) dbeta[c_base + c] += red_in[c_base + c];
+            if (dgamma) dgamma[c_base + c] += red_in[C + c_base + c];
+        }
+    }
+    __syncthreads();
+    if (row < rows) {
+        const float4 a = tabA[cg], k = tabB[cg];
+        const float2 sc = f2(a.x, a.y), sh = f2(a.z, a.w), one2 = f2(1.f, 1.f);
+        float2 nbb = f2(0.f, 0.f);
+        if (!REDUCE && beta_bn) {
+            const float2 b = *reinterpret_cast<const float2*>(beta_bn + c_base + 2 * cg);
+            nbb = f2(-b.x, -b.y);
+        }
+        const int C2 = C >> 1;
+        const int xb = REDUCE ? (int)blockIdx.x : (int)(gridDim.x - 1 - blockIdx.x);
+        const int p0 = xb * pix_per_block, p1 = min(P, p0 + pix_per_block);
+        float2 acc_s = f2(0.f, 0.f), acc_d = f2(0.f, 0.f);
+        for (int p = p0 + row; p < p1; p += rows * PU) {
+            float2 yv[PU];
+            uint32_t gr[PU];
+#pragma unroll
+            for (int j = 0; j < PU; ++j) {
+                const int pj = p + j * rows;
+                if (pj < p1) {
+                    const size_t e2 = (size_t)pj * C2 + (c_base >> 1) + cg;
+                    yv[j] = REDUCE ? __ldg(reinterpret_cast<const float2*>(y) + e2) : __ldcs(reinterpret_cast<const float2*>(y) + e2);
+                    gr[j] = REDUCE ? __ldg(reinterpret_cast<const uint32_t*>(gs) + e2) : __ldcs(reinterpret_cast<const uint32_t*>(gs) + e2);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PU; ++j) {
+                const int pj = p + j * rows;
+                if (pj < p1) {
+                    const float2 xm = __fmul2_rn(yv[j], sc);
+                    const float2 x = f2(__fadd_rn(xm.x, sh.x), __fadd_rn(xm.y, sh.y));
+                    const float2 g = f2(bf16_lo(gr[j]), bf16_hi(gr[j]));
+                    const float2 e = f2(ex2_approx(-1.4426950408889634f * x.x), ex2_approx(-1.4426950408889634f * x.y));
+                    const float2 d1 = __fadd2_rn(e, one2);
+                    const float2 sgm = f2(rcp_approx(d1.x), rcp_approx(d1.y));
+                    const float2 oms = __fadd2_rn(one2, f2(-sgm.x, -sgm.y));
+                    const float2 gx = __fmul2_rn(g, __fmul2_rn(sgm, __ffma2_rn(x, oms, one2)));
+                    if (REDUCE) {
+                        acc_s = __fadd2_rn(acc_s, gx);
+                        acc_d = __ffma2_rn(gx, __fadd2_rn(yv[j], f2(k.x, k.y)), acc_d);
+                    } else {
+                        const float2 t1 = __ffma2_rn(sc, gx, f2(k.x, k.y));
+                        const float2 d = __ffma2_rn(__fadd2_rn(x, nbb), f2(k.z, k.w), t1);
+                        *(reinterpret_cast<uint32_t*>(dy_out) + (size_t)pj * C2 + (c_base >> 1) + cg) = pack_bf16x2(d.x, d.y);
+                    }
+                }
+            }
+        }
+        if (REDUCE) {
+            const int cl = cg * 2;
+            atomicAdd(&accum[cl], acc_s.x); atomicAdd(&accum[cl + 1], acc_s.y);
+            atomicAdd(&accum[Cb + cl], acc_d.x); atomicAdd(&accum[Cb + cl + 1], acc_d.y);
+        }
+    }
+    if (REDUCE) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < Cb; c += 256) {
+            atomicAdd(&red_out[c_base + c], accum[c]);
+            atomicAdd(&red_out[C + c_base + c], accum[Cb + c] * invstd[c_base + c]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
 static int pick_ppb(int P, int rows, int T) {
@@ -796,6 +899,9 @@ static int launch_bwd2_t(const float* y, const float* scale, const float* shift,
     return check_cuda(cudaGetLastError(), REDUCE ? "bn_act_bwd2_kernel<reduce>" : "bn_act_bwd2_kernel<dx>");
 }
 
+static int g_t1_fast = 1;     // 0: T == 1 SiLU layers go through the generic kernel (A/B timing)
+void neuron_debug_set(int k, int v) { if (k == 0) g_t1_fast = v ? 0 : 1; }
+
 // pass = 0: reduce (writes red [T][2][C], zeroed here); pass = 1: dx (reads red; writes dy, gv_init; dgamma/dbeta +=)
 int launch_bn_act_bwd2(int pass, int act, const float* y, const float* scale, const float* shift, const float* mean,
                        const float* invstd, const float* beta_bn, const float* v_init, const __nv_bfloat16* gs,
@@ -804,6 +910,27 @@ int launch_bn_act_bwd2(int pass, int act, const float* y, const float* scale, co
     SNN_REQUIRE(C % 2 == 0 && C >= 2, "bn_act_bwd2: C=%d must be even", C);
     SNN_REQUIRE(T >= 1 && T <= 16, "bn_act_bwd2: T=%d must be in [1,16]", T);
     if (pass == 0) SNN_CUDA_OK(cudaMemsetAsync(red, 0, sizeof(float) * 2 * T * C, st));
+    if (act == ACT_SILU && T == 1 && g_t1_fast) {
+        int Cb = C;
+        while (Cb > 512 && Cb % 4 == 0) Cb >>= 1;
+        SNN_REQUIRE(C % Cb == 0 && Cb % 2 == 0 && Cb <= 512, "bn_act_bwd2: cannot tile C=%d", C);
+        const int rows = 256 / (Cb / 2), nyb = C / Cb;
+        long long want_blocks = (long long)num_sms() * 4 * (pass == 0 ? 1 : 2) / nyb;
+        if (want_blocks < 1) want_blocks = 1;
+        int ppb = (int)((P + want_blocks - 1) / want_blocks);
+        const int unit = rows * 4;
+        if (ppb < unit * (pass == 0 ? 2 : 1)) ppb = unit * (pass == 0 ? 2 : 1);
+        ppb = ((ppb + unit - 1) / unit) * unit;
+        const size_t smem = (size_t)(Cb / 2) * 32 + (pass == 0 ? (size_t)2 * Cb * 4 : 0);
+        dim3 grid((P + ppb - 1) / ppb, nyb);
+        if (pass == 0)
+            silu_t1_bwd2_kernel<true><<<grid, 256, smem, st>>>(y, scale, shift, mean, invstd, beta_bn, nullptr, gs, nullptr, red, nullptr,
+                                                               nullptr, P, C, Cb, ppb, 1.0f / (float)P);
+        else
+            silu_t1_bwd2_kernel<false><<<grid, 256, smem, st>>>(y, scale, shift, mean, invstd, beta_bn, red, gs, dy, nullptr, dgamma, dbeta,
+                                                                P, C, Cb, ppb, 1.0f / (float)P);
+        return check_cuda(cudaGetLastError(), "silu_t1_bwd2_kernel");
+    }
 #define SNN_BWD2(ACT, TM)                                                                                                   \
     return pass == 0 ? launch_bwd2_t<ACT, TM, true>(y, scale, shift, mean, invstd, beta_bn, nullptr, v_init, gs, gv_final,   \
                                                     nullptr, nullptr, red, nullptr, nullptr, T, P, C, beta, theta, alpha, st) \

@@ -275,3 +275,30 @@ def test_recompute_backward_matches_autograd(act, T, B, H, W, C):
         assert rel_err(dgamma, gg_ref) < 2e-4 and rel_err(dbeta, gb_ref) < 2e-4
         if act == LIF:
             assert rel_err(gv0.reshape(P, C), gv0_ref) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,C", [(3, 9, 5, 144), (2, 16, 16, 64), (1, 7, 3, 1024), (4, 8, 8, 72)])
+def test_silu_t1_fast_backward_equals_generic_kernel(B, H, W, C):
+    """T == 1 SiLU layers (Detect head, live frame only) use a 4-pixels-per-thread kernel; same arithmetic as the generic
+    two-pass kernel: reductions agree to the fp32-atomic order, dy to a handful of bf16 rounding flips."""
+    setup_exact()
+    K = _k()
+    from snn_object_detectionddp_b200 import _lib
+    T, P = 1, B * H * W
+    y, gamma, beta = _data(T, B, H, W, C, seed=17)
+    y = y + 0.3
+    gs = torch.randn(T * B, H, W, C, device="cuda").to(torch.bfloat16)
+    sums = K.bn_stats(y, T)
+    scale, shift, mean, invstd = K.bn_finalize(sums, gamma, beta, None, None, T, C, P, 1e-3, 0.03, True)
+    outs = []
+    try:
+        for generic in (0, 1):
+            _lib.lib().snn_debug_set(8, generic)
+            dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+            dy, _, red = K.bn_act_bwd_train(SILU, y, scale, shift, mean, invstd, beta, gs, T, dg, db)
+            outs.append((dy.float(), red.clone(), dg, db))
+    finally:
+        _lib.lib().snn_debug_set(8, 0)
+    (dy0, red0, dg0, db0), (dy1, red1, dg1, db1) = outs
+    assert rel_err(red0, red1) < 1e-5 and rel_err(dg0, dg1) < 1e-5 and rel_err(db0, db1) < 1e-5
+    assert rel_err(dy0, dy1) < 1e-4 and float((dy0 != dy1).float().mean()) < 1e-3
