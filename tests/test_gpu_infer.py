@@ -216,3 +216,16 @@ def test_graphed_window_detector_equals_eager():
         for b in range(2):
             n = int(counts_e[b])
             assert torch.equal(rows_g[b, :n], rows_e[b, :n]) and torch.equal(kept_g[b, :n], kept_e[b, :n])
+
+
+def test_nms_kernel_reproduces_torchvision_fixture(golden_dir):
+    """snn_nms vs the committed fixture recorded from the real torchvision.ops.nms (tests/golden/make_golden_nms.py):
+    rows, order and values bit-exact -- no oracle code involved at comparison time."""
+    import os
+    from snn_object_detectionddp_b200.nms import non_max_suppression
+    fx = torch.load(os.path.join(golden_dir, "nms_golden.pt"), weights_only=False)
+    for case in fx["cases"]:
+        kw = dict(case["kwargs"])
+        ours = non_max_suppression(case["pred"].to(DEV), kw.pop("conf_thres"), kw.pop("iou_thres"), max_det=300, **kw)
+        for a, b in zip(ours, case["rows"]):
+            assert torch.equal(a.cpu(), b), case["name"]

@@ -137,3 +137,18 @@ def test_lif_surrogate_gradcheck_form():
     import math
     exp = 1.0 / (1.0 + (math.pi * (u.detach() - 1.0)) ** 2)
     assert torch.allclose(u.grad, exp)
+
+
+def test_nms_oracle_reproduces_torchvision_fixture(golden_dir):
+    """tests/golden/nms_golden.pt was recorded with the REAL torchvision.ops.nms behind the restated ultralytics candidate
+    logic (tests/golden/make_golden_nms.py, incl. a torchvision.ops.batched_nms cross-check): the oracle must keep
+    reproducing it row for row."""
+    from oracle import detect_oracle as D
+    fx = torch.load(os.path.join(golden_dir, "nms_golden.pt"), weights_only=False)
+    assert len(fx["cases"]) == 3
+    for case in fx["cases"]:
+        rows = D.non_max_suppression(case["pred"], max_det=300, **case["kwargs"])
+        assert len(rows) == len(case["rows"])
+        for a, b in zip(rows, case["rows"]):
+            assert torch.equal(a, b), case["name"]
+        assert sum(r.shape[0] for r in rows) > 0
