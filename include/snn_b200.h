@@ -143,6 +143,17 @@ int snn_space_to_depth8(const float* frames, void* out_bf16, int B, int T, int H
  * runs on the device, bit-identical to the host's, and the host->device copy shrinks 4x */
 int snn_space_to_depth8_u8(const unsigned char* frames, void* out_bf16, int B, int T, int H, int W, void* stream);
 
+/* ---- UpBlock skip resize (model.py:43-44: F.interpolate(skip_x, size=x.shape[2:], mode='bilinear', align_corners=False)),
+ *      NHWC bf16 [NB,Hi,Wi,C] -> [NB,Ho,Wo,C], ATen's source-index / weight formula in fp32, one rounding to bf16.
+ *      backward = 1: src is the gradient w.r.t. the RESIZED tensor [NB,Ho,Wo,C], dst the gradient w.r.t. the input
+ *      [NB,Hi,Wi,C] (deterministic gather, no atomics).  (Hi, Wi) / (Ho, Wo) always name the forward's input / output. ---- */
+int snn_bilinear_resize(int backward, const void* src_bf16, void* dst_bf16, int NB, int Hi, int Wi, int Ho, int Wo, int C,
+                        void* stream);
+/* ---- bottom/right zero-pad (Hd >= Hs) or crop (Hd <= Hs) of an NHWC bf16 tensor: dst[n,h,w,:] = src[n,h,w,:] inside the
+ *      source extent, 0 outside.  In front of a stride-2 3x3 pad-1 conv (DownBlock.conv1, model.py:24) whose input has an
+ *      odd H or W (the 15x20 level of a 480x640 frame) the zero row/column IS the conv's padding; the crop is its backward. ---- */
+int snn_nhwc_pad_crop(const void* src_bf16, void* dst_bf16, int NB, int Hs, int Ws, int Hd, int Wd, int C, void* stream);
+
 /* ---- bias gradient of the biased convs (ConvLSTM2d.conv, UpBlock.up, out_p*): acc[c] += sum_p dy[p][c] ---- */
 int snn_colsum_bf16(const void* dy_bf16, float* acc, long long P, int C, void* stream);
 

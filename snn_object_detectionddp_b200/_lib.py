@@ -36,6 +36,8 @@ _SIGNATURES = {
     "snn_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _L, _I, _P],
     "snn_nhwc_to_nchw": [_P, _I, _P, _I, _I, _I, _L, _I, _P],
     "snn_colsum_bf16": [_P, _P, _L, _I, _P],
+    "snn_bilinear_resize": [_I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "snn_nhwc_pad_crop": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "snn_dw3x3_fprop": [_P, _P, _P, _I, _I, _I, _I, _P],
     "snn_dw3x3_dgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
     "snn_dw3x3_wgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
@@ -95,31 +97,53 @@ def ptr(t):
     return t.data_ptr()
 
 
+_call_dev = None   # device of the tensors of the call being prepared (set by require_cuda at the top of every wrapper)
+
+
 def stream_ptr():
-    return torch.cuda.current_stream().cuda_stream
+    """Current stream of the device the call's tensors live on (NOT of torch's current device: the reference does
+    `model.to('cuda:3')` without ever calling set_device, main.py:120-131)."""
+    return torch.cuda.current_stream(_call_dev).cuda_stream
 
 
 profile = None    # when set to a list, every call is bracketed by CUDA events: (name, work, ev_start, ev_end)
 
 
 def call(name, *args, work=None):
-    """Invoke one ABI entry point on the current stream.  `work` = ("flop" | "byte", amount) is the algorithmic
-    work of this launch (used by bench.py's live roofline accounting; ignored otherwise)."""
+    """Invoke one ABI entry point on the stream of the tensors' device.  `work` = ("flop" | "byte", amount) is the
+    algorithmic work of this launch (used by bench.py's live roofline accounting; ignored otherwise)."""
     global launch_count
+    dev = _call_dev
     if profile is not None:
         e0 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-    rc = getattr(lib(), name)(*args)
+        e0.record(torch.cuda.current_stream(dev))
+    fn = getattr(lib(), name)
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):          # kernels launch in the CURRENT context: make it the tensors' device
+            rc = fn(*args)
+    else:
+        rc = fn(*args)
     if rc != 0:
         raise SnnKernelError(f"{name} failed (rc={rc}): {lib().snn_last_error().decode()}")
     launch_count += 1
     if profile is not None:
         e1 = torch.cuda.Event(enable_timing=True)
-        e1.record()
+        e1.record(torch.cuda.current_stream(dev))
         profile.append((name, work, e0, e1))
 
 
 def require_cuda(*tensors):
+    """Every tensor of a call must be a CUDA tensor on ONE device; that device becomes the launch device."""
+    global _call_dev
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise SnnKernelError("snn_object_detectionddp_b200 kernels run on CUDA tensors only (no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise SnnKernelError(f"tensors of one kernel call live on different devices ({dev} vs {t.device})")
+    _call_dev = dev
+    return dev

@@ -1,5 +1,7 @@
 // extern "C" boundary of libsnnb200.so (declared in include/snn_b200.h).
 #include <stdarg.h>
+
+#include <atomic>
 #include <stdio.h>
 
 #include "../../include/snn_b200.h"
@@ -20,13 +22,20 @@ int check_cuda(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return 1;
 }
+int current_device() {
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
 int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
+    static std::atomic<int> cache[64];      // zero-initialised; per device ordinal
+    const int dev = current_device();
+    if (dev >= 0 && dev < 64) {
+        const int c = cache[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
     }
+    int n = 0;
+    if (dev < 0 || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
     return n;
 }
 
@@ -73,6 +82,8 @@ int launch_s2d8(const float*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 int launch_s2d8_u8(const uint8_t*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 int launch_adamw(float*, const float*, float*, float*, __nv_bfloat16*, long long, const float*, const double*, float*,
                  int*, int, cudaStream_t);
+int launch_bilinear(int, const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, int, int, cudaStream_t);
+int launch_pad_crop(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, int, int, cudaStream_t);
 int launch_detect_decode(const float*, const float*, const float*, const float*, int, int, int, int, int, float*, float*,
                          cudaStream_t);
 int launch_detect_loss_fwd(const float*, const float*, const float*, const float*, const float*, const float*, const uint8_t*,
@@ -199,6 +210,12 @@ int snn_space_to_depth8(const float* frames, void* out, int B, int T, int H, int
 }
 int snn_space_to_depth8_u8(const unsigned char* frames, void* out, int B, int T, int H, int W, void* stream) {
     return launch_s2d8_u8(frames, (__nv_bfloat16*)out, B, T, H, W, ST);
+}
+int snn_bilinear_resize(int backward, const void* src, void* dst, int NB, int Hi, int Wi, int Ho, int Wo, int C, void* stream) {
+    return launch_bilinear(backward, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, NB, Hi, Wi, Ho, Wo, C, ST);
+}
+int snn_nhwc_pad_crop(const void* src, void* dst, int NB, int Hs, int Ws, int Hd, int Wd, int C, void* stream) {
+    return launch_pad_crop((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, NB, Hs, Ws, Hd, Wd, C, ST);
 }
 int snn_colsum_bf16(const void* dy, float* acc, long long P, int C, void* stream) {
     return launch_colsum_bf16((const __nv_bfloat16*)dy, acc, P, C, ST);

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #define SNN_DEVINL __device__ __forceinline__
 
 namespace snn {
@@ -28,7 +30,24 @@ int check_cuda(cudaError_t e, const char* what);
         }                                                   \
     } while (0)
 
-int num_sms();
+int num_sms();          // SM count of the CURRENT device (cached per device ordinal)
+int current_device();   // cudaGetDevice, -1 on error
+
+// One-time initialisation PER DEVICE (function attributes such as the dynamic shared-memory limit live in the device's
+// context: a process that touches cuda:3 after cuda:0 must set them again).  Thread-safe; remembers the first error.
+struct PerDeviceOnce {
+    std::mutex m;
+    unsigned long long done = 0;
+    cudaError_t err[64];
+    template <typename F>
+    cudaError_t run(F f) {
+        const int d = current_device();
+        if (d < 0 || d >= 64) return f();
+        std::lock_guard<std::mutex> g(m);
+        if (!((done >> d) & 1ull)) { err[d] = f(); done |= 1ull << d; }
+        return err[d];
+    }
+};
 
 // ------------------------------------------------------------------------------------------
 // shared-memory address / mbarrier

@@ -17,6 +17,7 @@
 //
 // Warp roles (192 threads): warp0 = TMA producer + TMEM owner, warp1 = MMA issuer, warps2-5 =
 // epilogue (one TMEM lane quarter each).
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -58,7 +59,7 @@ struct ConvGemmParams {
                                       // mbarrier round trip) and bytes of one chunk (A 16 KB + this CTA's B slice)
     int nbuf;                         // epilogue staging tiles per warp (2, or 4 for small-K convs: TMA-store latency bound)
     int ksplit;                       // K split over the tap segments (fp32 output, TMA reduce-add): fills the GPU on small-M convs
-    int dbg;                          // timing experiments only: bit 0 = producer skips the TMA loads, bit 1 = no MMA issue
+    int dbg;                          // -DSNN_TIMING_KNOBS builds only: bit 0 = producer skips the TMA loads, bit 1 = no MMA issue
     Phase phase[4];
 };
 
@@ -177,9 +178,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
                     if (lead) {
                         const uint32_t fb = smem_u32(&full_bar[s]);
+#ifdef SNN_TIMING_KNOBS
                         if (p.dbg & 1) {
                             if (rank == 0) mbar_arrive(fb);
-                        } else if (!PAIR) {
+                        } else
+#endif
+                        if (!PAIR) {
                             mbar_expect_tx(fb, (uint32_t)(nsub * p.chunk_bytes));
                             for (int j = 0; j < nsub; ++j) {
                                 const uint32_t c_s = a_s + (uint32_t)(j * p.chunk_bytes);
@@ -221,7 +225,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t a_lo_c = (16u >> 4) << 16;
             const uint32_t b_lo_c = (p.b_mn ? (8192u >> 4) : (16u >> 4)) << 16;
             const uint32_t b_kstep = p.b_mn ? (2048u >> 4) : (32u >> 4);   // 16 K rows of 128 B | 32 B inside the 128 B row
+#ifdef SNN_TIMING_KNOBS
             const uint32_t dbg_nomma = (uint32_t)(p.dbg & 2);
+#else
+            constexpr uint32_t dbg_nomma = 0u;      // the timing-experiment knob is compiled out of the shipped library
+#endif
             int s = 0, lt = 0;
             uint32_t par = 0;
             uint32_t a_s = sbase;
@@ -337,6 +345,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         if (lane == 0) { if (p.nbuf == 4) bulk_wait_group_read<3>(); else bulk_wait_group_read<1>(); }
                         __syncwarp();
                     }
+                    if (p.stats && !valid) {
+                        // a pixel row outside the map (box does not divide Hd x Wd): a 3x3 tap of it may still have read
+                        // in-range input, so its accumulator is not zero -- it must not reach the statistics (the tensor
+                        // store clips it anyway)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = 0u;
+                    }
                     const uint32_t rowaddr = buf + (uint32_t)lane * 128u;
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
@@ -345,7 +360,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     __syncwarp();
                     if (p.stats && mt < m_tiles) {
                         // train-mode BatchNorm statistics of the conv output, fused: lane c sums column c of the staged
-                        // 32 x 32 tile in a fixed row order (deterministic; rows of out-of-range pixels are exact zeros).
+                        // 32 x 32 tile in a fixed row order (deterministic; rows of out-of-range pixels were zeroed above).
                         // The swizzle makes the 32 lanes of every row read 32 distinct banks.
                         float sm = 0.f, sq = 0.f;
                         const uint32_t cadr = buf + (uint32_t)((lane & 3) << 2);
@@ -754,9 +769,21 @@ static void pick_box(int NB, int H, int W, int npix, int* bn, int* bh, int* bw) 
 
 enum { GEOM_3x3_S1 = 0, GEOM_3x3_S2 = 1, GEOM_1x1 = 2, GEOM_T2x2_S2 = 3 };
 
-static int g_debug_flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+// Test knobs (snn_debug_set): plain relaxed atomics, read once per launch on the calling host thread.  Knob 7 (timing
+// experiments with invalid results) only exists in -DSNN_TIMING_KNOBS builds.
+struct DebugFlag {
+    std::atomic<int> v{0};
+    operator int() const { return v.load(std::memory_order_relaxed); }
+};
+static DebugFlag g_debug_flags[8];
 void neuron_debug_set(int k, int v);
-void debug_set(int k, int v) { if (k >= 0 && k < 8) g_debug_flags[k] = v; else if (k >= 8 && k < 12) neuron_debug_set(k - 8, v); }
+void debug_set(int k, int v) {
+#ifndef SNN_TIMING_KNOBS
+    if (k == 7) return;
+#endif
+    if (k >= 0 && k < 8) g_debug_flags[k].v.store(v, std::memory_order_relaxed);
+    else if (k >= 8 && k < 12) neuron_debug_set(k - 8, v);
+}
 
 static int smem_budget() { return 220 * 1024; }
 
@@ -765,14 +792,12 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int wN, int wT, int wK, i
 struct WDesc { const void* ptr; int wN, wT, wK; };
 
 static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const WDesc& wd, ConvGemmParams& p, cudaStream_t st) {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    });
-    SNN_CUDA_OK(attr_err);
+    static PerDeviceOnce once;
+    SNN_CUDA_OK(once.run([] {
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        return e;
+    }));
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     // CTA pairs need an even split of the B tile: K-major rows in multiples of 8 and N % 16 == 0 (cta_group::2),
     // MN-major 64-column boxes; g_debug_flags[6] == 1 forces the single-CTA kernel (tests / A-B timing)
@@ -812,7 +837,11 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     p.stages = stages;
     const size_t smem = (size_t)stages * p.stage_bytes + stage_extra + 1024;
     p.n_blocks = (p.n_store + p.BN - 1) / p.BN;
+#ifdef SNN_TIMING_KNOBS
     p.dbg = g_debug_flags[7];
+#else
+    p.dbg = 0;
+#endif
     CUtensorMap b, o;
     if (make_w_map(&b, wd.ptr, wd.wN, wd.wT, wd.wK, p.b_mn ? 64 : bn_cta)) return 2;
     if (p.tma_out) {
@@ -1023,14 +1052,12 @@ int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long lo
 // ------------------------------------------------------------------------------------------
 int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long ld_x, const void* dy, int Cout,
                long long ld_dy, float* dw, int w_K, int w_coff, cudaStream_t st) {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(wgrad_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(wgrad_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    });
-    SNN_CUDA_OK(attr_err);
+    static PerDeviceOnce once;
+    SNN_CUDA_OK(once.run([] {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        return e;
+    }));
     SNN_REQUIRE(Ci % 8 == 0 && Cout % 8 == 0 && w_K % 4 == 0 && w_coff % 4 == 0, "conv_wgrad: channel counts must be multiples of 8");
     WgradParams p;
     memset(&p, 0, sizeof(p));

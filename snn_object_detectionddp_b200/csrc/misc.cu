@@ -326,3 +326,152 @@ int launch_adamw(float* p, const float* g, float* m, float* v, __nv_bfloat16* sh
 }
 
 }  // namespace snn
+
+namespace snn {
+
+// ------------------------------------------------------------------------------------------
+// Bilinear resize of the skip tensor (reference model.py:43-44: F.interpolate(skip_x, size=x.shape[2:],
+// mode='bilinear', align_corners=False)), NHWC bf16, fp32 arithmetic, one rounding to bf16.
+// Source index / weights exactly as ATen's upsample_bilinear2d (align_corners=False):
+//   src = max(0, scale*(dst+0.5)-0.5), scale = in/out (fp32); i0 = (int)src; i1 = i0 + (i0 < in-1); l1 = src - i0.
+// HBM-bound: 8 channels (16 B) per thread.
+// ------------------------------------------------------------------------------------------
+SNN_DEVINL void bilin_src(int dst, float scale, int in_size, int* i0, int* ip, float* l1) {
+    float s = scale * ((float)dst + 0.5f) - 0.5f;
+    if (s < 0.f) s = 0.f;
+    int i = (int)s;
+    if (i > in_size - 1) i = in_size - 1;
+    *i0 = i;
+    *ip = (i < in_size - 1) ? 1 : 0;
+    *l1 = s - (float)i;
+}
+
+SNN_DEVINL void unpack8(const uint4 v, float* f) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+
+__global__ void __launch_bounds__(256)
+bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int NB, int Hi, int Wi, int Ho, int Wo,
+                    int C, float sh, float sw) {
+    const int c8 = C >> 3;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long total = (long long)NB * Ho * Wo * c8;
+    if (idx >= total) return;
+    const int cg = (int)(idx % c8);
+    const long long pix = idx / c8;
+    const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho);
+    const long long n = pix / ((long long)Wo * Ho);
+    int h0, hp, w0, wp;
+    float lh, lw;
+    bilin_src(oh, sh, Hi, &h0, &hp, &lh);
+    bilin_src(ow, sw, Wi, &w0, &wp, &lw);
+    const float kh0 = 1.f - lh, kw0 = 1.f - lw;
+    const uint4* base = reinterpret_cast<const uint4*>(x + ((n * Hi + h0) * Wi + w0) * C) + cg;
+    const long long rs = (long long)Wi * c8;          // uint4 per input row
+    float a[8], b[8], c[8], d[8];
+    unpack8(__ldg(base), a);
+    unpack8(__ldg(base + (wp ? c8 : 0)), b);
+    unpack8(__ldg(base + (hp ? rs : 0)), c);
+    unpack8(__ldg(base + (hp ? rs : 0) + (wp ? c8 : 0)), d);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = kh0 * (kw0 * a[j] + lw * b[j]) + lh * (kw0 * c[j] + lw * d[j]);
+    uint4 pk;
+    pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]); pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+    *(reinterpret_cast<uint4*>(y + pix * C) + cg) = pk;
+}
+
+// Backward as a deterministic GATHER: input pixel (ih, iw) collects from every output pixel whose 2x2 footprint touches
+// it, with the forward's own weights (no atomics).  For the up-sizing the path needs (out = in + 1) a footprint spans at
+// most 3 output rows / columns; the candidate range is computed conservatively and every candidate re-derives its
+// forward indices.
+__global__ void __launch_bounds__(256)
+bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ gy, __nv_bfloat16* __restrict__ gx, int NB, int Hi, int Wi, int Ho, int Wo,
+                    int C, float sh, float sw) {
+    const int c8 = C >> 3;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long total = (long long)NB * Hi * Wi * c8;
+    if (idx >= total) return;
+    const int cg = (int)(idx % c8);
+    const long long pix = idx / c8;
+    const int iw = (int)(pix % Wi), ih = (int)((pix / Wi) % Hi);
+    const long long n = pix / ((long long)Wi * Hi);
+    // outputs with src in (i-1, i+1): dst in ((i-0.5)/scale - 0.5, (i+1.5)/scale - 0.5); one extra candidate either side
+    int oh_lo = (int)floorf(((float)ih - 0.5f) / sh - 0.5f) - 1, oh_hi = (int)ceilf(((float)ih + 1.5f) / sh - 0.5f) + 1;
+    int ow_lo = (int)floorf(((float)iw - 0.5f) / sw - 0.5f) - 1, ow_hi = (int)ceilf(((float)iw + 1.5f) / sw - 0.5f) + 1;
+    if (ih == 0) oh_lo = 0;                      // clamped sources (src < 0 -> 0) all land on row 0
+    if (iw == 0) ow_lo = 0;
+    if (ih == Hi - 1) oh_hi = Ho - 1;
+    if (iw == Wi - 1) ow_hi = Wo - 1;
+    oh_lo = max(oh_lo, 0); ow_lo = max(ow_lo, 0); oh_hi = min(oh_hi, Ho - 1); ow_hi = min(ow_hi, Wo - 1);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+        int h0, hp; float lh;
+        bilin_src(oh, sh, Hi, &h0, &hp, &lh);
+        if (!(h0 == ih || h0 + hp == ih)) continue;
+        const float wh = (h0 == ih ? 1.f - lh : 0.f) + (h0 + hp == ih ? lh : 0.f);     // hp == 0 (last row): both terms, sum 1
+        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+            int w0, wp; float lw;
+            bilin_src(ow, sw, Wi, &w0, &wp, &lw);
+            if (!(w0 == iw || w0 + wp == iw)) continue;
+            const float ww = (w0 == iw ? 1.f - lw : 0.f) + (w0 + wp == iw ? lw : 0.f);
+            float g[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(gy + ((n * Ho + oh) * Wo + ow) * C) + cg), g);
+            const float k = wh * ww;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(k, g[j], acc[j]);
+        }
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(acc[0], acc[1]); pk.y = pack_bf16x2(acc[2], acc[3]); pk.z = pack_bf16x2(acc[4], acc[5]); pk.w = pack_bf16x2(acc[6], acc[7]);
+    *(reinterpret_cast<uint4*>(gx + pix * C) + cg) = pk;
+}
+
+int launch_bilinear(int backward, const __nv_bfloat16* src, __nv_bfloat16* dst, int NB, int Hi, int Wi, int Ho, int Wo, int C,
+                    cudaStream_t st) {
+    SNN_REQUIRE(C % 8 == 0 && C >= 8, "bilinear: C=%d must be a multiple of 8", C);
+    SNN_REQUIRE(NB >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1, "bilinear: bad sizes");
+    SNN_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "bilinear: pointers must be 16-byte aligned");
+    const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;     // ATen area_pixel_compute_scale (align_corners=False)
+    if (!backward) {
+        const long long total = (long long)NB * Ho * Wo * (C / 8);
+        bilinear_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, NB, Hi, Wi, Ho, Wo, C, sh, sw);
+    } else {
+        const long long total = (long long)NB * Hi * Wi * (C / 8);
+        bilinear_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, NB, Hi, Wi, Ho, Wo, C, sh, sw);
+    }
+    return check_cuda(cudaGetLastError(), "bilinear_kernel");
+}
+
+// ------------------------------------------------------------------------------------------
+// Zero-pad / crop of an NHWC bf16 tensor at the bottom / right: dst[n,h,w,:] = src[n,h,w,:] if (h < Hs && w < Ws) else 0.
+// Used in front of the stride-2 convs when H or W is odd (the 15x20 P5 level of a 480x640 frame): a 3x3 stride-2 pad-1
+// conv over the zero-padded even-sized map equals the conv over the odd-sized one (the extra row/column is the conv's own
+// zero padding), and the crop is the pad's backward.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pad_crop_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int NB, int Hs, int Ws, int Hd, int Wd, int C) {
+    const int c8 = C >> 3;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long total = (long long)NB * Hd * Wd * c8;
+    if (idx >= total) return;
+    const int cg = (int)(idx % c8);
+    const long long pix = idx / c8;
+    const int w = (int)(pix % Wd), h = (int)((pix / Wd) % Hd);
+    const long long n = pix / ((long long)Wd * Hd);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (h < Hs && w < Ws) v = __ldg(reinterpret_cast<const uint4*>(src + ((n * Hs + h) * Ws + w) * C) + cg);
+    *(reinterpret_cast<uint4*>(dst + pix * C) + cg) = v;
+}
+
+int launch_pad_crop(const __nv_bfloat16* src, __nv_bfloat16* dst, int NB, int Hs, int Ws, int Hd, int Wd, int C, cudaStream_t st) {
+    SNN_REQUIRE(C % 8 == 0 && C >= 8, "pad_crop: C=%d must be a multiple of 8", C);
+    SNN_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "pad_crop: pointers must be 16-byte aligned");
+    const long long total = (long long)NB * Hd * Wd * (C / 8);
+    if (total == 0) return 0;
+    pad_crop_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, NB, Hs, Ws, Hd, Wd, C);
+    return check_cuda(cudaGetLastError(), "pad_crop_kernel");
+}
+
+}  // namespace snn

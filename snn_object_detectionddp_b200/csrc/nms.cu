@@ -231,9 +231,10 @@ int launch_nms(const float* pred, int B, int nc, int A, float conf, float iou, i
     p.pred = pred; p.B = B; p.nc = nc; p.A = A; p.conf = conf; p.iou = iou; p.max_wh = max_wh;
     p.multi_label = (multi_label && nc > 1) ? 1 : 0; p.agnostic = agnostic; p.max_det = max_det; p.max_nms = max_nms;
     p.keys = keys; p.cap = cap; p.out = out; p.out_idx = out_idx; p.counts = counts;
-    static cudaError_t attr = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   kNmsSmemKeys * (int)sizeof(unsigned long long));
-    SNN_CUDA_OK(attr);
+    static PerDeviceOnce once;
+    SNN_CUDA_OK(once.run([] {
+        return cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsSmemKeys * (int)sizeof(unsigned long long));
+    }));
     nms_kernel<<<B, kNmsThreads, kNmsSmemKeys * sizeof(unsigned long long), st>>>(p);
     return check_cuda(cudaGetLastError(), "nms_kernel");
 }

@@ -103,6 +103,7 @@ def conv_fprop_stats(geom, x0, w_bf16, cout, T, x1=None):
 def bn_finalize_partials(part, gpt, gamma, beta, running_mean, running_var, num_batches_tracked, counters, T, C, P, eps, momentum):
     """Partials -> (scale, shift, mean, invstd) [T][C] + the T running-statistics updates + num_batches_tracked += T,
     in one launch.  `counters`: persistent zeroed uint32 [ceil(C/8)] (the kernel leaves it zeroed)."""
+    require_cuda(part, gamma, beta, running_mean, running_var, num_batches_tracked, counters)
     dev = part.device
     scale, shift, mean, invstd = (torch.empty((T, C), device=dev, dtype=torch.float32) for _ in range(4))
     sums = torch.empty((T, 2, C), device=dev, dtype=torch.float64)
@@ -174,6 +175,7 @@ def bn_stats(y, T):
 
 
 def bn_finalize(sums, gamma, beta, running_mean, running_var, T, C, P, eps, momentum, training):
+    require_cuda(sums, gamma, beta, running_mean, running_var)
     dev = gamma.device
     n = T if training else 1
     scale, shift, mean, invstd = (torch.empty((n, C), device=dev, dtype=torch.float32) for _ in range(4))
@@ -206,7 +208,7 @@ def bn_act_fwd(act, y, scale, shift, T, v_init=None, want_mask=True, want_v_fina
 def bn_act_bwd(act, training, y, scale, shift, mean, invstd, gs, T, v_init=None, gv_final=None, want_gv_init=False,
                beta=0.5, theta=1.0, alpha=2.0):
     """Returns (gx fp32 | None, dy bf16 | None, gv_init | None, red [T][2][C] | None)."""
-    require_cuda(y, gs)
+    require_cuda(y, scale, shift, mean, invstd, gs, v_init, gv_final)
     c = y.shape[-1]
     p = y.numel() // (T * c)
     dev = y.device
@@ -228,7 +230,7 @@ def bn_act_bwd_train(act, y, scale, shift, mean, invstd, beta_bn, gs, T, dgamma,
                      want_gv_init=False, beta=0.5, theta=1.0, alpha=2.0):
     """Train-mode (batch-statistics) backward of BN -> LIF|SiLU in two recompute passes (no fp32 gx round trip).
     Returns (dy bf16, gv_init | None, red [T][2][C]); dgamma / dbeta (fp32 [C]) are accumulated into."""
-    require_cuda(y, gs)
+    require_cuda(y, scale, shift, mean, invstd, beta_bn, gs, dgamma, dbeta, v_init, gv_final)
     c = y.shape[-1]
     p = y.numel() // (T * c)
     dev = y.device
@@ -246,6 +248,7 @@ def bn_act_bwd_train(act, y, scale, shift, mean, invstd, beta_bn, gs, T, dgamma,
 
 
 def bn_bwd_dx(red, gamma, gx, y, scale, mean, invstd, dgamma, dbeta, T):
+    require_cuda(red, gamma, gx, y, scale, mean, invstd, dgamma, dbeta)
     c = y.shape[-1]
     p = y.numel() // (T * c)
     coef = torch.empty((T, 2, c), device=y.device, dtype=torch.float32)
@@ -259,6 +262,7 @@ def bn_bwd_dx(red, gamma, gx, y, scale, mean, invstd, dgamma, dbeta, T):
 # ConvLSTM gates, layout conversion, optimizer
 # ---------------------------------------------------------------------------------------------
 def lstm_gates_fwd(gates, c_prev, ch, h_bf16_out=None, c_out=None):
+    require_cuda(gates, c_prev, h_bf16_out, c_out)
     p = gates.numel() // (4 * ch)
     shape = gates.shape[:-1] + (ch,)
     c_next = torch.empty(shape, device=gates.device, dtype=torch.float32) if c_out is None else c_out
@@ -270,6 +274,7 @@ def lstm_gates_fwd(gates, c_prev, ch, h_bf16_out=None, c_out=None):
 
 
 def lstm_gates_bwd(gates, c_prev, c_next, dh, dc_in, ch, dgates_out=None):
+    require_cuda(gates, c_prev, c_next, dh, dc_in, dgates_out)
     p = gates.numel() // (4 * ch)
     dgates = torch.empty(gates.shape, device=gates.device, dtype=torch.bfloat16) if dgates_out is None else dgates_out
     assert gates.is_contiguous() and dgates.is_contiguous() and dh.is_contiguous() and dh.dtype == torch.float32
@@ -299,19 +304,57 @@ def nhwc_to_nchw(x):
     return out
 
 
+def bilinear_resize(x, out_hw):
+    """bf16 NHWC [NB,Hi,Wi,C] -> [NB,Ho,Wo,C] (F.interpolate bilinear, align_corners=False; reference model.py:43-44)."""
+    require_cuda(x)
+    nb, hi, wi, c = x.shape
+    ho, wo = out_hw
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    y = torch.empty((nb, ho, wo, c), device=x.device, dtype=torch.bfloat16)
+    call("snn_bilinear_resize", 0, ptr(x), ptr(y), nb, hi, wi, ho, wo, c, stream_ptr(),
+         work=("byte", 2.0 * (x.numel() + y.numel())))
+    return y
+
+
+def bilinear_resize_bwd(gy, in_hw):
+    """Gradient of bilinear_resize w.r.t. its input: gy bf16 [NB,Ho,Wo,C] -> bf16 [NB,Hi,Wi,C]."""
+    require_cuda(gy)
+    nb, ho, wo, c = gy.shape
+    hi, wi = in_hw
+    assert gy.is_contiguous() and gy.dtype == torch.bfloat16
+    gx = torch.empty((nb, hi, wi, c), device=gy.device, dtype=torch.bfloat16)
+    call("snn_bilinear_resize", 1, ptr(gy), ptr(gx), nb, hi, wi, ho, wo, c, stream_ptr(),
+         work=("byte", 2.0 * (gx.numel() + gy.numel())))
+    return gx
+
+
+def pad_crop(x, out_hw):
+    """Bottom/right zero-pad or crop of a contiguous NHWC bf16 tensor to spatial size out_hw."""
+    require_cuda(x)
+    nb, hs, ws, c = x.shape
+    hd, wd = out_hw
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    y = torch.empty((nb, hd, wd, c), device=x.device, dtype=torch.bfloat16)
+    call("snn_nhwc_pad_crop", ptr(x), ptr(y), nb, hs, ws, hd, wd, c, stream_ptr(), work=("byte", 2.0 * (x.numel() + y.numel())))
+    return y
+
+
 def colsum_accumulate(dy, acc):
     """acc[c] (fp32) += sum over all pixels of dy[..., c] (bf16)."""
+    require_cuda(dy, acc)
     c = dy.shape[-1]
     assert dy.is_contiguous() and dy.dtype == torch.bfloat16 and acc.numel() == c and acc.is_contiguous()
     call("snn_colsum_bf16", ptr(dy), ptr(acc), dy.numel() // c, c, stream_ptr())
 
 
 def grad_sumsq(g, acc, zero_first=True):
+    require_cuda(g, acc)
     call("snn_grad_sumsq", ptr(g), g.numel(), ptr(acc), int(zero_first), stream_ptr(), work=("byte", 4.0 * g.numel()))
 
 
 def adamw_step(p, g, m, v, shadow, hp, sumsq, gnorm_out=None, step=None):
     """hp: one row of 8 floats, or (with `step`, a device int32 scalar) the whole [rows, 8] schedule table."""
+    require_cuda(p, g, m, v, shadow, hp, sumsq, gnorm_out, step)
     n_rows = hp.shape[0] if (step is not None and hp.dim() == 2) else 1
     call("snn_adamw_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), p.numel(), ptr(hp), ptr(sumsq), ptr(gnorm_out),
          ptr(step), n_rows, stream_ptr(), work=("byte", (28.0 + (2.0 if shadow is not None else 0.0)) * p.numel()))
@@ -334,6 +377,7 @@ def dw3x3_fprop(x, w9c):
 
 
 def dw3x3_dgrad(dy, w9c, out=None):
+    require_cuda(dy, w9c, out)
     nb, h, w, c = dy.shape
     assert dy.is_contiguous() and dy.dtype == torch.bfloat16
     dx = torch.empty((nb, h, w, c), device=dy.device, dtype=torch.bfloat16) if out is None else out
@@ -343,6 +387,7 @@ def dw3x3_dgrad(dy, w9c, out=None):
 
 
 def dw3x3_wgrad(x, dy, dw9c):
+    require_cuda(x, dy, dw9c)
     nb, h, w, c = x.shape
     assert x.is_contiguous() and dy.is_contiguous() and dw9c.is_contiguous() and dw9c.dtype == torch.float32
     call("snn_dw3x3_wgrad", ptr(x), ptr(dy), ptr(dw9c), nb, h, w, c, stream_ptr())
@@ -377,6 +422,7 @@ def detect_decode(distri, scores, anchors, stride, xywh, want_probs=True):
 
 
 def detect_loss_fwd(distri, scores, anchors, stride, tbox_px, tscores, fg):
+    require_cuda(distri, scores, anchors, stride, tbox_px, tscores, fg)
     b, a, r4 = distri.shape
     sums = torch.empty(3, device=distri.device, dtype=torch.float64)
     for t in (distri, scores, anchors, stride, tbox_px, tscores, fg):
@@ -388,6 +434,7 @@ def detect_loss_fwd(distri, scores, anchors, stride, tbox_px, tscores, fg):
 
 
 def detect_loss_bwd(distri, scores, anchors, stride, tbox_px, tscores, fg, coef):
+    require_cuda(distri, scores, anchors, stride, tbox_px, tscores, fg, coef)
     b, a, r4 = distri.shape
     g_distri, g_scores = torch.empty_like(distri), torch.empty_like(scores)
     assert coef.dtype == torch.float32 and coef.is_contiguous() and coef.numel() == 3

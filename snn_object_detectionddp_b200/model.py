@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import kernels as K
-from .ops import ConvBiasFn, ConvBNActFn, ConvLSTMSeqFn, NeuronCfg
+from .ops import BilinearResizeFn, ConvBiasFn, ConvBNActFn, ConvLSTMSeqFn, NeuronCfg, PadEvenFn
 from .params import store_for
 from ._lib import GEOM_1x1, GEOM_3x3_S1, GEOM_3x3_S2, GEOM_T2x2_S2
 
@@ -92,6 +92,11 @@ class ConvBlock(nn.Module):
         if dead_frames_ok and rc.live_T is not None and self.neuron.kind == "silu" and rc.live_T < rc.T:
             cfg["live_T"] = rc.live_T
             cfg["dead_grad_unread"] = getattr(rc, "dead_grad_unread", False)
+        if self.geom == GEOM_3x3_S2 and ((x0.shape[1] | x0.shape[2]) & 1):
+            # odd H or W (e.g. the 15x20 P5 level of a 480x640 frame): zero-pad to even -- the extra row / column is exactly
+            # the conv's own padding, so Ho = ceil(H/2) and the values equal nn.Conv2d(k3, s2, p1) on the odd-sized map
+            assert x1 is None
+            x0 = PadEvenFn.apply(x0)
         out, v = ConvBNActFn.apply(x0, x1, v_init, self.conv.weight, self.bn.weight, self.bn.bias, cfg)
         if rc.want_mask:
             self.last_mask = cfg.get("last_mask")
@@ -137,9 +142,8 @@ class UpBlock(nn.Module):
         v = v or (None, None)
         up = ConvBiasFn.apply(x, self.up.weight, self.up.bias, dict(store=rc.store, geom=GEOM_T2x2_S2))
         if up.shape[1:3] != skip.shape[1:3]:
-            raise NotImplementedError(
-                "skip/upsample size mismatch (reference model.py:43-44 bilinear branch): input H, W must be multiples "
-                "of 64 for the B200 path")
+            # reference model.py:43-44: F.interpolate(skip_x, size=x.shape[2:], mode='bilinear', align_corners=False)
+            skip = BilinearResizeFn.apply(skip, (up.shape[1], up.shape[2]))
         x, v1 = self.conv1.forward_seq(rc, skip, up, v[0])      # cat([skip_x, x]) order of model.py:45
         x, v2 = self.conv2.forward_seq(rc, x, None, v[1])
         return x, (v1, v2)
@@ -289,13 +293,18 @@ class YOLOFeatureExtractor(nn.Module):
     def forward_seq(self, frames, B, T):
         """frames fp32 [B,T,3,H,W] (or [B,3,H,W] with T=1) contiguous -> (p3, p4, p5) bf16 NHWC [T*B, ...]."""
         H, W = frames.shape[-2:]
-        if H % 64 or W % 64:
-            raise NotImplementedError("B200 path needs H, W multiples of 64 (see UpBlock)")
+        if H % 8 or W % 8:
+            raise ValueError(f"frame size {H}x{W}: H and W must be multiples of 8 (stride-8 patch packer of the stand-in pyramid)")
         x = K.space_to_depth8(frames.contiguous(), B, T)
         act = lambda y: K.bn_act_fwd(K.ACT_SILU, y, self._one, self._zero, 1)[0]
+
+        def even(f):       # odd level size (e.g. 15x20 at 480x640): the zero row / column is the stride-2 conv's own padding
+            h, w = f.shape[1], f.shape[2]
+            return K.pad_crop(f, (h + (h & 1), w + (w & 1))) if ((h | w) & 1) else f
+
         f3 = act(K.conv_fprop(GEOM_1x1, x, self.w_stem, self.WIDTH))
-        f4 = act(K.conv_fprop(GEOM_3x3_S2, f3, self.w_d4, self.WIDTH))
-        f5 = act(K.conv_fprop(GEOM_3x3_S2, f4, self.w_d5, self.WIDTH))
+        f4 = act(K.conv_fprop(GEOM_3x3_S2, even(f3), self.w_d4, self.WIDTH))
+        f5 = act(K.conv_fprop(GEOM_3x3_S2, even(f4), self.w_d5, self.WIDTH))
         bf = torch.bfloat16
         return (K.conv_fprop(GEOM_1x1, f3, self.w_p3, self.OUT, out_dtype=bf),
                 K.conv_fprop(GEOM_1x1, f4, self.w_p4, self.OUT, out_dtype=bf),
@@ -332,9 +341,10 @@ class YOLOTemporalUNet(nn.Module):
         self.skip_dead_backward = True      # see RunCtx.live_T (False: run the all-zero backward of the dead frames too)
 
     # ---- fused sequence path -------------------------------------------------------------
-    def forward_sequence(self, frames, hidden_state=None, return_state=False, all_steps=False):
+    def forward_sequence(self, frames, hidden_state=None, return_state=False, all_steps=False, record=None):
         """frames [B,T,3,H,W] fp32 on the GPU.  Returns (HeadOut of the LAST step as in train.py:64-66, hidden);
-        `hidden` is None unless return_state (final LSTM state + LIF membranes, for streaming inference)."""
+        `hidden` is None unless return_state (final LSTM state + LIF membranes, for streaming inference).
+        `record`: optional dict that receives every ConvBlock's output (spikes) by module name (flip-rate reports)."""
         B, T = frames.shape[0], frames.shape[1]
         st = store_for(self, frames.device)
         st.refresh_operands()
@@ -343,6 +353,7 @@ class YOLOTemporalUNet(nn.Module):
         # the head's inputs are produced by the U-Net output convs, which slice the dead frames' gradient away themselves:
         # head-internal gradients of the dead frames are never read and need no zero fill
         rc.dead_grad_unread = rc.live_T is not None
+        rc.record = record
         outs, new_state = self.temporal_unet.forward_seq(rc, feats, _unpack_hidden(hidden_state))
         det = self.detection_head.forward_seq(rc, outs, B, last_only=not all_steps)
         hidden = _pack_hidden(new_state, self.temporal_unet.neuron.kind) if return_state else None

@@ -49,6 +49,8 @@ class ConvBNActFn(Function):
         cout = weight.shape[0]
         sums = part = None
         gpt = 0
+        if any(ctx.needs_input_grad):
+            st.note_use(weight, *((gamma, beta) if training else ()))
         if geom == K.GEOM_DW3x3:
             y = K.dw3x3_fprop(x0, st.w_master3(weight).view(9, cout))
         elif training:
@@ -157,6 +159,33 @@ class ConvBNActFn(Function):
         return gx0, gx1, gv0, None, None, None, None
 
 
+class BilinearResizeFn(Function):
+    """UpBlock skip resize, reference model.py:43-44 (F.interpolate bilinear, align_corners=False), NHWC bf16."""
+
+    @staticmethod
+    def forward(ctx, x, out_hw):
+        ctx.in_hw = (x.shape[1], x.shape[2])
+        return K.bilinear_resize(x.contiguous(), out_hw)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return K.bilinear_resize_bwd(_bf16c(gy), ctx.in_hw), None
+
+
+class PadEvenFn(Function):
+    """Bottom/right zero-pad to even H, W in front of a stride-2 conv (the pad row/column is the conv's own padding)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        h, w = x.shape[1], x.shape[2]
+        ctx.in_hw = (h, w)
+        return K.pad_crop(x.contiguous(), (h + (h & 1), w + (w & 1)))
+
+    @staticmethod
+    def backward(ctx, gy):
+        return K.pad_crop(_bf16c(gy), ctx.in_hw)
+
+
 class ConvBiasFn(Function):
     """Plain conv with bias: out_p3/4/5 1x1 convs (model.py:119,146) and UpBlock.up (model.py:36,42)."""
 
@@ -164,6 +193,8 @@ class ConvBiasFn(Function):
     def forward(ctx, x0, weight, bias, cfg):
         st, geom = cfg["store"], cfg["geom"]
         cout = weight.shape[1] if geom == GEOM_T2x2_S2 else weight.shape[0]
+        if any(ctx.needs_input_grad):
+            st.note_use(weight, bias)
         out = K.conv_fprop(geom, x0, st.w_fprop(weight), cout, bias=bias, out_dtype=cfg.get("out_dtype", torch.bfloat16))
         ctx.cfg = cfg
         ctx.save_for_backward(x0, weight, bias)
@@ -212,6 +243,8 @@ class ConvLSTMSeqFn(Function):
         nb, hh, ww, cx = x.shape
         B = nb // T
         w = st.w_fprop(weight)
+        if any(ctx.needs_input_grad):
+            st.note_use(weight, bias)
         gates = K.conv_fprop(GEOM_3x3_S1, x, w, 4 * ch, bias=bias, w_coff=0)
         h_all = torch.empty((nb, hh, ww, ch), device=x.device, dtype=torch.bfloat16)
         c_all = torch.empty((nb, hh, ww, ch), device=x.device, dtype=torch.float32)

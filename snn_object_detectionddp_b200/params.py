@@ -27,7 +27,7 @@ def _kind_of(module, pname):
 
 
 class Entry:
-    __slots__ = ("name", "param", "kind", "offset", "numel", "shape3", "ready_epoch")
+    __slots__ = ("name", "param", "kind", "offset", "numel", "shape3", "ready_epoch", "pending")
 
     def __init__(self, name, param, kind, offset):
         self.name, self.param, self.kind, self.offset = name, param, kind, offset
@@ -42,6 +42,7 @@ class Entry:
         else:
             self.shape3 = None
         self.ready_epoch = -1
+        self.pending = 0        # forward uses of this tensor whose backward has not run yet (see ParamStore.note_use)
 
     def logical_view(self, flat):
         """View of flat[offset:offset+numel] with the parameter's logical shape (strided)."""
@@ -142,6 +143,7 @@ class ParamStore:
         self.grad_epoch += 1
         for e in self.entries:
             e.param.grad = e.logical_view(self.flat_g)
+            e.pending = 0
 
     def grad_view(self, p, three_d=False):
         """Gradient slice to accumulate into (PyTorch semantics: a `None` grad means start from zero)."""
@@ -155,9 +157,21 @@ class ParamStore:
             p.grad = ours
         return e.view3(self.flat_g) if three_d else ours
 
+    def note_use(self, *params):
+        """Called by the forward of every autograd op for the parameters it reads: the reference-style per-frame loop
+        (`model(frame, hidden)` T times, train.py:62-66) uses each parameter T times, and its gradient is final only
+        after the LAST of the T backward calls -- a bucket must not be all-reduced before that.  (Callers check
+        ctx.needs_input_grad: grad mode is always off inside Function.forward.)"""
+        for p in params:
+            if p is not None and p.requires_grad:
+                self.by_param[id(p)].pending += 1
+
     def grad_done(self, p):
-        if self.grad_ready_hook is not None:
-            self.grad_ready_hook(self.by_param[id(p)])
+        e = self.by_param[id(p)]
+        if e.pending > 0:
+            e.pending -= 1
+        if e.pending == 0 and self.grad_ready_hook is not None:
+            self.grad_ready_hook(e)
 
 
 def store_for(root, device):
