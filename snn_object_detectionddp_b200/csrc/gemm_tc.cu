@@ -888,9 +888,12 @@ static int pick_bn(int n_store) {
     return best;
 }
 
-static void set_domain(ConvGemmParams& p, int NB, int Hd, int Wd) {
+// nb_for_box: the image count the pixel box is chosen for.  Convs with fused BatchNorm statistics pass B (frames per
+// timestep) instead of NB = T*B: the 32-pixel partial-sum groups then cover the same pixels however many timesteps are
+// folded into the launch, so the fused T-step sequence and T per-frame calls give bit-identical statistics.
+static void set_domain(ConvGemmParams& p, int NB, int Hd, int Wd, int nb_for_box = 0) {
     p.NB = NB; p.Hd = Hd; p.Wd = Wd;
-    pick_box(NB, Hd, Wd, 128, &p.bn, &p.bh, &p.bw);
+    pick_box(nb_for_box > 0 ? nb_for_box : NB, Hd, Wd, 128, &p.bn, &p.bh, &p.bw);
     p.tiles_w = (Wd + p.bw - 1) / p.bw; p.tiles_h = (Hd + p.bh - 1) / p.bh; p.tiles_n = (NB + p.bn - 1) / p.bn;
 }
 
@@ -914,7 +917,7 @@ long long conv_stats_groups(int geom, int NB, int H, int W, int B, int* groups_p
     int Hd = H, Wd = W;
     if (geom == GEOM_3x3_S2) { Hd = H / 2; Wd = W / 2; }
     ConvGemmParams p;
-    set_domain(p, NB, Hd, Wd);
+    set_domain(p, NB, Hd, Wd, B);
     if (p.bn > 1 && B % p.bn != 0) return 0;
     const int tiles_hw = p.tiles_w * p.tiles_h;
     if (groups_per_t) *groups_per_t = 4 * (B / p.bn) * tiles_hw;
@@ -937,7 +940,7 @@ int conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long long
     p.os = 1; p.Ho = H; p.Wo = W;
     if (geom == GEOM_3x3_S2) { Hd = H / 2; Wd = W / 2; p.Ho = Hd; p.Wo = Wd; }
     if (geom == GEOM_T2x2_S2) { p.os = 2; p.Ho = 2 * H; p.Wo = 2 * W; }
-    set_domain(p, NB, Hd, Wd);
+    set_domain(p, NB, Hd, Wd, stats ? frames_per_step : 0);
     p.BN = pick_bn(Cout);
     p.n_store = Cout; p.wn_off = w_row_off;
     p.out = out; p.bias = bias; p.out_f32 = out_f32; p.accumulate = accumulate; p.out_ld = out_ld; p.out_coff = out_coff;

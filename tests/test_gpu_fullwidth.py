@@ -41,6 +41,15 @@ def _oracle(neuron, seed=0):
     return orc
 
 
+def _share_frozen_extractor(orc, net):
+    """Both sides read the SAME frozen features.  The extractor is a frozen, gradient-free stand-in (the reference's
+    pretrained YOLO11m cannot exist offline) whose own parity is tested separately
+    (test_feature_extractor_standin_matches_oracle, 4e-3); its bf16 output roundings occasionally differ from the fp32
+    restatement by one bf16 ulp, and a spiking net amplifies every such ulp into a cascade of flips -- that would test the
+    stand-in, not the path.  Product features: bf16 NHWC -> fp32 NCHW, exactly the values the product's U-Net consumes."""
+    orc.feature_extractor = net.feature_extractor
+
+
 def _sync_state(src, dst):
     """Copy trainer `src`'s whole training state into `dst` IN PLACE (a captured graph holds the addresses)."""
     for name in ("flat_p", "flat_m", "flat_v", "shadow", "flat_g"):
@@ -95,7 +104,8 @@ def _flip_report(name, s_prod, s_orc, u_orc, theta=1.0):
 def test_full_width_training_step_vs_oracle(neuron, B, T, HW):
     """BASELINE.json configs[1] / configs[2] at full width, one GPU, two optimizer steps.
 
-    silu (the reference's own network): loss items 2e-2, gradient norm 5e-2 -- bf16 activations 23 layers deep.
+    silu (the reference's own network): loss items 2e-3, gradient norm 5e-3 (measured 2.4e-4 / 5e-4 at B=64: large
+    BatchNorm groups average the bf16 rounding noise of the 23 layers).
     lif (build-defined): the 9 spiking layers in front of the ConvLSTM must agree with the oracle spike for spike except
     neurons whose oracle membrane is within 1e-5 of threshold (flip-rate protocol); behind the ConvLSTM, ulp-level
     differences of the fp32 hidden state move bf16 operand roundings and spikes drift -- rates are reported; loss items 0.1."""
@@ -104,12 +114,13 @@ def test_full_width_training_step_vs_oracle(neuron, B, T, HW):
     orc = _oracle(neuron, seed=5)
     net = _product(neuron, state=orc.state_dict())
     orc = orc.to(DEV).train()
+    _share_frozen_extractor(orc, net)
     frames, labels = MO.synthetic_batch(B, T, HW, HW, seed=21)
     frames, labels = frames.to(DEV), labels.to(DEV)
     loss_fn, opt, sched = MO.make_reference_trainer(orc, total_steps=20)
     tr = Trainer(net, total_steps=20, device=DEV)
     batch = {"batch_idx": labels[:, 0], "cls": labels[:, 1], "bboxes": labels[:, 2:]}
-    tol_loss, tol_gn = (2e-2, 5e-2) if neuron == "silu" else (0.1, 0.25)
+    tol_loss, tol_gn = (2e-3, 5e-3) if neuron == "silu" else (0.1, 0.25)
     if neuron == "lif":
         # spike flip report of the first forward (same parameters on both sides)
         names = {m: n for n, m in orc.temporal_unet.named_modules() if isinstance(m, O.OracleConvBlock)}
@@ -164,6 +175,7 @@ def test_native_480x640_frames_through_the_skip_resize_branch(neuron):
     orc = _oracle(neuron, seed=9)
     net = _product(neuron, state=orc.state_dict())
     orc = orc.to(DEV).train()
+    _share_frozen_extractor(orc, net)
     net.train()
     B, T = 2, 2
     g = torch.Generator().manual_seed(33)
