@@ -120,8 +120,10 @@ int snn_bn_bwd_dx(const float* red, const float* gamma, const float* gx, const f
 /* ---- ConvLSTM gate math (model.py:67-69): gates fp32 [P][4*Ch] in i|f|g|o order ---- */
 int snn_lstm_gates_fwd(const float* gates, const float* c_prev, float* c_next, float* h_next,
                        void* h_bf16, long long P, int Ch, void* stream);
+/* backward of one step: total dL/dh_t = dh (fp32, recurrent part from step t+1's W_h dgrad; may be NULL) + dh_bf16 (bf16, the
+ * consumer's part from bottleneck_conv's dgrad; may be NULL), summed inside the kernel */
 int snn_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_next,
-                       const float* dh, const float* dc_in, void* dgates_bf16, float* dc_prev,
+                       const float* dh, const void* dh_bf16, const float* dc_in, void* dgates_bf16, float* dc_prev,
                        long long P, int Ch, void* stream);
 
 /* ---- layout conversion at the nn.Module boundary (reference tensors are NCHW fp32) ---- */
@@ -160,10 +162,12 @@ int snn_colsum_bf16(const void* dy_bf16, float* acc, long long P, int C, void* s
 /* ---- optimizer: replaces clip_grad_norm_(10) + AdamW.step + OneCycleLR.step (train.py:77-80) over one flat buffer.
  *      hp (device) = rows of 8 floats {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, max_norm};
  *      step_ptr == NULL: row 0 is used; else row min(*step_ptr, n_rows-1) is used and *step_ptr is incremented
- *      afterwards (device-side schedule: no host sync, CUDA-graph replayable). ---- */
+ *      afterwards (device-side schedule: no host sync, CUDA-graph replayable).
+ *      zero_grad != 0: g is left zeroed (optimizer.zero_grad() of train.py:61 folded into the pass that consumes g). ---- */
 int snn_grad_sumsq(const float* g, long long n, double* acc, int zero_first, void* stream);
-int snn_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
-                   const float* hp, const double* sumsq, float* gnorm_out, int* step_ptr, int n_rows, void* stream);
+int snn_adamw_step(float* p, float* g, float* m, float* v, void* shadow_bf16, long long n,
+                   const float* hp, const double* sumsq, float* gnorm_out, int* step_ptr, int n_rows, int zero_grad,
+                   void* stream);
 
 /* ---- Detect decode (ultralytics Detect._inference, reached through model.py:209 in eval mode, and
  *      v8DetectionLoss.bbox_decode): boxes fp32 [N][4] in pixels (xywh != 0: cx,cy,w,h; else x1,y1,x2,y2) and
@@ -196,6 +200,36 @@ int snn_detect_loss_fwd(const float* distri, const float* scores, const float* a
 int snn_detect_loss_bwd(const float* distri, const float* scores, const float* anchors, const float* stride,
                         const float* tbox_px, const float* tscores, const uint8_t* fg, int B, int A, int nc, int reg_max,
                         const float* coef, float* g_distri, float* g_scores, void* stream);
+
+/* ---- whole v8DetectionLoss forward (train.py:74) in 5 launches, no host synchronisation, no ATen:
+ *      decode (DFL expectation -> xyxy pixels, sigmoid scores) -> TaskAlignedAssigner (top-k 10, alpha 0.5, beta 6:
+ *      per-(gt, anchor) CIoU / alignment metric, top-k candidates per gt with ties to the lower anchor index, anchors claimed
+ *      by several gts keep the largest overlap, normalised target scores) -> fused BCE + CIoU + DFL sums -> finalisation by
+ *      the last block: out6 = {loss*B [3], loss [3]} (what `loss_fn(preds, batch)` returns at train.py:74, hyp gains of
+ *      config.yaml:33-37 applied, normalised by max(sum target scores, 1)), coef3 = d(sum(loss*B))/d sums.
+ *      Predictions are read through a ROW MAP: nl > 0 = the Detect head's SCALE-MAJOR buffers (scale i = rows
+ *      [B*a_off[i], B*a_off[i+1]), image-major inside; a_off = nl+1 host ints, a_off[nl] = A) so that no torch.cat is needed;
+ *      nl = 0 = natural [B][A] rows.  Labels are the dense padding of the collate layout (train.py:27-37):
+ *      gt_cls int64 [B][M], gt_box fp32 [B][M][4] normalised (cx,cy,w,h), gt_valid uint8 [B][M]; (img_w, img_h) = stride-8 map
+ *      size * 8.  Caller-owned scratch: workspace of snn_tal_workspace_bytes(B,A,M) bytes, pboxes [B][A][4], probs [B][A][nc],
+ *      tbox_px [B][A][4], tscores [B][A][nc], fg [B][A] (targets, natural layout, kept for the backward), sums double[3],
+ *      counter uint32[1] (zero-initialised once; left zeroed), gains device float[3] = {box, cls, dfl}. ---- */
+long long snn_tal_workspace_bytes(int B, int A, int M);
+int snn_detect_assign_loss_fwd(const float* distri, const float* scores, int nl, const int* a_off, const float* anchors,
+                               const float* stride, const long long* gt_cls, const float* gt_box, const unsigned char* gt_valid,
+                               float img_w, float img_h, int B, int A, int M, int nc, int reg_max, int topk, const float* gains,
+                               void* workspace, float* pboxes, float* probs, float* tbox_px, float* tscores, unsigned char* fg,
+                               double* sums, unsigned int* counter, float* out6, float* coef3, void* stream);
+/* the assigner alone (inputs: sigmoid scores and xyxy-pixel boxes in natural [B][A] layout) */
+int snn_tal_assign(const float* probs, const float* pboxes, const float* anchors, const float* stride, const long long* gt_cls,
+                   const float* gt_box, const unsigned char* gt_valid, float img_w, float img_h, int B, int A, int M, int nc, int topk,
+                   void* workspace, float* tbox_px, float* tscores, unsigned char* fg, void* stream);
+/* backward of the fused loss: gradients at the prediction rows (row map as above), fp32 or bf16 (out_is_bf16: they are the
+ * `dy` operands of the head's closing 1x1 convs); gout3 (device float[3], may be NULL = ones) = upstream gradient of loss*B. */
+int snn_detect_loss_bwd_rows(const float* distri, const float* scores, int nl, const int* a_off, const float* anchors,
+                             const float* stride, const float* tbox_px, const float* tscores, const unsigned char* fg, int B, int A,
+                             int nc, int reg_max, const float* coef3, const float* gout3, void* g_distri, void* g_scores,
+                             int out_is_bf16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,7 @@ _SIGNATURES = {
     "snn_bn_act_bwd2": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _P],
     "snn_bn_bwd_dx": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "snn_lstm_gates_fwd": [_P, _P, _P, _P, _P, _L, _I, _P],
-    "snn_lstm_gates_bwd": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
+    "snn_lstm_gates_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
     "snn_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _L, _I, _P],
     "snn_nhwc_to_nchw": [_P, _I, _P, _I, _I, _I, _L, _I, _P],
     "snn_colsum_bf16": [_P, _P, _L, _I, _P],
@@ -46,9 +46,13 @@ _SIGNATURES = {
     "snn_detect_decode": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "snn_detect_loss_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     "snn_detect_loss_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "snn_detect_assign_loss_fwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P,
+                                   _P, _P, _P, _P],
+    "snn_tal_assign": [_P, _P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "snn_detect_loss_bwd_rows": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P],
     "snn_nms": [_P, _I, _I, _I, _F, _F, _I, _I, _I, _I, _F, _P, _L, _P, _P, _P, _P],
     "snn_grad_sumsq": [_P, _L, _P, _I, _P],
-    "snn_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _I, _P],
+    "snn_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _I, _I, _P],
 }
 
 _lib = None
@@ -60,7 +64,8 @@ class SnnKernelError(RuntimeError):
 
 
 def exported_symbols():
-    return sorted(list(_SIGNATURES) + ["snn_last_error", "snn_version", "snn_debug_set", "snn_conv_stats_groups", "snn_bn_stats_workspace_floats", "snn_nms_workspace_keys"])
+    return sorted(list(_SIGNATURES) + ["snn_last_error", "snn_version", "snn_debug_set", "snn_conv_stats_groups", "snn_bn_stats_workspace_floats", "snn_nms_workspace_keys",
+                                             "snn_tal_workspace_bytes"])
 
 
 def lib():
@@ -84,6 +89,8 @@ def lib():
         L.snn_bn_stats_workspace_floats.restype = _L
         L.snn_nms_workspace_keys.argtypes = [_I, _I, _I]
         L.snn_nms_workspace_keys.restype = _L
+        L.snn_tal_workspace_bytes.argtypes = [_I, _I, _I]
+        L.snn_tal_workspace_bytes.restype = _L
         L.snn_debug_set.argtypes = [_I, _I]
         L.snn_debug_set.restype = None
         _lib = L

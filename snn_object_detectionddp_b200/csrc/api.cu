@@ -69,8 +69,8 @@ int launch_bn_act_bwd2(int, int, const float*, const float*, const float*, const
 int launch_bn_bwd_dx(const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*,
                      float*, float*, __nv_bfloat16*, int, int, int, cudaStream_t);
 int launch_lstm_gates_fwd(const float*, const float*, float*, float*, __nv_bfloat16*, long long, int, cudaStream_t);
-int launch_lstm_gates_bwd(const float*, const float*, const float*, const float*, const float*, __nv_bfloat16*, float*,
-                          long long, int, cudaStream_t);
+int launch_lstm_gates_bwd(const float*, const float*, const float*, const float*, const __nv_bfloat16*, const float*, __nv_bfloat16*,
+                          float*, long long, int, cudaStream_t);
 int launch_nchw_to_nhwc(const float*, void*, int, int, int, int, long long, int, cudaStream_t);
 int launch_nhwc_to_nchw(const void*, int, float*, int, int, int, long long, int, cudaStream_t);
 int launch_sumsq(const float*, long long, double*, int, cudaStream_t);
@@ -80,16 +80,20 @@ int launch_dw3x3_dgrad(const __nv_bfloat16*, const float*, __nv_bfloat16*, int, 
 int launch_dw3x3_wgrad(const __nv_bfloat16*, const __nv_bfloat16*, float*, int, int, int, int, cudaStream_t);
 int launch_s2d8(const float*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 int launch_s2d8_u8(const uint8_t*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
-int launch_adamw(float*, const float*, float*, float*, __nv_bfloat16*, long long, const float*, const double*, float*,
-                 int*, int, cudaStream_t);
+int launch_adamw(float*, float*, float*, float*, __nv_bfloat16*, long long, const float*, const double*, float*,
+                 int*, int, int, cudaStream_t);
 int launch_bilinear(int, const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, int, int, cudaStream_t);
 int launch_pad_crop(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, int, int, cudaStream_t);
-int launch_detect_decode(const float*, const float*, const float*, const float*, int, int, int, int, int, float*, float*,
-                         cudaStream_t);
+int launch_detect_decode(const float*, const float*, const float*, const float*, int, int, int, int, int, float*, float*, int,
+                         const int*, cudaStream_t);
 int launch_detect_loss_fwd(const float*, const float*, const float*, const float*, const float*, const float*, const uint8_t*,
-                           int, int, int, int, double*, cudaStream_t);
+                           int, int, int, int, double*, int, const int*, const float*, int, const float*, unsigned int*, float*,
+                           float*, cudaStream_t);
 int launch_detect_loss_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const uint8_t*,
-                           int, int, int, int, const float*, float*, float*, cudaStream_t);
+                           int, int, int, int, const float*, const float*, void*, void*, int, int, const int*, cudaStream_t);
+long long tal_workspace_bytes(int, int, int);
+int launch_tal_assign(const float*, const float*, const float*, const float*, const long long*, const float*, const uint8_t*, float,
+                      float, int, int, int, int, int, void*, float*, float*, uint8_t*, float**, int*, cudaStream_t);
 
 }  // namespace snn
 
@@ -184,9 +188,9 @@ int snn_lstm_gates_fwd(const float* gates, const float* c_prev, float* c_next, f
                        int Ch, void* stream) {
     return launch_lstm_gates_fwd(gates, c_prev, c_next, h_next, (__nv_bfloat16*)h_bf16, P, Ch, ST);
 }
-int snn_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_next, const float* dh, const float* dc_in,
-                       void* dgates, float* dc_prev, long long P, int Ch, void* stream) {
-    return launch_lstm_gates_bwd(gates, c_prev, c_next, dh, dc_in, (__nv_bfloat16*)dgates, dc_prev, P, Ch, ST);
+int snn_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_next, const float* dh, const void* dh_bf16,
+                       const float* dc_in, void* dgates, float* dc_prev, long long P, int Ch, void* stream) {
+    return launch_lstm_gates_bwd(gates, c_prev, c_next, dh, (const __nv_bfloat16*)dh_bf16, dc_in, (__nv_bfloat16*)dgates, dc_prev, P, Ch, ST);
 }
 int snn_nchw_to_nhwc(const float* in, void* out, int out_is_bf16, int NB, int C, int HW, long long out_ld, int out_coff,
                      void* stream) {
@@ -223,24 +227,54 @@ int snn_colsum_bf16(const void* dy, float* acc, long long P, int C, void* stream
 int snn_grad_sumsq(const float* g, long long n, double* acc, int zero_first, void* stream) {
     return launch_sumsq(g, n, acc, zero_first, ST);
 }
-int snn_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, long long n, const float* hp,
-                   const double* sumsq, float* gnorm_out, int* step_ptr, int n_rows, void* stream) {
-    return launch_adamw(p, g, m, v, (__nv_bfloat16*)shadow, n, hp, sumsq, gnorm_out, step_ptr, n_rows, ST);
+int snn_adamw_step(float* p, float* g, float* m, float* v, void* shadow, long long n, const float* hp,
+                   const double* sumsq, float* gnorm_out, int* step_ptr, int n_rows, int zero_grad, void* stream) {
+    return launch_adamw(p, g, m, v, (__nv_bfloat16*)shadow, n, hp, sumsq, gnorm_out, step_ptr, n_rows, zero_grad, ST);
 }
 int snn_detect_decode(const float* distri, const float* scores, const float* anchors, const float* stride, int B, int A,
                       int nc, int reg_max, int xywh, float* boxes, float* probs, void* stream) {
-    return launch_detect_decode(distri, scores, anchors, stride, B, A, nc, reg_max, xywh, boxes, probs, ST);
+    return launch_detect_decode(distri, scores, anchors, stride, B, A, nc, reg_max, xywh, boxes, probs, 0, nullptr, ST);
 }
 int snn_detect_loss_fwd(const float* distri, const float* scores, const float* anchors, const float* stride,
                         const float* tbox_px, const float* tscores, const uint8_t* fg, int B, int A, int nc, int reg_max,
                         double* sums, void* stream) {
-    return launch_detect_loss_fwd(distri, scores, anchors, stride, tbox_px, tscores, fg, B, A, nc, reg_max, sums, ST);
+    return launch_detect_loss_fwd(distri, scores, anchors, stride, tbox_px, tscores, fg, B, A, nc, reg_max, sums, 0, nullptr, nullptr, 0,
+                                  nullptr, nullptr, nullptr, nullptr, ST);
 }
 int snn_detect_loss_bwd(const float* distri, const float* scores, const float* anchors, const float* stride,
                         const float* tbox_px, const float* tscores, const uint8_t* fg, int B, int A, int nc, int reg_max,
                         const float* coef, float* g_distri, float* g_scores, void* stream) {
-    return launch_detect_loss_bwd(distri, scores, anchors, stride, tbox_px, tscores, fg, B, A, nc, reg_max, coef, g_distri,
-                                  g_scores, ST);
+    return launch_detect_loss_bwd(distri, scores, anchors, stride, tbox_px, tscores, fg, B, A, nc, reg_max, coef, nullptr, g_distri,
+                                  g_scores, 0, 0, nullptr, ST);
+}
+long long snn_tal_workspace_bytes(int B, int A, int M) { return tal_workspace_bytes(B, A, M); }
+int snn_detect_assign_loss_fwd(const float* distri, const float* scores, int nl, const int* a_off, const float* anchors,
+                               const float* stride, const long long* gt_cls, const float* gt_box, const unsigned char* gt_valid,
+                               float img_w, float img_h, int B, int A, int M, int nc, int reg_max, int topk, const float* gains,
+                               void* workspace, float* pboxes, float* probs, float* tbox_px, float* tscores, unsigned char* fg,
+                               double* sums, unsigned int* counter, float* out6, float* coef3, void* stream) {
+    int rc = launch_detect_decode(distri, scores, anchors, stride, B, A, nc, reg_max, 0, pboxes, probs, nl, a_off, ST);
+    if (rc) return rc;
+    float* tss_part = nullptr;
+    int n_parts = 0;
+    rc = launch_tal_assign(probs, pboxes, anchors, stride, gt_cls, gt_box, gt_valid, img_w, img_h, B, A, M, nc, topk, workspace, tbox_px,
+                           tscores, fg, &tss_part, &n_parts, ST);
+    if (rc) return rc;
+    return launch_detect_loss_fwd(distri, scores, anchors, stride, tbox_px, tscores, fg, B, A, nc, reg_max, sums, nl, a_off, tss_part,
+                                  n_parts, gains, counter, out6, coef3, ST);
+}
+int snn_tal_assign(const float* probs, const float* pboxes, const float* anchors, const float* stride, const long long* gt_cls,
+                   const float* gt_box, const unsigned char* gt_valid, float img_w, float img_h, int B, int A, int M, int nc, int topk,
+                   void* workspace, float* tbox_px, float* tscores, unsigned char* fg, void* stream) {
+    return launch_tal_assign(probs, pboxes, anchors, stride, gt_cls, gt_box, gt_valid, img_w, img_h, B, A, M, nc, topk, workspace, tbox_px,
+                             tscores, fg, nullptr, nullptr, ST);
+}
+int snn_detect_loss_bwd_rows(const float* distri, const float* scores, int nl, const int* a_off, const float* anchors,
+                             const float* stride, const float* tbox_px, const float* tscores, const unsigned char* fg, int B, int A,
+                             int nc, int reg_max, const float* coef3, const float* gout3, void* g_distri, void* g_scores,
+                             int out_is_bf16, void* stream) {
+    return launch_detect_loss_bwd(distri, scores, anchors, stride, tbox_px, tscores, fg, B, A, nc, reg_max, coef3, gout3, g_distri,
+                                  g_scores, out_is_bf16, nl, a_off, ST);
 }
 
 }  // extern "C"

@@ -50,6 +50,24 @@ struct PerDeviceOnce {
 };
 
 // ------------------------------------------------------------------------------------------
+// Row map of the Detect head's prediction buffers.  The head writes its scales into SCALE-MAJOR buffers (scale i occupies
+// rows [B*a_off_i, B*a_off_{i+1}), image-major inside), so no torch.cat ever runs; nl == 0 = natural [B, A] layout.
+// ------------------------------------------------------------------------------------------
+struct RowMap {
+    int nl;
+    int a_off[5];      // first anchor of scale i (a_off[nl] = A)
+    int B;
+};
+__device__ __forceinline__ long long pred_row(const RowMap& rm, int b, int a, int A) {
+    if (rm.nl == 0) return (long long)b * A + a;
+    int i = 0;
+    while (i + 1 < rm.nl && a >= rm.a_off[i + 1]) ++i;
+    const int hw = rm.a_off[i + 1] - rm.a_off[i];
+    return (long long)rm.B * rm.a_off[i] + (long long)b * hw + (a - rm.a_off[i]);
+}
+int make_rowmap(RowMap* rm, int nl, const int* a_off, int B, int A);
+
+// ------------------------------------------------------------------------------------------
 // shared-memory address / mbarrier
 // ------------------------------------------------------------------------------------------
 SNN_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

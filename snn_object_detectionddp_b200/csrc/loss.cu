@@ -85,9 +85,10 @@ struct AnchorTerms {
 };
 
 // returns false for background anchors
+// n = natural index b*A + a of the targets, r = row of the prediction buffers (RowMap)
 SNN_DEVINL bool anchor_terms(const float* __restrict__ distri, const float* __restrict__ tscores,
                              const float* __restrict__ tbox_px, const float* __restrict__ anchors,
-                             const float* __restrict__ stride, const uint8_t* __restrict__ fg, long long n, int a, int nc,
+                             const float* __restrict__ stride, const uint8_t* __restrict__ fg, long long n, long long r, int a, int nc,
                              AnchorTerms& o) {
     if (!fg[n]) return false;
     float wsum = 0.f;
@@ -98,7 +99,7 @@ SNN_DEVINL bool anchor_terms(const float* __restrict__ distri, const float* __re
     for (int k = 0; k < 4; ++k) tb[k] = tbox_px[n * 4 + k] * inv_s;  // target_bboxes /= stride_tensor
     float lse[4];
     for (int k = 0; k < 4; ++k) {
-        const float4* lp = reinterpret_cast<const float4*>(distri + n * (4 * kRegMax) + k * kRegMax);
+        const float4* lp = reinterpret_cast<const float4*>(distri + r * (4 * kRegMax) + k * kRegMax);
         float l[kRegMax];
 #pragma unroll
         for (int j = 0; j < kRegMax / 4; ++j) {
@@ -152,20 +153,38 @@ SNN_DEVINL float block_sum(float v, float* sh) {
     return t;  // valid in thread 0
 }
 
+// Finalisation data of the fused path (NULL tss_part = legacy: raw sums only).  The LAST block to finish (atomic ticket;
+// the result does not depend on which block that is) turns the three sums into the loss the reference returns
+// (train.py:74: `loss * B` and `loss.detach()`), normalised by max(sum of target scores, 1) and weighted by hyp.box/cls/dfl
+// (config.yaml:33-37), and leaves the backward coefficients d(sum_k loss_k * B)/d(sum_k) = gain_k * B / tss.
+struct LossFinal {
+    const float* tss_part;     // per-block partial sums of the target scores (tal_targets_kernel), fixed-order total
+    int n_parts;
+    const float* gains;        // device [3]
+    unsigned int* counter;     // zeroed; left zeroed
+    float* out6;               // loss*B [3], loss [3]
+    float* coef3;
+    float batch;
+};
+
 __global__ void __launch_bounds__(128)
 detect_loss_fwd_kernel(const float* __restrict__ distri, const float* __restrict__ scores, const float* __restrict__ anchors,
                        const float* __restrict__ stride, const float* __restrict__ tbox_px, const float* __restrict__ tscores,
-                       const uint8_t* __restrict__ fg, long long N, int A, int nc, double* __restrict__ sums) {
+                       const uint8_t* __restrict__ fg, long long N, int A, int nc, double* __restrict__ sums, const RowMap rm,
+                       const LossFinal fin) {
     __shared__ float sh[4];
+    __shared__ unsigned int s_ticket;
     const long long n = (long long)blockIdx.x * 128 + threadIdx.x;
     float box = 0.f, dfl = 0.f, cls = 0.f;
     if (n < N) {
+        const int a = (int)(n % A);
+        const long long r = pred_row(rm, (int)(n / A), a, A);
         for (int c = 0; c < nc; ++c) {
-            const float x = scores[n * nc + c], t = tscores[n * nc + c];
+            const float x = scores[r * nc + c], t = tscores[n * nc + c];
             cls += fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
         }
         AnchorTerms at;
-        if (anchor_terms(distri, tscores, tbox_px, anchors, stride, fg, n, (int)(n % A), nc, at)) { box = at.box; dfl = at.dfl; }
+        if (anchor_terms(distri, tscores, tbox_px, anchors, stride, fg, n, r, a, nc, at)) { box = at.box; dfl = at.dfl; }
     }
     box = block_sum(box, sh);
     cls = block_sum(cls, sh);
@@ -175,31 +194,55 @@ detect_loss_fwd_kernel(const float* __restrict__ distri, const float* __restrict
         atomicAdd(&sums[1], (double)cls);
         atomicAdd(&sums[2], (double)dfl);
     }
+    if (fin.tss_part == nullptr) return;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_ticket = atomicAdd(fin.counter, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1 || threadIdx.x != 0) return;
+    __threadfence();
+    double tss = 0.0;
+    for (int i = 0; i < fin.n_parts; ++i) tss += (double)fin.tss_part[i];
+    if (tss < 1.0) tss = 1.0;
+    for (int k = 0; k < 3; ++k) {
+        const double s = __ldcg(&sums[k]);
+        const float l = (float)(s / tss) * fin.gains[k];
+        fin.out6[k] = l * fin.batch;
+        fin.out6[3 + k] = l;
+        fin.coef3[k] = (float)((double)fin.gains[k] * (double)fin.batch / tss);
+    }
+    *fin.counter = 0u;
 }
 
-// coef[3] (device) = dL/d(sum_box), dL/d(sum_cls), dL/d(sum_dfl)
+// coef[3] (device) = dL/d(sum_box), dL/d(sum_cls), dL/d(sum_dfl); gout[3] (device, optional) multiplies them (upstream
+// gradient of the three returned loss components).  Gradients are written at the prediction ROWS (RowMap), as fp32 or --
+// for the fused head path, where they are the bf16 `dy` operands of the closing 1x1 convs' backward -- as bf16.
+template <typename TG>
 __global__ void __launch_bounds__(128)
 detect_loss_bwd_kernel(const float* __restrict__ distri, const float* __restrict__ scores, const float* __restrict__ anchors,
                        const float* __restrict__ stride, const float* __restrict__ tbox_px, const float* __restrict__ tscores,
                        const uint8_t* __restrict__ fg, long long N, int A, int nc, const float* __restrict__ coef,
-                       float* __restrict__ g_distri, float* __restrict__ g_scores) {
+                       const float* __restrict__ gout, TG* __restrict__ g_distri, TG* __restrict__ g_scores, const RowMap rm) {
     const long long n = (long long)blockIdx.x * 128 + threadIdx.x;
     if (n >= N) return;
-    const float kb = coef[0], kc = coef[1], kd = coef[2];
+    const int a = (int)(n % A);
+    const long long r = pred_row(rm, (int)(n / A), a, A);
+    float kb = coef[0], kc = coef[1], kd = coef[2];
+    if (gout) { kb *= gout[0]; kc *= gout[1]; kd *= gout[2]; }
     for (int c = 0; c < nc; ++c) {
-        const float x = scores[n * nc + c], t = tscores[n * nc + c];
-        g_scores[n * nc + c] = kc * (1.f / (1.f + expf(-x)) - t);
+        const float x = scores[r * nc + c], t = tscores[n * nc + c];
+        g_scores[r * nc + c] = (TG)(kc * (1.f / (1.f + expf(-x)) - t));
     }
-    float4* gp = reinterpret_cast<float4*>(g_distri + n * (4 * kRegMax));
+    TG* gp = g_distri + r * (4 * kRegMax);
     AnchorTerms at;
-    if (!anchor_terms(distri, tscores, tbox_px, anchors, stride, fg, n, (int)(n % A), nc, at)) {
+    if (!anchor_terms(distri, tscores, tbox_px, anchors, stride, fg, n, r, a, nc, at)) {
 #pragma unroll
-        for (int j = 0; j < kRegMax; ++j) gp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 4 * kRegMax; ++j) gp[j] = (TG)0.f;
         return;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        float g[kRegMax];
         const float gb = kb * at.gdist_box[k];      // d[(1 - ciou) * w] / d dist_k
         const float kdw = kd * 0.25f * at.weight;
 #pragma unroll
@@ -208,10 +251,8 @@ detect_loss_bwd_kernel(const float* __restrict__ distri, const float* __restrict
             float v = gb * p * ((float)j - at.dist[k]) + kdw * p;
             if (j == at.tl[k]) v -= kdw * at.wl[k];
             if (j == at.tl[k] + 1) v -= kdw * (1.f - at.wl[k]);
-            g[j] = v;
+            gp[k * kRegMax + j] = (TG)v;
         }
-#pragma unroll
-        for (int j = 0; j < kRegMax / 4; ++j) gp[k * 4 + j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
     }
 }
 
@@ -221,13 +262,14 @@ detect_loss_bwd_kernel(const float* __restrict__ distri, const float* __restrict
 __global__ void __launch_bounds__(128)
 detect_decode_kernel(const float* __restrict__ distri, const float* __restrict__ scores, const float* __restrict__ anchors,
                      const float* __restrict__ stride, long long N, int A, int nc, int xywh, float* __restrict__ boxes,
-                     float* __restrict__ probs) {
+                     float* __restrict__ probs, const RowMap rm) {
     const long long n = (long long)blockIdx.x * 128 + threadIdx.x;
     if (n >= N) return;
     const int a = (int)(n % A);
+    const long long r = pred_row(rm, (int)(n / A), a, A);
     float dist[4];
     for (int k = 0; k < 4; ++k) {
-        const float4* lp = reinterpret_cast<const float4*>(distri + n * (4 * kRegMax) + k * kRegMax);
+        const float4* lp = reinterpret_cast<const float4*>(distri + r * (4 * kRegMax) + k * kRegMax);
         float l[kRegMax];
 #pragma unroll
         for (int j = 0; j < kRegMax / 4; ++j) {
@@ -249,38 +291,65 @@ detect_decode_kernel(const float* __restrict__ distri, const float* __restrict__
     else o = make_float4(x1 * st, y1 * st, x2 * st, y2 * st);
     reinterpret_cast<float4*>(boxes)[n] = o;
     if (probs)
-        for (int c = 0; c < nc; ++c) probs[n * nc + c] = 1.f / (1.f + expf(-scores[n * nc + c]));
+        for (int c = 0; c < nc; ++c) probs[n * nc + c] = 1.f / (1.f + expf(-scores[r * nc + c]));
+}
+
+int make_rowmap(RowMap* rm, int nl, const int* a_off, int B, int A) {
+    memset(rm, 0, sizeof(*rm));
+    rm->B = B;
+    if (nl == 0 || a_off == nullptr) return 0;
+    SNN_REQUIRE(nl >= 1 && nl <= 4, "row map: 1..4 scales (got %d)", nl);
+    for (int i = 0; i <= nl; ++i) rm->a_off[i] = a_off[i];
+    SNN_REQUIRE(a_off[0] == 0 && a_off[nl] == A, "row map: anchor offsets must run from 0 to A=%d", A);
+    for (int i = 0; i < nl; ++i) SNN_REQUIRE(a_off[i + 1] > a_off[i], "row map: anchor offsets must increase");
+    rm->nl = nl;
+    return 0;
 }
 
 int launch_detect_decode(const float* distri, const float* scores, const float* anchors, const float* stride, int B, int A,
-                         int nc, int reg_max, int xywh, float* boxes, float* probs, cudaStream_t st) {
+                         int nc, int reg_max, int xywh, float* boxes, float* probs, int nl, const int* a_off, cudaStream_t st) {
     SNN_REQUIRE(reg_max == kRegMax, "detect_decode: reg_max must be %d (got %d)", kRegMax, reg_max);
     const long long N = (long long)B * A;
     if (N == 0) return 0;
-    detect_decode_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(distri, scores, anchors, stride, N, A, nc, xywh, boxes, probs);
+    RowMap rm;
+    if (make_rowmap(&rm, nl, a_off, B, A)) return 2;
+    detect_decode_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(distri, scores, anchors, stride, N, A, nc, xywh, boxes, probs, rm);
     return check_cuda(cudaGetLastError(), "detect_decode_kernel");
 }
 
 int launch_detect_loss_fwd(const float* distri, const float* scores, const float* anchors, const float* stride,
                            const float* tbox_px, const float* tscores, const uint8_t* fg, int B, int A, int nc, int reg_max,
-                           double* sums, cudaStream_t st) {
+                           double* sums, int nl, const int* a_off, const float* tss_part, int n_parts, const float* gains,
+                           unsigned int* counter, float* out6, float* coef3, cudaStream_t st) {
     SNN_REQUIRE(reg_max == kRegMax, "detect_loss: reg_max must be %d (got %d)", kRegMax, reg_max);
     SNN_CUDA_OK(cudaMemsetAsync(sums, 0, 3 * sizeof(double), st));
     const long long N = (long long)B * A;
     if (N == 0) return 0;
+    RowMap rm;
+    if (make_rowmap(&rm, nl, a_off, B, A)) return 2;
+    LossFinal fin = {tss_part, n_parts, gains, counter, out6, coef3, (float)B};
+    if (tss_part) SNN_REQUIRE(gains && counter && out6 && coef3 && n_parts >= 1, "detect_loss_fwd: fused finalisation needs gains/counter/out6/coef3");
     detect_loss_fwd_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(distri, scores, anchors, stride, tbox_px, tscores, fg,
-                                                                        N, A, nc, sums);
+                                                                        N, A, nc, sums, rm, fin);
     return check_cuda(cudaGetLastError(), "detect_loss_fwd_kernel");
 }
 
 int launch_detect_loss_bwd(const float* distri, const float* scores, const float* anchors, const float* stride,
                            const float* tbox_px, const float* tscores, const uint8_t* fg, int B, int A, int nc, int reg_max,
-                           const float* coef, float* g_distri, float* g_scores, cudaStream_t st) {
+                           const float* coef, const float* gout, void* g_distri, void* g_scores, int out_bf16, int nl, const int* a_off,
+                           cudaStream_t st) {
     SNN_REQUIRE(reg_max == kRegMax, "detect_loss: reg_max must be %d (got %d)", kRegMax, reg_max);
     const long long N = (long long)B * A;
     if (N == 0) return 0;
-    detect_loss_bwd_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(distri, scores, anchors, stride, tbox_px, tscores, fg,
-                                                                        N, A, nc, coef, g_distri, g_scores);
+    RowMap rm;
+    if (make_rowmap(&rm, nl, a_off, B, A)) return 2;
+    const unsigned grid = (unsigned)((N + 127) / 128);
+    if (out_bf16)
+        detect_loss_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(distri, scores, anchors, stride, tbox_px, tscores, fg, N, A, nc, coef, gout,
+                                                                    (__nv_bfloat16*)g_distri, (__nv_bfloat16*)g_scores, rm);
+    else
+        detect_loss_bwd_kernel<float><<<grid, 128, 0, st>>>(distri, scores, anchors, stride, tbox_px, tscores, fg, N, A, nc, coef, gout,
+                                                            (float*)g_distri, (float*)g_scores, rm);
     return check_cuda(cudaGetLastError(), "detect_loss_bwd_kernel");
 }
 

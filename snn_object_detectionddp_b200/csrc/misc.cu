@@ -137,8 +137,8 @@ lstm_gates_fwd_kernel(const float* __restrict__ gates, const float* __restrict__
 // outputs dgates (bf16, operand of dgrad/wgrad) and dc_prev.
 __global__ void __launch_bounds__(256)
 lstm_gates_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_next,
-                      const float* __restrict__ dh, const float* __restrict__ dc_in, __nv_bfloat16* __restrict__ dgates,
-                      float* __restrict__ dc_prev, long long n4, int Ch) {
+                      const float* __restrict__ dh, const __nv_bfloat16* __restrict__ dh_bf16, const float* __restrict__ dc_in,
+                      __nv_bfloat16* __restrict__ dgates, float* __restrict__ dc_prev, long long n4, int Ch) {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= n4) return;
     const int ch4 = Ch >> 2;
@@ -150,7 +150,14 @@ lstm_gates_bwd_kernel(const float* __restrict__ gates, const float* __restrict__
     if (c_prev) cp = __ldg(reinterpret_cast<const float4*>(c_prev) + idx);
     if (dc_in) dci = __ldg(reinterpret_cast<const float4*>(dc_in) + idx);
     const float4 cnx = __ldg(reinterpret_cast<const float4*>(c_next) + idx);
-    const float4 dhh = __ldg(reinterpret_cast<const float4*>(dh) + idx);
+    // total gradient w.r.t. h_t = recurrent part (fp32, from the next step's W_h dgrad) + the consumer's part (bf16, from
+    // bottleneck_conv's dgrad); either may be absent.  (Round 1 cast and added them with separate ATen kernels.)
+    float4 dhh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dh) dhh = __ldg(reinterpret_cast<const float4*>(dh) + idx);
+    if (dh_bf16) {
+        const uint2 hb = __ldg(reinterpret_cast<const uint2*>(dh_bf16) + idx);
+        dhh.x += bf16_lo(hb.x); dhh.y += bf16_hi(hb.x); dhh.z += bf16_lo(hb.y); dhh.w += bf16_hi(hb.y);
+    }
     const float iv[4] = {gi.x, gi.y, gi.z, gi.w}, fv[4] = {gf.x, gf.y, gf.z, gf.w}, gv[4] = {gg.x, gg.y, gg.z, gg.w},
                 ov[4] = {go.x, go.y, go.z, go.w}, cv[4] = {cp.x, cp.y, cp.z, cp.w}, cn[4] = {cnx.x, cnx.y, cnx.z, cnx.w},
                 dhv[4] = {dhh.x, dhh.y, dhh.z, dhh.w}, dcv[4] = {dci.x, dci.y, dci.z, dci.w};
@@ -182,11 +189,11 @@ int launch_lstm_gates_fwd(const float* gates, const float* c_prev, float* c_next
     return check_cuda(cudaGetLastError(), "lstm_gates_fwd_kernel");
 }
 
-int launch_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_next, const float* dh, const float* dc_in,
-                          __nv_bfloat16* dgates, float* dc_prev, long long P, int Ch, cudaStream_t st) {
+int launch_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_next, const float* dh, const __nv_bfloat16* dh_bf16,
+                          const float* dc_in, __nv_bfloat16* dgates, float* dc_prev, long long P, int Ch, cudaStream_t st) {
     SNN_REQUIRE(Ch % 4 == 0, "lstm_gates: Ch must be a multiple of 4");
     const long long n4 = P * Ch / 4;
-    lstm_gates_bwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(gates, c_prev, c_next, dh, dc_in, dgates, dc_prev, n4, Ch);
+    lstm_gates_bwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(gates, c_prev, c_next, dh, dh_bf16, dc_in, dgates, dc_prev, n4, Ch);
     return check_cuda(cudaGetLastError(), "lstm_gates_bwd_kernel");
 }
 
@@ -258,9 +265,10 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 }
 
 __global__ void __launch_bounds__(256)
-adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              __nv_bfloat16* __restrict__ shadow, long long n4, const float* __restrict__ hp_table,
-             const double* __restrict__ sumsq, float* __restrict__ gnorm_out, const int* __restrict__ step_ptr, int n_rows) {
+             const double* __restrict__ sumsq, float* __restrict__ gnorm_out, const int* __restrict__ step_ptr, int n_rows,
+             int zero_grad) {
     // row of the tabulated schedule: picked by a DEVICE step counter so a captured CUDA graph advances on replay
     const float* hp = hp_table + (step_ptr ? (size_t)min(*step_ptr, n_rows - 1) * 8 : 0);
     const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], bc1 = hp[5], bc2 = hp[6], max_norm = hp[7];
@@ -273,7 +281,10 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     const float rsq_bc2 = 1.f / sqrtf(bc2);
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
         float4 pp = reinterpret_cast<float4*>(p)[i];
-        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        // zero_grad: the gradient is consumed here, leave it zeroed for the next step's accumulating wgrad kernels
+        // (replaces optimizer.zero_grad() of train.py:61 = a separate 481 MB fill at the start of every step)
+        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
         float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w}, ma[4] = {mm.x, mm.y, mm.z, mm.w},
               va[4] = {vv.x, vv.y, vv.z, vv.w};
@@ -311,15 +322,15 @@ int launch_sumsq(const float* g, long long n, double* acc, int zero_first, cudaS
 
 __global__ void step_advance_kernel(int* step) { *step += 1; }
 
-int launch_adamw(float* p, const float* g, float* m, float* v, __nv_bfloat16* shadow, long long n, const float* hp,
-                 const double* sumsq, float* gnorm_out, int* step_ptr, int n_rows, cudaStream_t st) {
+int launch_adamw(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, long long n, const float* hp,
+                 const double* sumsq, float* gnorm_out, int* step_ptr, int n_rows, int zero_grad, cudaStream_t st) {
     SNN_REQUIRE(n % 4 == 0, "adamw: length must be a multiple of 4");
     const long long n4 = n / 4;
     long long blocks = (n4 + 255) / 256;
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, shadow, n4, hp, sumsq, gnorm_out, step_ptr, n_rows);
+    adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, shadow, n4, hp, sumsq, gnorm_out, step_ptr, n_rows, zero_grad);
     SNN_CUDA_OK(cudaGetLastError());
     if (step_ptr) step_advance_kernel<<<1, 1, 0, st>>>(step_ptr);
     return check_cuda(cudaGetLastError(), "adamw_kernel");

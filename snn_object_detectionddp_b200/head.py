@@ -57,10 +57,15 @@ def dist2bbox(distance, anchor_points, xywh=True, dim=-1):
 
 
 class HeadOut:
-    """Head outputs of one timestep: per scale `box` [B,h,w,4*reg_max] and `cls` [B,h,w,nc], fp32 NHWC."""
+    """Head outputs of one timestep: per scale `box` [B,h,w,4*reg_max] and `cls` [B,h,w,nc], fp32 NHWC.
 
-    def __init__(self, box, cls, training):
+    The per-scale tensors are views of two SCALE-MAJOR buffers `flat_box` [B*A, 4*reg_max] / `flat_cls` [B*A, nc] (scale i
+    occupies rows [B*a_off[i], B*a_off[i+1]), image-major inside) that the closing 1x1 convs write directly, so the loss
+    kernels read the predictions without any torch.cat (they index rows through `a_off`)."""
+
+    def __init__(self, box, cls, training, flat_box=None, flat_cls=None, a_off=None):
         self.box, self.cls, self.training = box, cls, training
+        self.flat_box, self.flat_cls, self.a_off = flat_box, flat_cls, a_off
 
     def shapes(self):
         return [tuple(b.shape[1:3]) for b in self.box]
@@ -107,8 +112,15 @@ class Detect(nn.Module):
         """feats: 3 bf16 NHWC maps [T*B,h,w,ch].  Every timestep runs (BatchNorm running statistics advance once per
         frame exactly like the reference's per-frame calls); the returned HeadOut holds the last step (train.py:66)."""
         boxes, clss = [], []
-        live_n = None if (rc.live_T is None or rc.live_T >= rc.T or not last_only) else rc.live_T * B
-        f32 = dict(store=rc.store, geom=GEOM_1x1, out_dtype=torch.float32, live_n=live_n)
+        # scale-major prediction buffers (see HeadOut): the frames that are returned, all scales
+        n_out = B if last_only else feats[0].shape[0]
+        hw = [f.shape[1] * f.shape[2] for f in feats]
+        a_off = [0]
+        for v in hw:
+            a_off.append(a_off[-1] + v)
+        dev = feats[0].device
+        flat_box = torch.empty((n_out * a_off[-1], 4 * self.reg_max), device=dev, dtype=torch.float32)
+        flat_cls = torch.empty((n_out * a_off[-1], self.nc), device=dev, dtype=torch.float32)
         for i in range(self.nl):
             x = feats[i]
             if x.dtype != torch.bfloat16:
@@ -123,12 +135,15 @@ class Detect(nn.Module):
             if last_only:
                 # the closing 1x1 convs have no BatchNorm (no per-frame side effect): only the frames that are returned
                 b, c = b[-B:], c[-B:]
-                f32 = dict(store=rc.store, geom=GEOM_1x1, out_dtype=torch.float32)
-            b = ConvBiasFn.apply(b, self.cv2[i][2].weight, self.cv2[i][2].bias, f32)
-            c = ConvBiasFn.apply(c, self.cv3[i][2].weight, self.cv3[i][2].bias, f32)
+            h, w = x.shape[1], x.shape[2]
+            rows = slice(n_out * a_off[i], n_out * a_off[i + 1])
+            cfg_b = dict(store=rc.store, geom=GEOM_1x1, out_dtype=torch.float32, out=flat_box[rows].view(n_out, h, w, 4 * self.reg_max))
+            cfg_c = dict(store=rc.store, geom=GEOM_1x1, out_dtype=torch.float32, out=flat_cls[rows].view(n_out, h, w, self.nc))
+            b = ConvBiasFn.apply(b, self.cv2[i][2].weight, self.cv2[i][2].bias, cfg_b)
+            c = ConvBiasFn.apply(c, self.cv3[i][2].weight, self.cv3[i][2].bias, cfg_c)
             boxes.append(b)
             clss.append(c)
-        return HeadOut(boxes, clss, self.training)
+        return HeadOut(boxes, clss, self.training, flat_box, flat_cls, a_off)
 
     def decode(self, out):
         """Eval-mode Detect._inference: DFL expectation -> dist2bbox(xywh) * stride, sigmoid class scores -> [B,4+nc,A]."""

@@ -273,13 +273,16 @@ def lstm_gates_fwd(gates, c_prev, ch, h_bf16_out=None, c_out=None):
     return h_next, c_next, h_bf16
 
 
-def lstm_gates_bwd(gates, c_prev, c_next, dh, dc_in, ch, dgates_out=None):
-    require_cuda(gates, c_prev, c_next, dh, dc_in, dgates_out)
+def lstm_gates_bwd(gates, c_prev, c_next, dh, dc_in, ch, dgates_out=None, dh_bf16=None):
+    """dh (fp32 | None) + dh_bf16 (bf16 | None) = total gradient w.r.t. h_t, summed inside the kernel."""
+    require_cuda(gates, c_prev, c_next, dh, dh_bf16, dc_in, dgates_out)
     p = gates.numel() // (4 * ch)
     dgates = torch.empty(gates.shape, device=gates.device, dtype=torch.bfloat16) if dgates_out is None else dgates_out
-    assert gates.is_contiguous() and dgates.is_contiguous() and dh.is_contiguous() and dh.dtype == torch.float32
+    assert gates.is_contiguous() and dgates.is_contiguous()
+    assert dh is None or (dh.is_contiguous() and dh.dtype == torch.float32)
+    assert dh_bf16 is None or (dh_bf16.is_contiguous() and dh_bf16.dtype == torch.bfloat16)
     dc_prev = torch.empty(c_next.shape, device=gates.device, dtype=torch.float32)
-    call("snn_lstm_gates_bwd", ptr(gates), ptr(c_prev), ptr(c_next), ptr(dh), ptr(dc_in), ptr(dgates), ptr(dc_prev), p, ch,
+    call("snn_lstm_gates_bwd", ptr(gates), ptr(c_prev), ptr(c_next), ptr(dh), ptr(dh_bf16), ptr(dc_in), ptr(dgates), ptr(dc_prev), p, ch,
          stream_ptr())
     return dgates, dc_prev
 
@@ -352,12 +355,14 @@ def grad_sumsq(g, acc, zero_first=True):
     call("snn_grad_sumsq", ptr(g), g.numel(), ptr(acc), int(zero_first), stream_ptr(), work=("byte", 4.0 * g.numel()))
 
 
-def adamw_step(p, g, m, v, shadow, hp, sumsq, gnorm_out=None, step=None):
-    """hp: one row of 8 floats, or (with `step`, a device int32 scalar) the whole [rows, 8] schedule table."""
+def adamw_step(p, g, m, v, shadow, hp, sumsq, gnorm_out=None, step=None, zero_grad=False):
+    """hp: one row of 8 floats, or (with `step`, a device int32 scalar) the whole [rows, 8] schedule table.
+    zero_grad: leave g zeroed (the next step's optimizer.zero_grad() folded into this pass)."""
     require_cuda(p, g, m, v, shadow, hp, sumsq, gnorm_out, step)
     n_rows = hp.shape[0] if (step is not None and hp.dim() == 2) else 1
     call("snn_adamw_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), p.numel(), ptr(hp), ptr(sumsq), ptr(gnorm_out),
-         ptr(step), n_rows, stream_ptr(), work=("byte", (28.0 + (2.0 if shadow is not None else 0.0)) * p.numel()))
+         ptr(step), n_rows, int(bool(zero_grad)), stream_ptr(),
+         work=("byte", (28.0 + (2.0 if shadow is not None else 0.0) + (4.0 if zero_grad else 0.0)) * p.numel()))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -419,6 +424,73 @@ def detect_decode(distri, scores, anchors, stride, xywh, want_probs=True):
     call("snn_detect_decode", ptr(distri), ptr(scores), ptr(anchors), ptr(stride), b, a, nc, r4 // 4, int(xywh), ptr(boxes),
          ptr(probs), stream_ptr())
     return boxes, probs
+
+
+def _a_off_arg(a_off):
+    """Row map of scale-major prediction buffers -> (nl, ctypes int array | None); None / () = natural [B][A] rows."""
+    if not a_off:
+        return 0, None
+    arr = (_lib.ctypes.c_int * len(a_off))(*[int(v) for v in a_off])
+    return len(a_off) - 1, arr
+
+
+def detect_assign_loss_fwd(distri, scores, a_off, anchors, stride, gt_cls, gt_box, gt_valid, img_wh, B, A, nc, reg_max, topk,
+                           gains, counter):
+    """decode -> task-aligned assignment -> fused loss sums -> finalisation, 5 launches (include/snn_b200.h).
+    distri [B*A, 4*reg_max] / scores [B*A, nc] fp32 in the row order `a_off` describes.  Returns
+    (out6 = loss*B [3] ++ loss [3], coef3, (tbox_px, tscores, fg))."""
+    require_cuda(distri, scores, anchors, stride, gt_cls, gt_box, gt_valid, gains, counter)
+    dev = distri.device
+    M = gt_cls.shape[1]
+    assert gt_cls.dtype == torch.int64 and gt_box.dtype == torch.float32 and gt_valid.dtype in (torch.bool, torch.uint8)
+    assert gt_cls.is_contiguous() and gt_box.is_contiguous() and gt_valid.is_contiguous() and distri.is_contiguous() and scores.is_contiguous()
+    assert tuple(gt_cls.shape) == (B, M) and tuple(gt_box.shape) == (B, M, 4) and distri.numel() == B * A * 4 * reg_max
+    assert counter.dtype == torch.int32 and gains.dtype == torch.float32 and gains.numel() == 3
+    ws = torch.empty((int(_lib.lib().snn_tal_workspace_bytes(B, A, M)) + 15) // 16 * 4, device=dev, dtype=torch.float32)
+    pboxes = torch.empty((B, A, 4), device=dev, dtype=torch.float32)
+    probs = torch.empty((B, A, nc), device=dev, dtype=torch.float32)
+    tbox = torch.empty((B, A, 4), device=dev, dtype=torch.float32)
+    tscores = torch.empty((B, A, nc), device=dev, dtype=torch.float32)
+    fg = torch.empty((B, A), device=dev, dtype=torch.uint8)
+    sums = torch.empty(3, device=dev, dtype=torch.float64)
+    out6 = torch.empty(6, device=dev, dtype=torch.float32)
+    coef3 = torch.empty(3, device=dev, dtype=torch.float32)
+    nl, arr = _a_off_arg(a_off)
+    call("snn_detect_assign_loss_fwd", ptr(distri), ptr(scores), nl, arr, ptr(anchors), ptr(stride), ptr(gt_cls), ptr(gt_box),
+         ptr(gt_valid), float(img_wh[0]), float(img_wh[1]), B, A, M, nc, reg_max, int(topk), ptr(gains), ptr(ws), ptr(pboxes),
+         ptr(probs), ptr(tbox), ptr(tscores), ptr(fg), ptr(sums), ptr(counter), ptr(out6), ptr(coef3), stream_ptr())
+    return out6, coef3, (tbox, tscores, fg)
+
+
+def tal_assign(probs, pboxes, anchors, stride, gt_cls, gt_box, gt_valid, img_wh, nc, topk=10):
+    """The assigner kernels alone: probs [B,A,nc] (sigmoid), pboxes [B,A,4] xyxy px -> (tbox_px, tscores, fg)."""
+    require_cuda(probs, pboxes, anchors, stride, gt_cls, gt_box, gt_valid)
+    B, A = probs.shape[0], probs.shape[1]
+    M = gt_cls.shape[1]
+    dev = probs.device
+    ws = torch.empty((int(_lib.lib().snn_tal_workspace_bytes(B, A, M)) + 15) // 16 * 4, device=dev, dtype=torch.float32)
+    tbox = torch.empty((B, A, 4), device=dev, dtype=torch.float32)
+    tscores = torch.empty((B, A, nc), device=dev, dtype=torch.float32)
+    fg = torch.empty((B, A), device=dev, dtype=torch.uint8)
+    assert probs.is_contiguous() and pboxes.is_contiguous() and gt_cls.dtype == torch.int64
+    call("snn_tal_assign", ptr(probs), ptr(pboxes), ptr(anchors), ptr(stride), ptr(gt_cls.contiguous()), ptr(gt_box.contiguous()),
+         ptr(gt_valid.contiguous()), float(img_wh[0]), float(img_wh[1]), B, A, M, nc, int(topk), ptr(ws), ptr(tbox), ptr(tscores), ptr(fg),
+         stream_ptr())
+    return tbox, tscores, fg
+
+
+def detect_loss_bwd_rows(distri, scores, a_off, anchors, stride, targets, B, A, nc, reg_max, coef3, gout3, bf16):
+    """Gradients of sum(gout3 * loss*B) w.r.t. the prediction rows; bf16 (fused head path) or fp32."""
+    tbox, tscores, fg = targets
+    require_cuda(distri, scores, anchors, stride, tbox, tscores, fg, coef3, gout3)
+    dt = torch.bfloat16 if bf16 else torch.float32
+    g_distri = torch.empty(distri.shape, device=distri.device, dtype=dt)
+    g_scores = torch.empty(scores.shape, device=distri.device, dtype=dt)
+    nl, arr = _a_off_arg(a_off)
+    assert gout3 is None or (gout3.dtype == torch.float32 and gout3.is_contiguous() and gout3.numel() == 3)
+    call("snn_detect_loss_bwd_rows", ptr(distri), ptr(scores), nl, arr, ptr(anchors), ptr(stride), ptr(tbox), ptr(tscores), ptr(fg),
+         B, A, nc, reg_max, ptr(coef3), ptr(gout3), ptr(g_distri), ptr(g_scores), int(bf16), stream_ptr())
+    return g_distri, g_scores
 
 
 def detect_loss_fwd(distri, scores, anchors, stride, tbox_px, tscores, fg):

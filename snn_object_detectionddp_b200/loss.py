@@ -4,11 +4,12 @@
 PARITY UNPINNED: ultralytics is an un-vendored, unpinned third party; its published 8.3.x algorithm is
 restated.  Split of the work:
 
-* target assignment (TaskAlignedAssigner, top-k 10, alpha 0.5, beta 6) -- no gradient flows through it; expressed as
-  dense, *synchronisation-free* tensor ops on the device (no boolean-mask indexing, no ``.item()``/``.max()`` host
-  reads), so the training step never stalls the host;
-* everything differentiable (BCE class loss over [B,A,nc], CIoU box loss, DFL, their reductions and the backward)
-  -- two fused kernels of libsnnb200 (csrc/loss.cu) behind ``DetectLossFn``.
+* target assignment (TaskAlignedAssigner, top-k 10, alpha 0.5, beta 6) -- no gradient flows through it; three kernels
+  of libsnnb200 (csrc/assign.cu), synchronisation-free.  `task_aligned_assign` below is the same algorithm as dense torch
+  ops: the host-checkable formulation the kernels are tested against (tests/test_host_logic.py pins it to the restated
+  ultralytics assigner on CPU; tests/test_gpu_train.py pins the kernels to it) -- the product path does not call it;
+* everything differentiable (BCE class loss over [B,A,nc], CIoU box loss, DFL, their reductions, the normalisation by the
+  target-score sum, the hyp gains and the backward) -- csrc/loss.cu, behind ``DetectLossFn``.
 """
 import torch
 from torch.autograd import Function
@@ -17,20 +18,43 @@ from . import kernels as K
 
 
 class DetectLossFn(Function):
-    """(pred_distri [B,A,64], pred_scores [B,A,nc]; targets) -> fp32 sums {box, cls, dfl} (un-normalised)."""
+    """v8DetectionLoss forward + backward on the libsnnb200 kernels (5 + 1 launches, no host synchronisation):
+    decode -> task-aligned assignment -> fused BCE / CIoU / DFL sums -> finalisation ; one backward kernel.
+
+    `preds` are either the six per-scale tensors of a HeadOut (views of its scale-major buffers; gradients come back as
+    bf16 NHWC views, directly the `dy` operands of the head's closing convs) or (pred_distri [B,A,64], pred_scores
+    [B,A,nc]) in natural layout (drop-in list-of-maps path; fp32 gradients).  Returns (loss*B [3], loss [3])."""
 
     @staticmethod
-    def forward(ctx, distri, scores, anchors, stride, tbox_px, tscores, fg):
-        distri, scores = distri.contiguous(), scores.contiguous()
-        sums = K.detect_loss_fwd(distri, scores, anchors, stride, tbox_px, tscores, fg)
-        ctx.save_for_backward(distri, scores, anchors, stride, tbox_px, tscores, fg)
-        return sums.float()
+    def forward(ctx, meta, *preds):
+        if meta["a_off"]:
+            distri, scores = meta["flat_box"], meta["flat_cls"]
+        else:
+            distri, scores = preds[0].contiguous(), preds[1].contiguous()
+        B, A, nc, reg_max = meta["B"], meta["A"], meta["nc"], meta["reg_max"]
+        cls, box, valid = meta["labels"]
+        out6, coef3, targets = K.detect_assign_loss_fwd(distri, scores, meta["a_off"], meta["anchors"], meta["stride"], cls, box, valid,
+                                                        meta["img_wh"], B, A, nc, reg_max, meta["topk"], meta["gains"], meta["counter"])
+        ctx.meta, ctx.saved = meta, (distri, scores, coef3, targets)
+        ctx.shapes = [tuple(p.shape) for p in preds]
+        loss_b, items = out6[:3], out6[3:]
+        ctx.mark_non_differentiable(items)
+        return loss_b, items
 
     @staticmethod
-    def backward(ctx, g):
-        distri, scores, anchors, stride, tbox_px, tscores, fg = ctx.saved_tensors
-        gd, gs = K.detect_loss_bwd(distri, scores, anchors, stride, tbox_px, tscores, fg, g.contiguous().float())
-        return gd, gs, None, None, None, None, None
+    def backward(ctx, g_loss, _g_items):
+        meta = ctx.meta
+        distri, scores, coef3, targets = ctx.saved
+        gout = g_loss if (g_loss.dtype == torch.float32 and g_loss.is_contiguous()) else g_loss.float().contiguous()
+        fused = bool(meta["a_off"])
+        gd, gs = K.detect_loss_bwd_rows(distri, scores, meta["a_off"], meta["anchors"], meta["stride"], targets, meta["B"], meta["A"],
+                                        meta["nc"], meta["reg_max"], coef3, gout, bf16=fused)
+        if not fused:
+            return None, gd.view(ctx.shapes[0]), gs.view(ctx.shapes[1])
+        B, a_off, nl = meta["B"], meta["a_off"], len(meta["a_off"]) - 1
+        grads = [gd[B * a_off[i]:B * a_off[i + 1]].view(ctx.shapes[i]) for i in range(nl)]
+        grads += [gs[B * a_off[i]:B * a_off[i + 1]].view(ctx.shapes[nl + i]) for i in range(nl)]
+        return (None, *grads)
 
 
 def _ciou_dense(b1, b2, eps=1e-7):
@@ -148,32 +172,35 @@ class v8DetectionLoss:
         cat = torch.cat([f.reshape(b, self.no, -1) for f in feats], 2).permute(0, 2, 1)
         return cat[..., :4 * self.reg_max].contiguous(), cat[..., 4 * self.reg_max:].contiguous(), [tuple(f.shape[2:]) for f in feats]
 
-    def __call__(self, preds, batch):
-        distri, scores, shapes = self._flatten(preds)
-        distri, scores = distri.float(), scores.float()
-        dev, B = distri.device, distri.shape[0]
-        anchors, stride = self._anchors(shapes, dev)
-        if self._gains is None or self._gains.device != dev:
-            self._gains = torch.tensor([self.hyp.box, self.hyp.cls, self.hyp.dfl], device=dev, dtype=torch.float32)
+    def _labels(self, batch, B, dev):
         if "padded" in batch:
             cls, box, valid = (t.to(dev, non_blocking=True) for t in batch["padded"])
         else:
             lab = torch.cat((batch["batch_idx"].view(-1, 1).float(), batch["cls"].view(-1, 1).float(),
                              batch["bboxes"].view(-1, 4).float()), 1)
             cls, box, valid = pad_targets(lab, B, dev)
-        H, W = shapes[0][0] * self.stride[0], shapes[0][1] * self.stride[0]
-        if (H, W, str(dev)) not in self._scale_cache:
-            self._scale_cache[(H, W, str(dev))] = torch.tensor([W, H, W, H], device=dev, dtype=torch.float32)
-        scale = self._scale_cache[(H, W, str(dev))]
-        with torch.no_grad():
-            xy, wh = box[..., :2] * scale[:2], box[..., 2:] * scale[2:] / 2
-            gt_xyxy = torch.cat((xy - wh, xy + wh), -1) * valid[..., None]
-            mask_gt = valid & (gt_xyxy.sum(-1) > 0)
-            pd_boxes, pd_probs = K.detect_decode(distri.detach().contiguous(), scores.detach().contiguous(), anchors, stride,
-                                                 xywh=False)
-            t_boxes, t_scores, fg = task_aligned_assign(pd_probs, pd_boxes, anchors * stride[:, None], cls, gt_xyxy, mask_gt,
-                                                        self.nc, self.topk)
-            tss = t_scores.sum().clamp_(min=1.0)
-        sums = DetectLossFn.apply(distri, scores, anchors, stride, t_boxes, t_scores, fg)
-        loss = sums / tss * self._gains
-        return loss * B, loss.detach()
+        return cls.long().contiguous(), box.float().contiguous(), valid.contiguous()
+
+    def __call__(self, preds, batch):
+        from .head import HeadOut
+        fused = isinstance(preds, HeadOut) and preds.flat_box is not None
+        if fused:
+            shapes, dev, B = preds.shapes(), preds.flat_box.device, preds.box[0].shape[0]
+            tensors = tuple(preds.box) + tuple(preds.cls)
+            a_off, flat_box, flat_cls = tuple(preds.a_off), preds.flat_box, preds.flat_cls
+        else:
+            distri, scores, shapes = self._flatten(preds)
+            tensors = (distri.float(), scores.float())
+            dev, B = distri.device, distri.shape[0]
+            a_off, flat_box, flat_cls = (), None, None
+        anchors, stride = self._anchors(shapes, dev)
+        if self._gains is None or self._gains.device != dev:
+            self._gains = torch.tensor([self.hyp.box, self.hyp.cls, self.hyp.dfl], device=dev, dtype=torch.float32)
+            self._counter = torch.zeros(1, device=dev, dtype=torch.int32)      # ticket of the finalising block (kernel leaves it 0)
+        # imgsz = stride-8 map size * stride (ultralytics: feats[0].shape[2:] * stride[0]); (W, H) order for the xywh scaling
+        img_wh = (shapes[0][1] * self.stride[0], shapes[0][0] * self.stride[0])
+        meta = dict(a_off=a_off, flat_box=flat_box, flat_cls=flat_cls, anchors=anchors, stride=stride, labels=self._labels(batch, B, dev),
+                    img_wh=img_wh, B=B, A=anchors.shape[0], nc=self.nc, reg_max=self.reg_max, topk=self.topk, gains=self._gains,
+                    counter=self._counter)
+        loss_b, items = DetectLossFn.apply(meta, *tensors)
+        return loss_b, items

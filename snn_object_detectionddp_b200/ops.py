@@ -195,7 +195,10 @@ class ConvBiasFn(Function):
         cout = weight.shape[1] if geom == GEOM_T2x2_S2 else weight.shape[0]
         if any(ctx.needs_input_grad):
             st.note_use(weight, bias)
-        out = K.conv_fprop(geom, x0, st.w_fprop(weight), cout, bias=bias, out_dtype=cfg.get("out_dtype", torch.bfloat16))
+        # cfg["out"]: a caller-provided output view (the Detect head's closing convs write straight into the scale-major
+        # prediction buffers the loss kernels read: no torch.cat)
+        out = K.conv_fprop(geom, x0, st.w_fprop(weight), cout, bias=bias, out=cfg.get("out"),
+                           out_dtype=cfg.get("out_dtype", torch.bfloat16))
         ctx.cfg = cfg
         ctx.save_for_backward(x0, weight, bias)
         return out
@@ -273,18 +276,16 @@ class ConvLSTMSeqFn(Function):
         B = nb // T
         wt = st.w_fprop(weight)
         dgates = torch.empty(gates.shape, device=x.device, dtype=torch.bfloat16)
-        dh_rec = None if g_hlast is None else g_hlast.float()
+        dh_rec = None if g_hlast is None else g_hlast.contiguous().float()
         dc = None if g_clast is None else g_clast.contiguous().float()
         h0b = None if h0 is None else h0.to(torch.bfloat16).contiguous()
+        g_hall = _bf16c(g_hall)
         for t in range(T - 1, -1, -1):
             sl = slice(t * B, (t + 1) * B)
-            dh = None if g_hall is None else g_hall[sl].float()
-            if dh_rec is not None:
-                dh = dh_rec if dh is None else dh + dh_rec
-            if dh is None:
-                dh = torch.zeros((B, hh, ww, ch), device=x.device, dtype=torch.float32)
+            # dL/dh_t = consumer's gradient (bf16 slice of g_hall) + recurrent gradient (fp32 dgrad of step t+1): summed in-kernel
             c_prev = c_all[(t - 1) * B:t * B] if t > 0 else (None if c0 is None else c0.contiguous())
-            _, dc = K.lstm_gates_bwd(gates[sl], c_prev, c_all[sl], dh.contiguous(), dc, ch, dgates_out=dgates[sl])
+            _, dc = K.lstm_gates_bwd(gates[sl], c_prev, c_all[sl], dh_rec, dc, ch, dgates_out=dgates[sl],
+                                     dh_bf16=None if g_hall is None else g_hall[sl])
             if t > 0 or ctx.has_state:
                 dh_rec = K.conv_dgrad(GEOM_3x3_S1, dgates[sl], wt, (hh, ww), ch, ci_off=cx, out_dtype=torch.float32)
             else:

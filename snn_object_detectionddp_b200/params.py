@@ -83,6 +83,7 @@ class ParamStore:
         self.opt_epoch = 0           # bumped by the fused optimizer (it rewrites master + shadow)
         self.grad_epoch = 0          # bumped by zero_grad(); used by DDP bucket bookkeeping
         self.grad_ready_hook = None  # callable(entry) fired right after an entry's gradient is complete
+        self.grads_clean = False     # flat_g is known to be all zeros
         for e in self.entries:
             _STORE_OF_PARAM[id(e.param)] = self
 
@@ -106,6 +107,7 @@ class ParamStore:
             e.logical_view(flat_p).copy_(e.param.data.to(device=device, dtype=torch.float32))
         self.flat_p = flat_p
         self.flat_g = torch.zeros(self.total, device=device, dtype=torch.float32)
+        self.grads_clean = True
         keep = old_m is not None and old_m.device == device
         self.flat_m = old_m if keep else torch.zeros(self.total, device=device, dtype=torch.float32)
         self.flat_v = old_v if keep else torch.zeros(self.total, device=device, dtype=torch.float32)
@@ -139,7 +141,11 @@ class ParamStore:
 
     # -- gradients -------------------------------------------------------------------------
     def zero_grad(self):
-        self.flat_g.zero_()
+        """optimizer.zero_grad() of train.py:61.  The fused optimizer leaves the gradient buffer zeroed itself
+        (snn_adamw_step(zero_grad=1)); the 481 MB fill only runs when something accumulated since (external optimizer)."""
+        if not self.grads_clean:
+            self.flat_g.zero_()
+        self.grads_clean = True
         self.grad_epoch += 1
         for e in self.entries:
             e.param.grad = e.logical_view(self.flat_g)
@@ -149,6 +155,7 @@ class ParamStore:
         """Gradient slice to accumulate into (PyTorch semantics: a `None` grad means start from zero)."""
         e = self.by_param[id(p)]
         g = p.grad
+        self.grads_clean = False
         ours = e.logical_view(self.flat_g)
         if g is None or g.data_ptr() != ours.data_ptr():
             self.flat_g[e.offset:e.offset + e.numel].zero_()

@@ -60,6 +60,7 @@ class Trainer:
         self._eager_calls = 0
         self._sumsq = torch.zeros(1, device=self.device, dtype=torch.float64)
         self.grad_norm = torch.zeros(1, device=self.device, dtype=torch.float32)
+        self._ones3 = torch.ones(3, device=self.device, dtype=torch.float32)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.bucketer = None
@@ -92,7 +93,8 @@ class Trainer:
             self.bucketer.begin_step()
         det, _ = model.forward_sequence(frames)
         loss, items = self.loss_fn(det, batch)
-        loss.sum().backward()
+        # = loss.sum().backward() of train.py:75-76 without the reduction / expand kernels
+        torch.autograd.backward((loss,), (self._ones3,))
         if self.bucketer is not None:
             self.bucketer.finish()
         self.optimizer_step()
@@ -102,7 +104,8 @@ class Trainer:
         st = self.store
         K.grad_sumsq(st.flat_g, self._sumsq)
         K.adamw_step(st.flat_p, st.flat_g, st.flat_m, st.flat_v, st.shadow, self.hp, self._sumsq, self.grad_norm,
-                     step=self._step_dev)
+                     step=self._step_dev, zero_grad=True)
+        st.grads_clean = True            # the optimizer pass zeroed the gradient buffer (next step's zero_grad is free)
         st.opt_epoch += 1
         self.step_idx += 1
 

@@ -338,3 +338,89 @@ def test_device_prefetcher_pageable_and_pinned_sources():
         for a, b in zip(got[1], batches[i][1]):
             assert torch.equal(a.cpu(), b)
     assert pf.bytes_per_batch() == sum(t.numel() * t.element_size() for t in (batches[4][0],) + batches[4][1])
+
+
+# ------------------------------------------------------------------------------------------------
+# assigner kernels (csrc/assign.cu) and the fused head -> loss path (scale-major buffers, bf16 gradients)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,B,nmax,hw", [(0, 4, 6, 128), (1, 2, 1, 128), (2, 3, 12, 256), (3, 64, 8, 256)])
+def test_tal_assign_kernels_match_dense_formulation(seed, B, nmax, hw):
+    """snn_tal_assign (3 launches) == the dense torch formulation of TaskAlignedAssigner (loss.task_aligned_assign, itself
+    pinned to the restated ultralytics assigner on CPU by tests/test_host_logic.py) on the same random predictions.
+    Anchors whose alignment metric is exactly 0 may be picked differently among the zero ties of the top-k (torch.topk's
+    tie order is unspecified; the kernels take the lower index): they carry target score 0 = no loss weight, so the
+    comparison is on the anchors with weight > 0: same foreground set, same boxes, scores to 1e-5."""
+    from snn_object_detectionddp_b200 import kernels as K
+    from snn_object_detectionddp_b200.head import make_anchors
+    from snn_object_detectionddp_b200.loss import task_aligned_assign
+    g = torch.Generator().manual_seed(seed)
+    nc, strides = 8, (8.0, 16.0, 32.0)
+    anchors, st = make_anchors([(hw // int(s), hw // int(s)) for s in strides], strides)
+    A = anchors.shape[0]
+    probs = torch.rand(B, A, nc, generator=g) * 0.5
+    ctr = (anchors * st)[None].expand(B, -1, -1)
+    half = torch.rand(B, A, 2, generator=g) * 30 + 4
+    jit = (torch.rand(B, A, 2, generator=g) - 0.5) * 6
+    pboxes = torch.cat((ctr + jit - half, ctr + jit + half), -1)
+    n = torch.randint(0, nmax + 1, (B,), generator=g)
+    n[0] = nmax
+    cls = torch.randint(0, nc, (B, nmax), generator=g)
+    cxy = torch.rand(B, nmax, 2, generator=g) * 0.7 + 0.15
+    wh = torch.rand(B, nmax, 2, generator=g) * 0.3 + 0.06
+    box = torch.cat((cxy, wh), -1)
+    valid = torch.arange(nmax)[None] < n[:, None]
+    probs, pboxes, anchors, st, cls, box, valid = (t.to(DEV).contiguous() for t in (probs, pboxes, anchors, st.view(-1), cls, box, valid))
+    tb, ts, fg = K.tal_assign(probs, pboxes, anchors, st, cls, box, valid, (float(hw), float(hw)), nc)
+    scale = torch.tensor([hw, hw, hw, hw], device=DEV, dtype=torch.float32)
+    xy, half_wh = box[..., :2] * scale[:2], box[..., 2:] * scale[2:] / 2
+    gt_xyxy = torch.cat((xy - half_wh, xy + half_wh), -1) * valid[..., None]
+    mask_gt = valid & (gt_xyxy.sum(-1) > 0)
+    r_tb, r_ts, r_fg = task_aligned_assign(probs, pboxes, anchors * st[:, None], cls, gt_xyxy, mask_gt, nc, 10)
+    w_k, w_r = ts.sum(-1), r_ts.sum(-1)
+    assert int((w_r > 0).sum()) > 0
+    assert torch.equal(w_k > 0, w_r > 0), int(((w_k > 0) != (w_r > 0)).sum())
+    assert torch.allclose(ts, r_ts, rtol=1e-5, atol=1e-7), float((ts - r_ts).abs().max())
+    pos = w_r > 0
+    assert bool((fg.bool() | ~pos).all()) and torch.equal(tb[pos], r_tb[pos])
+    # foreground flags may differ only on zero-weight anchors
+    assert int((fg.bool() != r_fg.bool()).sum()) == int(((fg.bool() != r_fg.bool()) & ~pos).sum())
+    tb2, ts2, fg2 = K.tal_assign(probs, pboxes, anchors, st, cls, box, valid, (float(hw), float(hw)), nc)
+    assert torch.equal(ts, ts2) and torch.equal(fg, fg2) and torch.equal(tb, tb2)          # deterministic
+
+
+def test_fused_head_loss_path_equals_list_of_maps_path():
+    """`loss_fn(HeadOut)` (scale-major prediction buffers written by the head's closing convs, bf16 gradients handed
+    straight to their backward: no torch.cat / split anywhere) == `loss_fn([maps])` (the reference's call with the list
+    of [B, nc+64, h, w] maps, train.py:74): same loss values; parameter gradients agree to 1e-2 (the fused path rounds the
+    prediction gradients to bf16 once, as every other `dy` on the path)."""
+    setup_exact()
+    from snn_object_detectionddp_b200.loss import v8DetectionLoss
+    from snn_object_detectionddp_b200.params import store_for
+    res = []
+    for fused in (True, False):
+        _, net = _models("lif", seed=21)
+        net.train()
+        B, T, HW = 4, 2, 128
+        frames, labels = MO.synthetic_batch(B, T, HW, HW, seed=22)
+        frames, labels = frames.to(DEV), labels.to(DEV)
+        batch = {"batch_idx": labels[:, 0], "cls": labels[:, 1], "bboxes": labels[:, 2:]}
+        st = store_for(net, DEV)
+        st.zero_grad()
+        det, _ = net.forward_sequence(frames)
+        assert det.flat_box is not None and det.a_off == [0, 256, 320, 336]
+        loss, items = v8DetectionLoss(net)(det if fused else det.maps_nchw(), batch)
+        loss.sum().backward()
+        torch.cuda.synchronize()
+        res.append((loss.detach().clone(), items.clone(), st.flat_g.clone(), st))
+    (l_f, it_f, g_f, st), (l_m, it_m, g_m, _) = res
+    assert torch.allclose(it_f, it_m, rtol=1e-6) and torch.allclose(l_f, l_m, rtol=1e-6), (it_f, it_m)
+    assert float(it_f[0]) > 0 and float(g_m.abs().max()) > 0
+    worst = []
+    for e in st.entries:
+        sl = slice(e.offset, e.offset + e.numel)
+        if float(g_m[sl].norm()) > 0:
+            worst.append((rel_err(g_f[sl], g_m[sl]), e.name))
+    print("fused vs list-of-maps, worst parameter-gradient differences:", sorted(worst, reverse=True)[:3])
+    assert rel_err(g_f, g_m) < 1e-2
+    head = [w for w in worst if w[1].startswith("detection_head.") and (".cv2.0.2." in w[1] or ".cv3.0.2." in w[1])]
+    assert head and max(head)[0] < 1e-2, head
