@@ -196,8 +196,12 @@ class ConvBiasFn(Function):
         if any(ctx.needs_input_grad):
             st.note_use(weight, bias)
         # cfg["out"]: a caller-provided output view (the Detect head's closing convs write straight into the scale-major
-        # prediction buffers the loss kernels read: no torch.cat)
-        out = K.conv_fprop(geom, x0, st.w_fprop(weight), cout, bias=bias, out=cfg.get("out"),
+        # prediction buffers the loss kernels read: no torch.cat).  It must NOT stay reachable from ctx: output -> grad_fn ->
+        # ctx -> output would be a reference cycle that keeps the whole autograd graph of a step (and its AccumulateGrad
+        # nodes, bound to the stream they were created on) alive until the next garbage collection -- a later CUDA-graph
+        # capture then fails with "dependency created on uncaptured work in another stream".
+        cfg = dict(cfg)
+        out = K.conv_fprop(geom, x0, st.w_fprop(weight), cout, bias=bias, out=cfg.pop("out", None),
                            out_dtype=cfg.get("out_dtype", torch.bfloat16))
         ctx.cfg = cfg
         ctx.save_for_backward(x0, weight, bias)

@@ -99,6 +99,10 @@ class ParamStore:
         device = torch.device(device)
         if device.type != "cuda" and not getattr(K, "_EMULATED", False):
             raise K._lib.SnnKernelError("parameters must live on a CUDA device (no CPU fallback)")
+        if device.type == "cuda" and device.index is None:
+            # "cuda" and "cuda:0" must name the same store: a mismatch would silently rebuild the flat buffers (zeroed
+            # bf16 operand copies, stale DDP bucket views)
+            device = torch.device("cuda", torch.cuda.current_device())
         if self.flat_p is not None and self.device == device and all(self._attached(e) for e in self.entries):
             return self
         old_m, old_v = self.flat_m, self.flat_v

@@ -150,6 +150,7 @@ def test_full_width_training_step_vs_oracle(neuron, B, T, HW):
         e2e, forced = [], []
         blocks = dict(net.temporal_unet.named_modules())
         st = store_for(net, DEV)
+        st.refresh_operands()
         for name, s_list in rec_s.items():
             s_o, u_o = torch.stack(s_list), torch.stack(rec_u[name])                 # [T,B,C,H,W]
             sp = rec[name]
