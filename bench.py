@@ -3,6 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W]                 # our arm (1 GPU, or under torchrun: N ranks)
     python bench.py --impl reference [--steps K] [--warmup W]           # CPU arm: oracle port of the reference path
+    python bench.py --impl eager-gpu                                    # GPU comparator: the oracle modules in PyTorch eager
     python bench.py --microbench lif                                    # BASELINE.json configs[3] LIF sweep (GB/s)
 
 A "step" is one training step of the reference (train.py:58-80): T-frame unroll with state carry, detection loss on
@@ -12,8 +13,12 @@ BASELINE.json configs[1] per GPU (default SNN detector, T=4, batch 64, 256x256 f
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs already in HBM), `e2e` = the same metric
 through the public API with pinned HOST buffers (H2D of the frames + labels and a D2H read of the loss every step),
-`roofline` = the dominant kernel timed live with CUDA events inside the timed region, `cpu_baseline` = the oracle
-port of the reference path timed on this box's host cores (N=1 only).
+`kernels` / `roofline` = per-kernel durations INSIDE the replayed CUDA graph (CUPTI activity records of extra replays
+right after the timed region, matched launch by launch to the ABI calls recorded at capture; fallback: CUDA events
+around eager launches), `cfg3` = the same measurement on BASELINE.json configs[2] (T=8, 512x512, batch 16/GPU) so that
+the scaling runs carry it at every N, `ranks_in_lockstep` = every rank holds bit-identical parameters after the timed
+steps, `cpu_baseline` = the oracle port of the reference path on this box's host cores and `gpu_eager_baseline` = the
+same oracle modules in PyTorch eager on this GPU (N=1 only), `lif_microbench` = configs[3] sweep with its own clocks.
 """
 import argparse
 import json
@@ -38,7 +43,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager-gpu"])
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3], help="BASELINE.json configs index + 1")
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
     ap.add_argument("--neuron", default="lif", choices=["lif", "silu"])
@@ -48,23 +53,28 @@ def parse():
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event accounting")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph")
     ap.add_argument("--ref-batch", type=int, default=2, help="sequences per step of the CPU arm (bounded sample)")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the configs[2] (T=8, 512x512) sub-record")
+    ap.add_argument("--no-lif", action="store_true", help="skip the configs[3] LIF sweep sub-record")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager GPU comparator")
     return ap.parse_args()
 
 
-def workload(args):
-    if args.config == 1:
+def workload(args, cfg=None):
+    cfg = args.config if cfg is None else cfg
+    if cfg == 1:
         B, T, HW = 2, 4, 256
-    elif args.config == 2:
+    elif cfg == 2:
         B, T, HW = 64, 4, 256
     else:
         B, T, HW = 16, 8, 512
-    if args.batch:
+    if args.batch and cfg == args.config:
         B = args.batch
     return B, T, HW
 
 
-def workload_name(args, B, T, HW):
-    return (f"BASELINE.json configs[{args.config - 1}]: default SNN detector ({args.neuron} neurons), T={T}, batch {B}/GPU, "
+def workload_name(args, B, T, HW, cfg=None):
+    cfg = args.config if cfg is None else cfg
+    return (f"BASELINE.json configs[{cfg - 1}]: default SNN detector ({args.neuron} neurons), T={T}, batch {B}/GPU, "
             f"synthetic {HW}x{HW} RGB frames, one train step (fwd + loss + bwd + clip + AdamW + OneCycle)")
 
 
@@ -167,9 +177,154 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def summarize_profile(records, steps, pk):
-    """records: (name, work, ev0, ev1) of every ABI call in the timed region -> per-entry-point totals."""
-    agg = {}
+# ------------------------------------------------------------------------------------------------
+# GPU comparator: the same oracle modules (= the reference's classes restated, oracle/) in PyTorch eager on this GPU
+# ------------------------------------------------------------------------------------------------
+def gpu_eager_run(T, HW, batch, steps, warmup, neuron, dev):
+    """Reference step semantics (train.py:58-80) on the GPU through stock PyTorch kernels (cuDNN convs, eager autograd,
+    torch.optim.AdamW): fp32 with torch's defaults (TF32 convolutions) and bf16 autocast, channels_last.  Stand-in extractor /
+    restated head + loss as in the CPU arm.  Test infrastructure timed as a baseline -- never on the product path."""
+    import torch
+    from oracle import model_oracle as MO
+    out = {}
+    frames, labels = MO.synthetic_batch(batch, T, HW, HW, nc=NUM_CLASSES, seed=42)
+    frames, labels = frames.to(dev), labels.to(dev)
+    for mode in ("fp32", "bf16_autocast"):
+        torch.manual_seed(42)
+        model = MO.OracleYOLOTemporalUNet(num_classes=NUM_CLASSES, hyp=HYP, neuron=neuron)
+        MO.initialize_model_oracle(model)
+        model = model.to(dev).to(memory_format=torch.channels_last).train()
+        loss_fn, opt, sched = MO.make_reference_trainer(model, total_steps=1000, max_lr=MAX_LR, weight_decay=WEIGHT_DECAY)
+
+        def step():
+            if mode == "fp32":
+                return MO.reference_train_step(model, loss_fn, opt, sched, frames, labels)
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                hidden = None
+                for t in range(frames.shape[1]):
+                    preds, hidden = model(frames[:, t], hidden)
+            b = {"batch_idx": labels[:, 0], "cls": labels[:, 1], "bboxes": labels[:, 2:]}
+            loss, items = loss_fn([p.float() for p in preds], b)
+            loss.sum().backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=10.0)
+            opt.step()
+            sched.step()
+            return loss, items, None
+
+        try:
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {"value": batch / (ms * 1e-3), "ms_per_step": ms}
+        except Exception as e:          # e.g. an op without a bf16 autocast path: report, do not hide
+            out[mode] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        del model, opt, sched, loss_fn
+        torch.cuda.empty_cache()
+    out.update(unit="images/s", kind="port", batch=batch,
+               what=f"oracle modules (reference classes restated) in PyTorch eager on this GPU, channels_last, per-frame loop, torch AdamW; "
+                    f"{steps} timed + {warmup} warm-up steps of {batch} sequences (T={T}, {HW}x{HW})")
+    return out
+
+
+def run_gpu_eager(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.cuda.set_device(0)
+    B, T, HW = workload(args)
+    r = gpu_eager_run(T, HW, B, max(2, min(args.steps, 5)), 2, args.neuron, torch.device("cuda", 0))
+    best = max((v for v in (r.get("fp32"), r.get("bf16_autocast")) if v and "value" in v), key=lambda v: v["value"])
+    print(json.dumps({"impl": "eager-gpu", "metric": "train images/sec", "value": best["value"], "unit": "images/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": best["ms_per_step"], "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32/bf16", "data": "synthetic",
+                      "config": {"workload": workload_name(args, B, T, HW)}, "gpu_eager_baseline": r, "gpu_launches": 0}), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-kernel accounting
+# ------------------------------------------------------------------------------------------------
+# ABI entry point -> substrings of the GPU kernels it launches, in launch order (memsets are not kernels)
+EXPECT = {
+    "snn_conv_fprop": ["conv_gemm_kernel"], "snn_conv_fprop_stats": ["conv_gemm_kernel"], "snn_conv_dgrad": ["conv_gemm_kernel"],
+    "snn_conv_wgrad": ["wgrad_gemm_kernel"], "snn_bn_finalize_partials": ["bn_finalize_partials_kernel"],
+    "snn_bn_stats_from_partials": ["bn_stats_from_partials_kernel"], "snn_bn_stats": ["bn_stats_kernel", "bn_stats_from_partials_kernel"],
+    "snn_bn_finalize": ["bn_finalize_kernel"], "snn_bn_act_fwd": ["bn_act_fwd_kernel"], "snn_bn_act_bwd2": ["bwd2_kernel"],
+    "snn_bn_act_bwd": ["bn_act_bwd_kernel"], "snn_bn_bwd_dx": ["bn_bwd_finalize_kernel", "bn_bwd_dx_kernel"],
+    "snn_lstm_gates_fwd": ["lstm_gates_fwd_kernel"], "snn_lstm_gates_bwd": ["lstm_gates_bwd_kernel"],
+    "snn_colsum_bf16": ["colsum_bf16_kernel"], "snn_dw3x3_fprop": ["dw3x3_fwd_kernel"], "snn_dw3x3_dgrad": ["dw3x3_dgrad_kernel"],
+    "snn_dw3x3_wgrad": ["dw3x3_wgrad_kernel"], "snn_space_to_depth8": ["s2d8_kernel"], "snn_space_to_depth8_u8": ["s2d8_u8_kernel"],
+    "snn_grad_sumsq": ["sumsq_kernel"], "snn_adamw_step": ["adamw_kernel", "step_advance_kernel"],
+    "snn_detect_assign_loss_fwd": ["detect_decode_kernel", "tal_metric_topk_kernel", "tal_resolve_kernel", "tal_targets_kernel",
+                                   "detect_loss_fwd_kernel"],
+    "snn_detect_loss_bwd_rows": ["detect_loss_bwd_kernel"], "snn_weight_prep": ["weight_prep_kernel"],
+    "snn_bilinear_resize": ["bilinear_"], "snn_nhwc_pad_crop": ["pad_crop_kernel"],
+}
+
+
+def cupti_graph_accounting(replay_fn, trace, replays):
+    """Kernel durations INSIDE the replayed graph: CUPTI activity records (torch.profiler) of `replays` extra replays,
+    matched in launch order to the ABI calls recorded while the graph was captured.  Returns
+    (agg {abi name: {ms, calls, flop, byte}}, shapes {(abi name, tag): {...}}, other {kernel name: ms}, total kernel ms)
+    or None if CUPTI is unavailable / the sequence cannot be matched."""
+    import torch
+    try:
+        import torch.profiler as tp
+        with tp.profile(activities=[tp.ProfilerActivity.CUDA, tp.ProfilerActivity.CPU]) as prof:
+            for _ in range(replays):
+                replay_fn()
+            torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and not e.name.lower().startswith(("memcpy", "memset"))]
+    except Exception as e:
+        return None, f"torch.profiler failed: {type(e).__name__}: {e}"[:200]
+    if not evs:
+        return None, "no CUDA kernel records from torch.profiler (CUPTI unavailable)"
+    evs.sort(key=lambda e: e.time_range.start)
+    seq = [(name, work, sub, k == 0) for name, work in trace for k, sub in enumerate(EXPECT.get(name, []))]
+    agg, shapes, other = {}, {}, {}
+    j, total = 0, 0.0
+    for _ in range(replays):
+        for name, work, sub, first in seq:
+            while j < len(evs) and sub not in evs[j].name:
+                d = evs[j].time_range.elapsed_us() * 1e-3
+                other[evs[j].name[:80]] = other.get(evs[j].name[:80], 0.0) + d
+                total += d
+                j += 1
+            if j >= len(evs):
+                return None, f"kernel records ran out while matching {name} ({sub}): capture trace and replay differ"
+            d = evs[j].time_range.elapsed_us() * 1e-3
+            j += 1
+            total += d
+            a = agg.setdefault(name, dict(ms=0.0, calls=0, flop=0.0, byte=0.0))
+            a["ms"] += d
+            if first:
+                a["calls"] += 1
+                if work:
+                    a[work[0]] += work[1]
+            if work and len(work) > 2:
+                sh = shapes.setdefault((name, work[2]), dict(ms=0.0, calls=0, amount=0.0, kind=work[0]))
+                sh["ms"] += d
+                if first:
+                    sh["calls"] += 1
+                    sh["amount"] += work[1]
+    while j < len(evs):
+        d = evs[j].time_range.elapsed_us() * 1e-3
+        other[evs[j].name[:80]] = other.get(evs[j].name[:80], 0.0) + d
+        total += d
+        j += 1
+    return (agg, shapes, other, total), None
+
+
+def events_accounting(records):
+    agg, shapes = {}, {}
     for name, work, e0, e1 in records:
         ms = e0.elapsed_time(e1)
         a = agg.setdefault(name, dict(ms=0.0, calls=0, flop=0.0, byte=0.0))
@@ -177,51 +332,49 @@ def summarize_profile(records, steps, pk):
         a["calls"] += 1
         if work:
             a[work[0]] += work[1]
-    shapes = {}
-    for name, work, e0, e1 in records:
         if work and len(work) > 2:
-            a = shapes.setdefault((name, work[2]), dict(ms=0.0, calls=0, amount=0.0, kind=work[0]))
-            a["ms"] += e0.elapsed_time(e1); a["calls"] += 1; a["amount"] += work[1]
+            sh = shapes.setdefault((name, work[2]), dict(ms=0.0, calls=0, amount=0.0, kind=work[0]))
+            sh["ms"] += ms; sh["calls"] += 1; sh["amount"] += work[1]
+    return agg, shapes
+
+
+def summarize(agg, shapes, steps, pk):
     by_shape = []
     for (name, tag), a in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:40]:
         rate = a["amount"] / (a["ms"] * 1e-3)
         by_shape.append({"kernel": name, "shape": tag, "ms_per_step": round(a["ms"] / steps, 4), "calls_per_step": a["calls"] / steps,
                          ("tflops" if a["kind"] == "flop" else "gbs"): round(rate / (1e12 if a["kind"] == "flop" else 1e9), 1)})
-    summarize_profile.by_shape = by_shape
     out = {}
     for name, a in agg.items():
         d = dict(ms_per_step=a["ms"] / steps, calls_per_step=a["calls"] / steps)
         if a["flop"]:
             d["tflops"] = a["flop"] / (a["ms"] * 1e-3) / 1e12
             d["frac_of_bf16_sustained"] = d["tflops"] / pk["tf_sust"]
+            d["frac_of_bf16_burst"] = d["tflops"] / pk["tf_burst"]
         if a["byte"]:
             d["gbs"] = a["byte"] / (a["ms"] * 1e-3) / 1e9
             d["frac_of_hbm"] = d["gbs"] / pk["hbm"]
         out[name] = d
-    return out, agg
+    return out, by_shape
 
 
-def run_ours(args):
+# ------------------------------------------------------------------------------------------------
+# our arm: one configuration
+# ------------------------------------------------------------------------------------------------
+def measure_config(args, cfg_idx, dev, rank, local, world, pk, full):
+    """Device-resident throughput, end-to-end throughput, per-kernel accounting of one BASELINE.json config.
+    `full`: also e2e + kernel accounting (the main line); the cfg3 sub-record keeps e2e but skips the kernel table."""
     import torch
     import torch.distributed as dist
     from snn_object_detectionddp_b200 import _lib
+    from snn_object_detectionddp_b200.data import DevicePrefetcher, synthetic_batch
     from snn_object_detectionddp_b200.model import YOLOTemporalUNet
     from snn_object_detectionddp_b200.trainer import Trainer
     from snn_object_detectionddp_b200.weight_initialization import initialize_model
-    from snn_object_detectionddp_b200.data import synthetic_batch
 
-    rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.lib()        # fail loudly if libsnnb200.so is missing: there is no fallback
-    B, T, HW = workload(args)
-    pk = peaks()
-
+    B, T, HW = workload(args, cfg_idx)
     torch.manual_seed(42)
-    model = YOLOTemporalUNet(num_classes=NUM_CLASSES, yolo_model_name="yolo11m.pt", use_conv_lstm=True, hyp=HYP,
-                             neuron=args.neuron)
+    model = YOLOTemporalUNet(num_classes=NUM_CLASSES, yolo_model_name="yolo11m.pt", use_conv_lstm=True, hyp=HYP, neuron=args.neuron)
     initialize_model(model)
     trainer = Trainer(model, max_lr=MAX_LR, weight_decay=WEIGHT_DECAY, total_steps=1000, device=dev)
     frames_cpu, labels_cpu = synthetic_batch(B, T, HW, HW, nc=NUM_CLASSES, seed=42 + rank)
@@ -238,20 +391,19 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ----------------
-    launches0 = _lib.launch_count
-    for _ in range(max(args.warmup, 3)):                  # >= 3: two eager steps, then the graph capture + first replay
+    trace = None
+    for i in range(max(args.warmup, 3)):                  # >= 3: two eager steps, then the graph capture + first replay
+        if graphed and i == 2:
+            _lib.trace = trace = []                       # the ABI calls recorded INTO the graph = launches of one replay
         step_fn(frames, batch_dev)
+        _lib.trace = None
     barrier()
-    calls_per_step = None
-    if graphed:                                           # ABI calls recorded into the graph = launches per replay
-        l0 = _lib.launch_count
-        trainer.train_step(frames, batch_dev)
-        calls_per_step = _lib.launch_count - l0
-        barrier()
+    if graphed and (trainer._graph is None or trainer._graph_failed):
+        raise RuntimeError("CUDA-graph capture of the training step failed; rerun with --no-graph to time eager launches")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    records = None if (args.no_profile or graphed) else []
+    records = None if (args.no_profile or graphed or not full) else []
     _lib.profile = records
     launches0 = _lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -261,20 +413,63 @@ def run_ours(args):
     ev1.record()
     barrier()
     _lib.profile = None
-    launches = calls_per_step * args.steps if graphed else _lib.launch_count - launches0
+    launches = len(trace) * args.steps if graphed else _lib.launch_count - launches0
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
     last_loss = [float(v) for v in items]
 
+    # ---------------- per-kernel accounting + roofline of the dominant kernel ----------------
+    # (done right after the timed region, before the e2e leg re-captures the graph for uint8 host frames)
+    res = dict(B=B, T=T, HW=HW, value=world * B * args.steps / (ms_total * 1e-3), ms_per_step=ms_total / args.steps, e2e=None, clocks=None,
+               launches=launches, last_loss=last_loss, lockstep=None, graphed=graphed, kernels=None, by_shape=None, roofline=None,
+               timing=None, kernel_ms_sum=None, other_kernels=None)
+    if full and not args.no_profile:
+        acc, timing, kernel_sum, other = None, None, None, None
+        if graphed:
+            got, why = cupti_graph_accounting(lambda: trainer.train_step_graphed(frames, batch_dev), trace, 3)
+            if got is not None:
+                agg, shapes, other_d, total = got
+                acc, timing, kernel_sum = (agg, shapes, 3), "CUPTI activity records of 3 extra replays of the captured graph, matched to the ABI calls in launch order", total / 3
+                other = {k: round(v / 3, 4) for k, v in sorted(other_d.items(), key=lambda kv: -kv[1])[:12]}
+            else:
+                timing = "fallback to CUDA events around eager launches: " + why
+        if acc is None:
+            records = records if records else []
+            if not records:
+                _lib.profile = records
+                torch.cuda._sleep(int(1.5e8))            # hold the stream ~75 ms so the launches below queue up back to back
+                for _ in range(args.steps):
+                    trainer.train_step(frames, batch_dev)
+                barrier()
+                _lib.profile = None
+            agg, shapes = events_accounting(records)
+            acc, kernel_sum = (agg, shapes, args.steps), sum(a["ms"] for a in agg.values()) / args.steps
+            timing = (timing or "") + " CUDA events around every ABI call of an eager pass"
+        agg, shapes, nsteps = acc
+        res["kernels"], res["by_shape"] = summarize(agg, shapes, nsteps, pk)
+        res["timing"], res["kernel_ms_sum"], res["other_kernels"] = timing, kernel_sum, other
+        name, a = max(agg.items(), key=lambda kv: kv[1]["ms"])
+        tr_path = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from the committed ncu capture
+        traffic = json.load(open(tr_path)).get(name) if os.path.isfile(tr_path) else None
+        if a["flop"]:
+            ach = a["flop"] / (a["ms"] * 1e-3) / 1e12
+            res["roofline"] = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                               "frac": ach / pk["tf_burst"], "frac_of_sustained": ach / pk["tf_sust"], "frac_of_nominal_2250": ach / 2250.0,
+                               "traffic": traffic, "peak_source": pk["src"] + ", burst bf16 (the timed region is a fraction of a second at max clocks)",
+                               "share_of_step": a["ms"] / nsteps / (ms_total / args.steps), "launches_per_step": a["calls"] / nsteps}
+        else:
+            ach = a["byte"] / (a["ms"] * 1e-3) / 1e9
+            res["roofline"] = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                               "frac_of_nominal_8000": ach / 8000.0, "traffic": traffic, "peak_source": pk["src"],
+                               "share_of_step": a["ms"] / nsteps / (ms_total / args.steps), "launches_per_step": a["calls"] / nsteps}
     # ---------------- end to end through the public API with host buffers ----------------
     e2e = None
     if not args.no_e2e:
         # host frames as the dataset decodes them: uint8 RGB (reference dataset.py:139-152 converts to fp32 / 255 on the HOST and
         # ships 4x the bytes); the division runs in the frame packer kernel, bit-identical to the host's
         frames_u8 = (frames_cpu * 255.0).round().clamp_(0, 255).to(torch.uint8)
-        from snn_object_detectionddp_b200.data import DevicePrefetcher
         host_batches = [(frames_u8.clone().pin_memory(),
                          tuple(t.pin_memory() for t in trainer.prepare_batch(labels_cpu, B, max_boxes=MAXB)["padded"])) for _ in range(2)]
         loss_host = torch.zeros(args.steps + args.warmup, 3).pin_memory()
@@ -300,58 +495,58 @@ def run_ours(args):
         ems = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        h2d_bytes = pf.bytes_per_batch()
-        e2e = {"value": world * B * args.steps / (float(ems) * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
+        e2e = {"value": world * B * args.steps / (float(ems) * 1e-3), "unit": "images/s", "h2d_bytes_per_step": pf.bytes_per_batch(),
                "d2h_bytes_per_step": 12, "ms_per_step": float(ems) / args.steps,
                "api": ("Trainer.train_step_graphed" if graphed else "Trainer.train_step")
                       + " fed by data.DevicePrefetcher: double-buffered pinned host frames (uint8 [B,T,3,H,W], /255 on the device)"
                         " + padded labels, copied on a side stream"}
+    clocks = sampler.stop() if rank == 0 else None          # sampled over the timed regions (device-resident, accounting replays, e2e)
+    res["e2e"], res["clocks"] = e2e, clocks
 
-    clocks = sampler.stop() if rank == 0 else None          # sampled over both timed regions (device-resident + e2e)
+    # ---------------- every rank holds the same parameters after the timed steps ----------------
+    lockstep = None
+    if world > 1:
+        st = trainer.store
+        chk = torch.stack([st.flat_p.double().sum(), st.flat_p.double().abs().sum(), st.flat_m.double().abs().sum()])
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        lockstep = bool(all(torch.equal(allc[0], c) for c in allc[1:]))
+    res["lockstep"] = lockstep
 
-    # ---------------- per-kernel accounting + roofline of the dominant kernel ----------------
-    roofline, kernels_summary = None, None
-    if graphed and not args.no_profile:
-        # a replayed graph has no per-launch events: time the SAME kernels in an instrumented eager pass of the same
-        # K steps right after the timed region (kernel durations do not depend on how they were launched)
-        records = []
-        _lib.profile = records
-        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        pe0.record()
-        for _ in range(args.steps):
-            trainer.train_step(frames, batch_dev)
-        pe1.record()
-        barrier()
-        _lib.profile = None
-        eager_ms_total = pe0.elapsed_time(pe1)
-    else:
-        eager_ms_total = ms_total
-    if records:
-        kernels_summary, agg = summarize_profile(records, args.steps, pk)
-        top = max(agg.items(), key=lambda kv: kv[1]["ms"])
-        name, a = top
-        if a["flop"]:
-            ach = a["flop"] / (a["ms"] * 1e-3) / 1e12
-            roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                        "frac": ach / pk["tf_sust"], "frac_of_nominal_2250": ach / 2250.0, "traffic": None,
-                        "peak_source": pk["src"] + ", sustained bf16",
-                        "share_of_step": a["ms"] / ms_total, "launches_per_step": a["calls"] / args.steps}
-        else:
-            ach = a["byte"] / (a["ms"] * 1e-3) / 1e9
-            roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": ach / pk["hbm"], "frac_of_nominal_8000": ach / 8000.0, "traffic": None, "peak_source": pk["src"],
-                        "share_of_step": a["ms"] / ms_total, "launches_per_step": a["calls"] / args.steps}
-        tr = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from the committed ncu capture
-        if os.path.isfile(tr):
-            roofline["traffic"] = json.load(open(tr)).get(name)
+    res["graph_active"] = bool(graphed and trainer._graph is not None and not trainer._graph_failed)
+    trainer._graph = None
+    del trainer, model
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from snn_object_detectionddp_b200 import _lib
+
+    rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()        # fail loudly if libsnnb200.so is missing: there is no fallback
+    pk = peaks()
+    main = measure_config(args, args.config, dev, rank, local, world, pk, full=True)
+    cfg3 = None
+    if args.config != 3 and not args.no_cfg3:
+        r3 = measure_config(args, 3, dev, rank, local, world, pk, full=False)
+        cfg3 = {"workload": workload_name(args, r3["B"], r3["T"], r3["HW"], 3), "value": r3["value"], "unit": "images/s",
+                "ms_per_step": r3["ms_per_step"], "per_gpu_batch": r3["B"], "T": r3["T"], "frames_per_s": r3["value"] * r3["T"],
+                "e2e": r3["e2e"], "clocks": r3["clocks"], "gpu_launches": r3["launches"], "cuda_graph_active": r3["graph_active"],
+                "ranks_in_lockstep": r3["lockstep"], "last_loss_items": r3["last_loss"]}
 
     def shutdown():
-        """Leave without waiting on NCCL teardown: the captured graph still references the communicator's kernels and
-        destroy_process_group() was seen to block for minutes on the 2-GPU box after the result line was out."""
+        """Leave without waiting on NCCL teardown: destroy_process_group() was seen to block for minutes on the 2-GPU box
+        after the result line was out (captured graphs had referenced the communicator's kernels)."""
         sys.stdout.flush()
         sys.stderr.flush()
         if world > 1:
-            trainer._graph = None
             torch.cuda.synchronize()
             dist.barrier()
             torch.cuda.synchronize()
@@ -363,24 +558,36 @@ def run_ours(args):
         shutdown()
         return
 
-    cpu_baseline = None
+    B, T, HW = main["B"], main["T"], main["HW"]
+    cpu_baseline = gpu_eager = lif = None
+    if world == 1 and not args.no_gpu_eager:
+        gpu_eager = gpu_eager_run(T, HW, B, 3, 2, args.neuron, dev)
+    if world == 1 and not args.no_lif:
+        s2 = ClockSampler(local)
+        s2.start()
+        rows = lif_sweep(pk, quick=True)
+        lif = {"config": "BASELINE.json configs[3]: T in {4,8,16} x (C, HxW) in {(64,64^2),(128,64^2),(128,32^2),(256,32^2),(256,16^2),(512,16^2)}, "
+                         "tensors >= 1 GiB (L2 is 126 MB), algorithmic bytes: fwd 6.125, bwd 14 (two recompute passes) per neuron-timestep",
+               "hbm_peak_gbs": pk["hbm"], "rows": rows, "clocks": s2.stop(),
+               "fwd_frac_min": min(r["fwd_frac"] for r in rows), "bwd_frac_min": min(r["bwd_frac"] for r in rows)}
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(T, HW, args.ref_batch, 3, 1, args.neuron)
         cpu_baseline = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     line = {
-        "metric": "train images/sec", "value": world * B * args.steps / (ms_total * 1e-3), "unit": "images/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "metric": "train images/sec", "value": main["value"], "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(args, B, T, HW),
-                   "per_gpu_batch": B, "T": T, "frames_per_s": world * B * T * args.steps / (ms_total * 1e-3),
+                   "per_gpu_batch": B, "T": T, "frames_per_s": main["value"] * T,
                    "l2": "per-step working set (240 MB bf16 weights + GBs of activations) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world}", "feature_extractor": "stand-in frozen pyramid (YOLO11m weights unobtainable offline)"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "cuda_graph_active": bool(graphed and trainer._graph is not None and not trainer._graph_failed),
-        "kernels": kernels_summary, "kernels_by_shape": getattr(summarize_profile, "by_shape", None), "last_loss_items": last_loss, "cuda_graph": graphed,
-        "kernel_ms_sum_per_step": (sum(v["ms_per_step"] for v in kernels_summary.values()) if kernels_summary else None),
-        "eager_instrumented_ms_per_step": (eager_ms_total / args.steps if kernels_summary else None),
+        "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["launches"], "roofline": main["roofline"],
+        "cpu_baseline": cpu_baseline, "gpu_eager_baseline": gpu_eager, "cfg3": cfg3, "ranks_in_lockstep": main["lockstep"],
+        "cuda_graph_active": main["graph_active"], "cuda_graph": main["graphed"],
+        "kernel_timing": main["timing"], "kernels": main["kernels"], "kernels_by_shape": main["by_shape"],
+        "kernel_ms_sum_per_step": main["kernel_ms_sum"], "other_kernels_ms_per_step": main["other_kernels"],
+        "lif_microbench": lif, "last_loss_items": main["last_loss"],
     }
     print(json.dumps(line), flush=True)
     shutdown()
@@ -389,11 +596,10 @@ def run_ours(args):
 # ------------------------------------------------------------------------------------------------
 # LIF microbench (BASELINE.json configs[3])
 # ------------------------------------------------------------------------------------------------
-def run_lif_microbench(args):
+def lif_sweep(pk, quick=False):
     import torch
     from snn_object_detectionddp_b200 import kernels as K
-    pk = peaks()
-    torch.cuda.set_device(0)
+    from snn_object_detectionddp_b200._lib import call, ptr, stream_ptr
     rows = []
     for T in (4, 8, 16):
         for C, HWs in ((64, 64), (128, 64), (128, 32), (256, 32), (256, 16), (512, 16)):
@@ -405,7 +611,7 @@ def run_lif_microbench(args):
             gs = torch.randn(T * Bn, HWs, HWs, C, device="cuda").to(torch.bfloat16)
             n = y.numel()
 
-            def timeit(fn, reps=5):
+            def timeit(fn, reps=3 if quick else 5):
                 fn(); torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -416,12 +622,12 @@ def run_lif_microbench(args):
 
             bnb = torch.full((C,), 0.2, device="cuda")
             dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-            from snn_object_detectionddp_b200._lib import call, ptr, stream_ptr
             red = torch.zeros(T, 2, C, device="cuda")
             dy = torch.empty_like(gs)
             P = n // (T * C)
             a = (ptr(y), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(bnb), None, ptr(gs), None, ptr(red), ptr(dy), None,
                  ptr(dg), ptr(db), T, P, C, 0.5, 1.0, 2.0)
+            K.require_cuda(y)
             f_ms = timeit(lambda: K.bn_act_fwd(0, y, scale, shift, T))
             r_ms = timeit(lambda: call("snn_bn_act_bwd2", 0, 0, *a, stream_ptr()))
             d_ms = timeit(lambda: call("snn_bn_act_bwd2", 1, 0, *a, stream_ptr()))
@@ -435,7 +641,17 @@ def run_lif_microbench(args):
     for r in rows:
         r["fwd_frac"], r["bwd_frac"] = r["fwd_gbs"] / pk["hbm"], r["bwd_train_gbs"] / pk["hbm"]
         r["fwd_frac_of_nominal_8000"], r["bwd_frac_of_nominal_8000"] = r["fwd_gbs"] / 8000.0, r["bwd_train_gbs"] / 8000.0
-    print(json.dumps({"microbench": "lif", "hbm_peak_gbs": pk["hbm"], "peak_source": pk["src"], "rows": rows}), flush=True)
+    return rows
+
+
+def run_lif_microbench(args):
+    import torch
+    pk = peaks()
+    torch.cuda.set_device(0)
+    s = ClockSampler(0)
+    s.start()
+    rows = lif_sweep(pk)
+    print(json.dumps({"microbench": "lif", "hbm_peak_gbs": pk["hbm"], "peak_source": pk["src"], "rows": rows, "clocks": s.stop()}), flush=True)
 
 
 if __name__ == "__main__":
@@ -444,5 +660,7 @@ if __name__ == "__main__":
         run_lif_microbench(a)
     elif a.impl == "reference":
         run_reference(a)
+    elif a.impl == "eager-gpu":
+        run_gpu_eager(a)
     else:
         run_ours(a)

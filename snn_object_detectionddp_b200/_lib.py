@@ -114,6 +114,8 @@ def stream_ptr():
 
 
 profile = None    # when set to a list, every call is bracketed by CUDA events: (name, work, ev_start, ev_end)
+trace = None      # when set to a list, every call appends (name, work): the launch sequence of a step (bench.py matches it
+                  # against the CUPTI kernel records of a replayed CUDA graph)
 
 
 def call(name, *args, work=None):
@@ -133,6 +135,8 @@ def call(name, *args, work=None):
     if rc != 0:
         raise SnnKernelError(f"{name} failed (rc={rc}): {lib().snn_last_error().decode()}")
     launch_count += 1
+    if trace is not None:
+        trace.append((name, work))
     if profile is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record(torch.cuda.current_stream(dev))
