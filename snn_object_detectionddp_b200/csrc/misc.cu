@@ -265,10 +265,9 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 }
 
 __global__ void __launch_bounds__(256)
-adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              __nv_bfloat16* __restrict__ shadow, long long n4, const float* __restrict__ hp_table,
-             const double* __restrict__ sumsq, float* __restrict__ gnorm_out, const int* __restrict__ step_ptr, int n_rows,
-             int zero_grad) {
+             const double* __restrict__ sumsq, float* __restrict__ gnorm_out, const int* __restrict__ step_ptr, int n_rows) {
     // row of the tabulated schedule: picked by a DEVICE step counter so a captured CUDA graph advances on replay
     const float* hp = hp_table + (step_ptr ? (size_t)min(*step_ptr, n_rows - 1) * 8 : 0);
     const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], bc1 = hp[5], bc2 = hp[6], max_norm = hp[7];
@@ -281,10 +280,7 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
     const float rsq_bc2 = 1.f / sqrtf(bc2);
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
         float4 pp = reinterpret_cast<float4*>(p)[i];
-        const float4 gg = reinterpret_cast<const float4*>(g)[i];
-        // zero_grad: the gradient is consumed here, leave it zeroed for the next step's accumulating wgrad kernels
-        // (replaces optimizer.zero_grad() of train.py:61 = a separate 481 MB fill at the start of every step)
-        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
         float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
         float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w}, ma[4] = {mm.x, mm.y, mm.z, mm.w},
               va[4] = {vv.x, vv.y, vv.z, vv.w};
@@ -330,8 +326,12 @@ int launch_adamw(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, 
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, shadow, n4, hp, sumsq, gnorm_out, step_ptr, n_rows, zero_grad);
+    adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, shadow, n4, hp, sumsq, gnorm_out, step_ptr, n_rows);
     SNN_CUDA_OK(cudaGetLastError());
+    // zero_grad: the gradient has been consumed; leave it zeroed for the next step's accumulating wgrad kernels
+    // (optimizer.zero_grad() of train.py:61).  A memset node right behind the kernel: 67 us for 481 MB.  Storing the zeros
+    // from inside the kernel (to the line it has just loaded) was measured 4x slower for the WHOLE pass (0.58 -> 2.35 ms).
+    if (zero_grad) SNN_CUDA_OK(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)n, st));
     if (step_ptr) step_advance_kernel<<<1, 1, 0, st>>>(step_ptr);
     return check_cuda(cudaGetLastError(), "adamw_kernel");
 }

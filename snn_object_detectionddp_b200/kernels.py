@@ -362,7 +362,7 @@ def adamw_step(p, g, m, v, shadow, hp, sumsq, gnorm_out=None, step=None, zero_gr
     n_rows = hp.shape[0] if (step is not None and hp.dim() == 2) else 1
     call("snn_adamw_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), p.numel(), ptr(hp), ptr(sumsq), ptr(gnorm_out),
          ptr(step), n_rows, int(bool(zero_grad)), stream_ptr(),
-         work=("byte", (28.0 + (2.0 if shadow is not None else 0.0) + (4.0 if zero_grad else 0.0)) * p.numel()))
+         work=("byte", (28.0 + (2.0 if shadow is not None else 0.0)) * p.numel()))
 
 
 # ---------------------------------------------------------------------------------------------

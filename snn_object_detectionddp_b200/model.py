@@ -254,22 +254,53 @@ def _pack_hidden(state, kind):
 
 
 # ----------------------------------------------------------------------------------------------
+def _load_ultralytics_model(model_name):
+    """The reference's backbone (model.py:78: `YOLO(model_name).model`) when the `ultralytics` package AND the weights file
+    are obtainable; None otherwise (offline image: neither is)."""
+    try:
+        from ultralytics import YOLO          # un-vendored third party, see SURVEY.md 8c
+    except Exception:
+        return None
+    try:
+        return YOLO(model_name).model
+    except Exception as e:                    # package present but weights missing / download impossible
+        import warnings
+        warnings.warn(f"ultralytics is importable but YOLO({model_name!r}) failed ({type(e).__name__}: {e}); "
+                      "using the stand-in feature pyramid")
+        return None
+
+
 class YOLOFeatureExtractor(nn.Module):
     """Frozen multi-scale feature source (reference model.py:74-98).
 
-    The reference wraps a pretrained ultralytics YOLO11m and returns its three raw 144-channel head maps; neither
-    the package nor the weights can exist offline, and the frozen third-party net is out of scope as a kernel
-    target.  This is the documented STAND-IN: a deterministic, frozen, randomly initialised
-    stride-8/16/32 pyramid with the same interface, run with the same tensor-core kernels under no_grad:
+    backend 'ultralytics' -- what the reference does: `self.model = YOLO(model_name).model`, frozen, always in eval mode,
+        `forward(x)` returns the three raw head inputs of `_, features = self.model(x)` (model.py:88-91).  Used whenever
+        the package and the weights are importable/loadable (backend='auto', the default).  The frozen third-party net
+        runs through its own PyTorch kernels (it is not a kernel target); its NCHW fp32 maps are repacked
+        to the NHWC bf16 layout of the B200 path by one libsnnb200 kernel per level.
+    backend 'standin' -- neither the package nor `yolo11m.pt` can exist offline: a deterministic, frozen, randomly
+        initialised stride-8/16/32 pyramid with the same interface, run with the tensor-core kernels under no_grad:
         pack 8x8 patches -> 1x1 conv 192->128 + SiLU -> [P3 = 1x1 ->144]
         3x3 s2 128->128 + SiLU -> [P4 = 1x1 ->144];  3x3 s2 + SiLU -> [P5 = 1x1 ->144]
     """
     WIDTH = 128
     OUT = 144
 
-    def __init__(self, model_name="yolo11m.pt", freeze=True, seed=1234):
+    def __init__(self, model_name="yolo11m.pt", freeze=True, seed=1234, backend="auto"):
         super().__init__()
+        assert backend in ("auto", "ultralytics", "standin")
         self.model_name = model_name
+        real = _load_ultralytics_model(model_name) if backend in ("auto", "ultralytics") else None
+        if backend == "ultralytics" and real is None:
+            raise RuntimeError("backend='ultralytics' requested but `ultralytics` / the weights are not available")
+        self.backend = "ultralytics" if real is not None else "standin"
+        if real is not None:
+            self.model = real                              # same attribute name as the reference: state_dict keys match
+            if freeze:
+                for p in self.model.parameters():
+                    p.requires_grad = False
+                self.model.eval()
+            return
         g = torch.Generator().manual_seed(seed)
         w, o = self.WIDTH, self.OUT
 
@@ -284,15 +315,28 @@ class YOLOFeatureExtractor(nn.Module):
 
     def train(self, mode=True):          # stays in eval like the reference (model.py:84-86)
         self.training = mode
+        if self.backend == "ultralytics":
+            self.model.eval()
         return self
 
+    @torch.no_grad()
     def get_feature_channels(self, dummy_input_shape=(1, 3, 640, 640)):
-        return [self.OUT] * 3
+        if self.backend == "standin":
+            return [self.OUT] * 3
+        dummy = torch.randn(*dummy_input_shape, device=next(self.model.parameters()).device)     # model.py:94-98
+        _, features = self.model(dummy)
+        return [f.shape[1] for f in features]
 
     @torch.no_grad()
     def forward_seq(self, frames, B, T):
-        """frames fp32 [B,T,3,H,W] (or [B,3,H,W] with T=1) contiguous -> (p3, p4, p5) bf16 NHWC [T*B, ...]."""
+        """frames fp32 in [0,1] or uint8 [B,T,3,H,W] (or [B,3,H,W] with T=1) contiguous -> (p3, p4, p5) bf16 NHWC [T*B, ...]
+        (timestep-major folded batch)."""
         H, W = frames.shape[-2:]
+        if self.backend == "ultralytics":
+            x = frames.reshape(B, T, 3, H, W).transpose(0, 1).reshape(T * B, 3, H, W)
+            x = x.float() / 255.0 if x.dtype == torch.uint8 else x.float()
+            _, features = self.model(x)
+            return tuple(K.nchw_to_nhwc(f.float()) for f in features)
         if H % 8 or W % 8:
             raise ValueError(f"frame size {H}x{W}: H and W must be multiples of 8 (stride-8 patch packer of the stand-in pyramid)")
         x = K.space_to_depth8(frames.contiguous(), B, T)
@@ -311,6 +355,10 @@ class YOLOFeatureExtractor(nn.Module):
                 K.conv_fprop(GEOM_1x1, f5, self.w_p5, self.OUT, out_dtype=bf))
 
     def forward(self, x):
+        if self.backend == "ultralytics":      # reference model.py:88-91, verbatim semantics
+            with torch.no_grad():
+                _, features = self.model(x)
+            return tuple(features)
         feats = self.forward_seq(x, x.shape[0], 1)
         return tuple(_to_nchw_f32(f) for f in feats)
 
@@ -319,17 +367,18 @@ class YOLOFeatureExtractor(nn.Module):
 class YOLOTemporalUNet(nn.Module):
     """Reference model.py:148-211: frozen extractor -> TemporalUNet -> Detect head.
 
-    Extra (additive) constructor arguments: `neuron` ('lif' default | 'silu' | dict with type/beta/v_th/alpha),
-    so `YOLOTemporalUNet(num_classes, yolo_model_name, use_conv_lstm, hyp)` from main.py:126-131 still works.
+    Extra (additive) constructor arguments: `neuron` ('lif' default | 'silu' | dict with type/beta/v_th/alpha) and
+    `extractor_backend` ('auto': the real ultralytics YOLO when importable, else the stand-in pyramid), so
+    `YOLOTemporalUNet(num_classes, yolo_model_name, use_conv_lstm, hyp)` from main.py:126-131 still works.
     """
 
     def __init__(self, num_classes=80, yolo_model_name="yolo11m.pt", use_conv_lstm=True,
-                 hyp: dict = {"box": 7.5, "cls": 0.5, "dfl": 1.5, "reg_max": 16}, neuron=None):
+                 hyp: dict = {"box": 7.5, "cls": 0.5, "dfl": 1.5, "reg_max": 16}, neuron=None, extractor_backend="auto"):
         super().__init__()
         from .head import Detect
         self.args = SimpleNamespace(**hyp)
         self.nc = num_classes
-        self.feature_extractor = YOLOFeatureExtractor(model_name=yolo_model_name, freeze=True)
+        self.feature_extractor = YOLOFeatureExtractor(model_name=yolo_model_name, freeze=True, backend=extractor_backend)
         feature_channels = self.feature_extractor.get_feature_channels()
         self.temporal_unet = TemporalUNet(feature_channels=feature_channels, use_conv_lstm=use_conv_lstm, neuron=neuron)
         self.detection_head = Detect(nc=num_classes, ch=feature_channels)
@@ -373,5 +422,7 @@ class YOLOTemporalUNet(nn.Module):
     def load_state_dict(self, state_dict, strict=True, assign=False):
         """Reference checkpoints carry the frozen YOLO weights under `feature_extractor.model.*`; the stand-in
         extractor has no persistent state, so those keys are dropped."""
+        if self.feature_extractor.backend == "ultralytics":
+            return super().load_state_dict(state_dict, strict=strict, assign=assign)
         sd = {k: v for k, v in state_dict.items() if not k.startswith("feature_extractor.")}
         return super().load_state_dict(sd, strict=strict, assign=assign)

@@ -96,14 +96,20 @@ def test_graphed_step_equals_eager_step_full_width():
 
 
 def _flip_report(name, s_prod, s_orc, u_orc, theta=1.0):
-    """flips = disagreeing spikes; far = those whose ORACLE membrane is not within 1e-5 of threshold (north_star's window);
-    max_dist = the largest |u - theta| among the flipped neurons."""
+    """Spikes [T,B,C,H,W].  flips = disagreeing spikes; near = flips whose ORACLE membrane is within 1e-5 of threshold
+    (north_star's window); carried = flips of a neuron that already had a near-threshold flip at an EARLIER timestep (the
+    LIF membrane is state: one flipped reset changes that neuron's next membrane by up to beta*theta, teacher-forcing the
+    layer INPUT cannot undo it); unexplained = the rest, with the largest |u - theta| among them."""
     flips = s_prod != s_orc
     dist = (u_orc - theta).abs()
-    near = dist < 1e-5
-    md = float(dist[flips].max()) if bool(flips.any()) else 0.0
-    return dict(layer=name, n=s_orc.numel(), flips=int(flips.sum()), far=int((flips & ~near).sum()), max_dist=md,
-                rate=float(s_orc.float().mean()))
+    near = flips & (dist < 1e-5)
+    seeded = torch.zeros_like(near)
+    seeded[1:] = near.cummax(0).values[:-1]           # a near-threshold flip happened strictly before t in this neuron
+    carried = flips & ~near & seeded
+    unexplained = flips & ~near & ~seeded
+    md = float(dist[unexplained].max()) if bool(unexplained.any()) else 0.0
+    return dict(layer=name, n=s_orc.numel(), flips=int(flips.sum()), near=int(near.sum()), carried=int(carried.sum()),
+                unexplained=int(unexplained.sum()), max_dist_unexplained=md, far=int((flips & ~near).sum()), rate=float(s_orc.float().mean()))
 
 
 @pytest.mark.parametrize("neuron,B,T,HW", [("silu", 64, 4, 256), ("lif", 64, 4, 256), ("lif", 16, 8, 512)],
@@ -170,14 +176,14 @@ def test_full_width_training_step_vs_oracle(neuron, B, T, HW):
         print("\nLIF flip report, teacher-forced per layer:", *forced, sep="\n  ")
         print("LIF flip report, end to end (first forward):", *e2e, sep="\n  ")
         assert len(forced) == 16
-        # Measured on B200: 0-27 flips per layer out of 4-67 M neuron-steps (<= 1e-6), about 3/4 of them inside north_star's
-        # 1e-5 window; the rest sit within 1e-4 of threshold: the membrane is O(1) and the fp32 accumulation ORDER of a
-        # K = 1152...9216 tensor-core conv differs from cuDNN's by ~1e-6 relative, which BatchNorm's 1/std scales up.
+        # Measured on B200: 0-27 flips per layer out of 4-67 M neuron-steps (<= 1e-6): every one is either inside north_star's
+        # 1e-5 window or carried by the same neuron's membrane from such a flip at an earlier timestep; anything else would be
+        # "unexplained" (allowed only within 1e-4 of threshold = fp32 accumulation-order noise of a K <= 9216 conv after BN).
         assert all(r["flips"] <= 1e-6 * r["n"] + 4 for r in forced), forced
-        assert all(r["max_dist"] < 1e-4 for r in forced), [r for r in forced if r["max_dist"] >= 1e-4]
-        assert sum(r["far"] for r in forced) <= 0.5 * sum(r["flips"] for r in forced) + 4, forced
+        assert all(r["max_dist_unexplained"] < 1e-4 for r in forced), [r for r in forced if r["max_dist_unexplained"] >= 1e-4]
+        assert sum(r["unexplained"] for r in forced) <= 4, forced
         assert all(0.02 < r["rate"] < 0.7 for r in forced), forced
-        assert e2e[0]["layer"] == "enc1" and e2e[0]["max_dist"] < 1e-4 and e2e[0]["flips"] <= 1e-6 * e2e[0]["n"] + 4, e2e[0]
+        assert e2e[0]["layer"] == "enc1" and e2e[0]["max_dist_unexplained"] < 1e-4 and e2e[0]["flips"] <= 1e-6 * e2e[0]["n"] + 4, e2e[0]
         # (the forwards above advanced the BatchNorm running statistics of both sides; train mode does not read them)
     for step in range(2):
         _, it_o, gn_o = MO.reference_train_step(orc, loss_fn, opt, sched, frames, labels)
