@@ -145,3 +145,146 @@ def test_grad_bucketer_gloo_world2():
         p.join(120)
         assert p.exitcode == 0
     assert q.get() == "ok"
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: metrics, sampler, split, extractor adapter, multi-use gradient readiness
+# ------------------------------------------------------------------------------------------------
+class _Writer:
+    def __init__(self):
+        self.scalar, self.scalars = [], []
+
+    def add_scalar(self, tag, value, step):
+        self.scalar.append((tag, float(value), int(step)))
+
+    def add_scalars(self, tag, d, step):
+        self.scalars.append((tag, {k: float(v) for k, v in d.items()}, int(step)))
+
+
+def test_device_metrics_emit_reference_tensorboard_tags_with_one_sync_per_n_steps():
+    """reference train.py:81-100: per-batch tags and values; here the values are read back once per `every` steps."""
+    from snn_object_detectionddp_b200.train import DeviceMetrics, _log_batches
+    m, w = DeviceMetrics("cpu", every=3), _Writer()
+    rows = [torch.tensor([1.0, 2.0, 3.0]) * (i + 1) for i in range(7)]
+    flushes = 0
+    for i, it in enumerate(rows):
+        if m.update(it, 100 + i, lr=0.01 * i, scale=4.0):
+            _log_batches(w, m.flush(), True)
+            flushes += 1
+    _log_batches(w, m.flush(), True)
+    assert flushes == 2
+    assert [s for s in w.scalar if s[0] == "Loss/train_batch"] == [("Loss/train_batch", 4.0 * 6.0 * (i + 1), 100 + i) for i in range(7)]
+    assert [round(s[1], 6) for s in w.scalar if s[0] == "LearningRate/batch"] == [round(0.01 * i, 6) for i in range(7)]
+    assert w.scalars[2] == ("Train_Loss_Components_Batch", {"box_loss_batch": 3.0, "cls_loss_batch": 6.0, "dfl_loss_batch": 9.0}, 102)
+    avg, comps = m.averages(7)
+    assert abs(avg - 4.0 * 6.0 * 4.0) < 1e-5 and torch.allclose(comps, torch.tensor([4.0, 8.0, 12.0]))
+    wv = _Writer()
+    _log_batches(wv, [(5, torch.tensor([1.0, 1.0, 1.0]), 0.0, 3.0)], False)
+    assert wv.scalar == [("Loss/val_batch", 3.0, 5)] and wv.scalars[0][0] == "Val_Loss_Components_Batch"
+
+
+def test_sharded_sampler_partitions_like_distributed_sampler():
+    from snn_object_detectionddp_b200.train import ShardedSampler
+    data = list(range(103))
+    for world in (1, 2, 8):
+        for drop_last in (False, True):
+            per_rank = []
+            for r in range(world):
+                s = ShardedSampler(data, rank=r, world_size=world, shuffle=True, seed=7, drop_last=drop_last)
+                s.set_epoch(3)
+                idx = list(s)
+                assert len(idx) == len(s)
+                per_rank.append(idx)
+            assert len({len(p) for p in per_rank}) == 1                       # equal work on every rank
+            allidx = [i for p in per_rank for i in p]
+            if drop_last:
+                assert len(set(allidx)) == len(allidx) == (103 // world) * world
+            else:
+                assert set(allidx) == set(data) and len(allidx) - 103 < world   # padded by wrap-around only
+    a = ShardedSampler(data, 0, 2, seed=7); b = ShardedSampler(data, 0, 2, seed=7)
+    a.set_epoch(0); b.set_epoch(1)
+    assert list(a) != list(b)                                                  # reshuffled every epoch
+    b.set_epoch(0)
+    assert list(a) == list(b)                                                  # same permutation on every process
+    ref = torch.utils.data.distributed.DistributedSampler(data, num_replicas=2, rank=1, shuffle=False)
+    assert list(ShardedSampler(data, 1, 2, shuffle=False)) == list(ref)
+
+
+def test_sequence_grouped_split_keeps_recordings_apart():
+    """reference main.py:16-27: a recording sequence (image directory) lands entirely in train or in validation."""
+    from snn_object_detectionddp_b200.train import get_train_val_split
+
+    class DS:
+        samples = [(f"/d/seq{ i // 7 }", i, None) for i in range(70)]
+
+        def __len__(self):
+            return 70
+
+        def __getitem__(self, i):
+            return i
+
+    tr, va = get_train_val_split({}, DS())
+    dirs = lambda sub: {DS.samples[i][0] for i in sub.indices}
+    assert not (dirs(tr) & dirs(va)) and len(dirs(tr)) == 8 and len(dirs(va)) == 2
+    assert sorted(tr.indices + va.indices) == list(range(70))
+    tr2, va2 = get_train_val_split({}, DS())
+    assert tr2.indices == tr.indices                                           # random_state=42: the reference's split
+
+
+def test_extractor_uses_real_ultralytics_when_importable(monkeypatch):
+    """reference model.py:74-98: YOLO(model_name).model, frozen, always eval, `_, features = model(x)`.  ultralytics is
+    not installable here, so a module with the same surface is injected; without it the stand-in pyramid is used."""
+    import sys
+    import types
+    import snn_object_detectionddp_b200.model as M
+    assert M.YOLOFeatureExtractor(backend="auto").backend == "standin"
+    with pytest.raises(RuntimeError):
+        M.YOLOFeatureExtractor(backend="ultralytics")
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c3, self.c4, self.c5 = (torch.nn.Conv2d(3, c, 1, stride=s) for c, s in ((16, 8), (24, 16), (32, 32)))
+
+        def forward(self, x):
+            return None, [self.c3(x), self.c4(x), self.c5(x)]
+
+    seen = {}
+
+    class YOLO:
+        def __init__(self, name):
+            seen["name"] = name
+            self.model = Net()
+
+    fake = types.ModuleType("ultralytics")
+    fake.YOLO = YOLO
+    monkeypatch.setitem(sys.modules, "ultralytics", fake)
+    ext = M.YOLOFeatureExtractor("yolo11m.pt")
+    assert ext.backend == "ultralytics" and seen["name"] == "yolo11m.pt"
+    assert all(not p.requires_grad for p in ext.parameters())
+    ext.train()
+    assert not ext.model.training                                              # stays in eval (model.py:84-86)
+    assert ext.get_feature_channels((1, 3, 64, 64)) == [16, 24, 32]
+    f = ext(torch.rand(2, 3, 64, 64))
+    assert [tuple(t.shape) for t in f] == [(2, 16, 8, 8), (2, 24, 4, 4), (2, 32, 2, 2)]
+    assert any(k.startswith("model.c3") for k in ext.state_dict())            # reference key names: feature_extractor.model.*
+
+
+def test_gradient_readiness_counts_every_use_of_a_parameter():
+    """The reference-style per-frame loop uses each parameter T times: its DDP bucket may be reduced only after the LAST
+    backward of those uses (round-1 finding: it was launched after the first)."""
+    from snn_object_detectionddp_b200.params import ParamStore
+    lin = torch.nn.Conv2d(8, 8, 3, bias=True)
+    st = ParamStore(lin)
+    ready = []
+    st.grad_ready_hook = lambda e: ready.append(e.name)
+    for _ in range(3):
+        st.note_use(lin.weight, lin.bias)
+    st.grad_done(lin.weight); st.grad_done(lin.weight)
+    assert ready == []
+    st.grad_done(lin.weight)
+    assert ready == ["weight"]
+    st.grad_done(lin.bias); st.grad_done(lin.bias); st.grad_done(lin.bias)
+    assert ready == ["weight", "bias"]
+    st.grad_done(lin.bias)                       # a use that was never announced (no_grad forward): fires immediately
+    assert ready[-1] == "bias"
