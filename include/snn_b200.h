@@ -137,6 +137,12 @@ int snn_nhwc_to_nchw(const void* in, int in_is_bf16, float* out, int NB, int C, 
 int snn_dw3x3_fprop(const void* x_bf16, const float* w, float* y, int NB, int H, int W, int C, void* stream);
 int snn_dw3x3_dgrad(const void* dy_bf16, const float* w, void* dx_bf16, int NB, int H, int W, int C, void* stream);
 int snn_dw3x3_wgrad(const void* x_bf16, const void* dy_bf16, float* dw, int NB, int H, int W, int C, void* stream);
+/* depthwise forward with the train-mode BatchNorm statistics fused (as snn_conv_fprop_stats): partials fp32
+ * [T][blocks][2][C], blocks = snn_dw3x3_stats_blocks(B, W, C) per timestep, one row per thread block, written without
+ * atomics and reduced in a fixed order by snn_bn_finalize_partials(groups_per_step = blocks). */
+long long snn_dw3x3_stats_blocks(int frames_per_step, int W, int C);
+int snn_dw3x3_fprop_stats(const void* x_bf16, const float* w9c, float* y, int NB, int H, int W, int C, int T, float* partials,
+                          void* stream);
 
 /* ---- frame packer of the stand-in feature pyramid (the frozen YOLO11m of model.py:74-98 cannot exist
  *      offline): fp32 frames [B][T][3][H][W] -> bf16 NHWC [T*B][H/8][W/8][192] ---- */

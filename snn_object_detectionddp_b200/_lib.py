@@ -39,6 +39,7 @@ _SIGNATURES = {
     "snn_bilinear_resize": [_I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "snn_nhwc_pad_crop": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "snn_dw3x3_fprop": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "snn_dw3x3_fprop_stats": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "snn_dw3x3_dgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
     "snn_dw3x3_wgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
     "snn_space_to_depth8": [_P, _P, _I, _I, _I, _I, _P],
@@ -65,7 +66,7 @@ class SnnKernelError(RuntimeError):
 
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["snn_last_error", "snn_version", "snn_debug_set", "snn_conv_stats_groups", "snn_bn_stats_workspace_floats", "snn_nms_workspace_keys",
-                                             "snn_tal_workspace_bytes"])
+                                             "snn_tal_workspace_bytes", "snn_dw3x3_stats_blocks"])
 
 
 def lib():
@@ -89,6 +90,8 @@ def lib():
         L.snn_bn_stats_workspace_floats.restype = _L
         L.snn_nms_workspace_keys.argtypes = [_I, _I, _I]
         L.snn_nms_workspace_keys.restype = _L
+        L.snn_dw3x3_stats_blocks.argtypes = [_I, _I, _I]
+        L.snn_dw3x3_stats_blocks.restype = _L
         L.snn_tal_workspace_bytes.argtypes = [_I, _I, _I]
         L.snn_tal_workspace_bytes.restype = _L
         L.snn_debug_set.argtypes = [_I, _I]

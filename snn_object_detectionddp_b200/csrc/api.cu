@@ -75,7 +75,8 @@ int launch_nchw_to_nhwc(const float*, void*, int, int, int, int, long long, int,
 int launch_nhwc_to_nchw(const void*, int, float*, int, int, int, long long, int, cudaStream_t);
 int launch_sumsq(const float*, long long, double*, int, cudaStream_t);
 int launch_colsum_bf16(const __nv_bfloat16*, float*, long long, int, cudaStream_t);
-int launch_dw3x3_fwd(const __nv_bfloat16*, const float*, float*, int, int, int, int, cudaStream_t);
+int launch_dw3x3_fwd(const __nv_bfloat16*, const float*, float*, int, int, int, int, float*, int, cudaStream_t);
+long long dw3x3_stats_blocks(int, int, int);
 int launch_dw3x3_dgrad(const __nv_bfloat16*, const float*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 int launch_dw3x3_wgrad(const __nv_bfloat16*, const __nv_bfloat16*, float*, int, int, int, int, cudaStream_t);
 int launch_s2d8(const float*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
@@ -201,7 +202,11 @@ int snn_nhwc_to_nchw(const void* in, int in_is_bf16, float* out, int NB, int C, 
     return launch_nhwc_to_nchw(in, in_is_bf16, out, NB, C, HW, in_ld, in_coff, ST);
 }
 int snn_dw3x3_fprop(const void* x, const float* w, float* y, int NB, int H, int W, int C, void* stream) {
-    return launch_dw3x3_fwd((const __nv_bfloat16*)x, w, y, NB, H, W, C, ST);
+    return launch_dw3x3_fwd((const __nv_bfloat16*)x, w, y, NB, H, W, C, nullptr, 0, ST);
+}
+long long snn_dw3x3_stats_blocks(int frames_per_step, int W, int C) { return dw3x3_stats_blocks(frames_per_step, W, C); }
+int snn_dw3x3_fprop_stats(const void* x, const float* w, float* y, int NB, int H, int W, int C, int T, float* partials, void* stream) {
+    return launch_dw3x3_fwd((const __nv_bfloat16*)x, w, y, NB, H, W, C, partials, T, ST);
 }
 int snn_dw3x3_dgrad(const void* dy, const float* w, void* dx, int NB, int H, int W, int C, void* stream) {
     return launch_dw3x3_dgrad((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, NB, H, W, C, ST);

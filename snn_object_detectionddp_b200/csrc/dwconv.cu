@@ -7,115 +7,165 @@
 
 namespace snn {
 
-// 8 channels / thread
-__global__ void __launch_bounds__(256)
-dw3x3_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int NB, int H, int W,
-                 int C) {
-    const int c8 = C >> 3;
-    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-    const long long total = (long long)NB * H * W * c8;
-    if (idx >= total) return;
-    const int cg = (int)(idx % c8);
-    const long long pix = idx / c8;
-    const int wx = (int)(pix % W), hy = (int)((pix / W) % H);
-    const long long n = pix / ((long long)W * H);
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-        const int h2 = hy + kh - 1;
-        if (h2 < 0 || h2 >= H) continue;
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-            const int w2 = wx + kw - 1;
-            if (w2 < 0 || w2 >= W) continue;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((n * H + h2) * W + w2) * C) + cg);
-            const float4 wa = __ldg(reinterpret_cast<const float4*>(w + (kh * 3 + kw) * C) + cg * 2);
-            const float4 wb = __ldg(reinterpret_cast<const float4*>(w + (kh * 3 + kw) * C) + cg * 2 + 1);
-            acc[0] += bf16_lo(v.x) * wa.x; acc[1] += bf16_hi(v.x) * wa.y; acc[2] += bf16_lo(v.y) * wa.z; acc[3] += bf16_hi(v.y) * wa.w;
-            acc[4] += bf16_lo(v.z) * wb.x; acc[5] += bf16_hi(v.z) * wb.y; acc[6] += bf16_lo(v.w) * wb.z; acc[7] += bf16_hi(v.w) * wb.w;
-        }
-    }
-    float4* o = reinterpret_cast<float4*>(y + pix * C) + cg * 2;
-    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+// ------------------------------------------------------------------------------------------
+// Column-walking kernels.  A thread owns 8 channels of ONE image column (n, w) and walks h = 0..H-1 with a 3x3 window of
+// packed bf16 in registers: every step loads the three 16-byte pieces of the next input row (the two neighbours' pieces
+// are L1 hits, the neighbouring columns live in the same block) instead of nine, the nine tap weights sit in shared memory.
+// Round 1 used one thread per output pixel: 9 activation + 18 weight loads per 8 outputs -> 1.6 TB/s (24 % of HBM).
+//   fprop : y fp32 = conv(x bf16) (+ per-timestep BatchNorm partial sums in the same pass: the separate snn_bn_stats pass over
+//           y, 4 B/element, is gone; partials [T][blocks][2][C], one per block, reduced in a fixed order)
+//   dgrad : dx bf16 = conv(dy bf16, flipped taps)
+//   wgrad : dw[tap][c] += sum_pixels dy * x[pixel + tap] (72 register accumulators per thread, fixed-order block reduce,
+//           one atomicAdd per (tap, channel) and block)
+// ------------------------------------------------------------------------------------------
+SNN_DEVINL void unpack8f(const uint4 v, float* f) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+SNN_DEVINL uint4 ld_px(const __nv_bfloat16* __restrict__ base, long long row_off, int w, int W, int C, int cg) {
+    if (w < 0 || w >= W) return make_uint4(0u, 0u, 0u, 0u);
+    return __ldg(reinterpret_cast<const uint4*>(base + row_off + (long long)w * C) + cg);
 }
 
-// dx[n,h,w,c] = sum_taps dy[n, h-(kh-1), w-(kw-1), c] * w[kh,kw,c]
+// grid (ceil(cols_per_group / slots), groups): group = timestep (fprop with statistics) or 1; a column = (image, w)
+template <bool DGRAD>
 __global__ void __launch_bounds__(256)
-dw3x3_dgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, int NB,
-                   int H, int W, int C) {
-    const int c8 = C >> 3;
-    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-    const long long total = (long long)NB * H * W * c8;
-    if (idx >= total) return;
-    const int cg = (int)(idx % c8);
-    const long long pix = idx / c8;
-    const int wx = (int)(pix % W), hy = (int)((pix / W) % H);
-    const long long n = pix / ((long long)W * H);
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-        const int h2 = hy - (kh - 1);
-        if (h2 < 0 || h2 >= H) continue;
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-            const int w2 = wx - (kw - 1);
-            if (w2 < 0 || w2 >= W) continue;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + ((n * H + h2) * W + w2) * C) + cg);
-            const float4 wa = __ldg(reinterpret_cast<const float4*>(w + (kh * 3 + kw) * C) + cg * 2);
-            const float4 wb = __ldg(reinterpret_cast<const float4*>(w + (kh * 3 + kw) * C) + cg * 2 + 1);
-            acc[0] += bf16_lo(v.x) * wa.x; acc[1] += bf16_hi(v.x) * wa.y; acc[2] += bf16_lo(v.y) * wa.z; acc[3] += bf16_hi(v.y) * wa.w;
-            acc[4] += bf16_lo(v.z) * wb.x; acc[5] += bf16_hi(v.z) * wb.y; acc[6] += bf16_lo(v.w) * wb.z; acc[7] += bf16_hi(v.w) * wb.w;
-        }
+dw3x3_col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt, float* __restrict__ y32,
+                 __nv_bfloat16* __restrict__ y16, float* __restrict__ part, int imgs_per_group, int H, int W, int C) {
+    extern __shared__ float sh[];                 // [9][C] weights, then (statistics) [slots][2][C]
+    const int c8 = C >> 3, slots = 256 / c8;
+    float* shw = sh;
+    float* shs = sh + 9 * C;
+    for (int i = threadIdx.x; i < 9 * C; i += 256) {
+        const int tap = i / C, c = i % C;
+        shw[i] = wgt[(DGRAD ? 8 - tap : tap) * C + c];            // dgrad: flipped taps
     }
-    uint4 pk;
-    pk.x = pack_bf16x2(acc[0], acc[1]); pk.y = pack_bf16x2(acc[2], acc[3]);
-    pk.z = pack_bf16x2(acc[4], acc[5]); pk.w = pack_bf16x2(acc[6], acc[7]);
-    *(reinterpret_cast<uint4*>(dx + pix * C) + cg) = pk;
-}
-
-// dw[tap][c] += sum_pixels dy[pix, c] * x[pix + tap, c];  block = (C/4 threads per pixel) x rows, smem reduce, atomics
-__global__ void __launch_bounds__(256)
-dw3x3_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, int NB,
-                   int H, int W, int C, int pix_per_block) {
-    extern __shared__ float shw[];  // [9][C]
-    const int tpp = C >> 2;
-    const int rows = 256 / tpp;
-    const int cg = threadIdx.x % tpp, row = threadIdx.x / tpp;
-    for (int i = threadIdx.x; i < 9 * C; i += 256) shw[i] = 0.f;
     __syncthreads();
-    if (row < rows) {
-        const long long P = (long long)NB * H * W;
-        const long long p0 = (long long)blockIdx.x * pix_per_block, p1 = min(P, p0 + (long long)pix_per_block);
-        float acc[9][4];
+    const int slot = threadIdx.x / c8, cg = threadIdx.x % c8;
+    const int cols = imgs_per_group * W;
+    const int col = blockIdx.x * slots + slot;
+    float ssum[8], ssq[8];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
-        for (long long p = p0 + row; p < p1; p += rows) {
-            const int wx = (int)(p % W), hy = (int)((p / W) % H);
-            const long long n = p / ((long long)W * H);
-            const uint2 g = __ldg(reinterpret_cast<const uint2*>(dy + p * C) + cg);
-            const float g4[4] = {bf16_lo(g.x), bf16_hi(g.x), bf16_lo(g.y), bf16_hi(g.y)};
+    for (int i = 0; i < 8; ++i) ssum[i] = ssq[i] = 0.f;
+    if (slot < slots && col < cols) {
+        const int w = col % W;
+        const long long n = (long long)blockIdx.y * imgs_per_group + col / W;
+        const __nv_bfloat16* img = x + n * H * W * C;
+        const long long rs = (long long)W * C;
+        uint4 r0[3], r1[3], r2[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { r0[k] = make_uint4(0u, 0u, 0u, 0u); r1[k] = ld_px(img, 0, w + k - 1, W, C, cg); }
+        for (int h = 0; h < H; ++h) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) r2[k] = (h + 1 < H) ? ld_px(img, (long long)(h + 1) * rs, w + k - 1, W, C, cg) : make_uint4(0u, 0u, 0u, 0u);
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
-                const int h2 = hy + kh - 1;
-                if (h2 < 0 || h2 >= H) continue;
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
-                    const int w2 = wx + kw - 1;
-                    if (w2 < 0 || w2 >= W) continue;
-                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(x + ((n * H + h2) * W + w2) * C) + cg);
-                    acc[kh * 3 + kw][0] += g4[0] * bf16_lo(v.x); acc[kh * 3 + kw][1] += g4[1] * bf16_hi(v.x);
-                    acc[kh * 3 + kw][2] += g4[2] * bf16_lo(v.y); acc[kh * 3 + kw][3] += g4[3] * bf16_hi(v.y);
+                    float v[8];
+                    unpack8f(kh == 0 ? r0[kw] : (kh == 1 ? r1[kw] : r2[kw]), v);
+                    const float4 wa = *reinterpret_cast<const float4*>(shw + (kh * 3 + kw) * C + cg * 8);
+                    const float4 wb = *reinterpret_cast<const float4*>(shw + (kh * 3 + kw) * C + cg * 8 + 4);
+                    acc[0] += v[0] * wa.x; acc[1] += v[1] * wa.y; acc[2] += v[2] * wa.z; acc[3] += v[3] * wa.w;
+                    acc[4] += v[4] * wb.x; acc[5] += v[5] * wb.y; acc[6] += v[6] * wb.z; acc[7] += v[7] * wb.w;
                 }
             }
+            const long long o = ((n * H + h) * W + w) * C + cg * 8;
+            if (DGRAD) {
+                uint4 pk;
+                pk.x = pack_bf16x2(acc[0], acc[1]); pk.y = pack_bf16x2(acc[2], acc[3]);
+                pk.z = pack_bf16x2(acc[4], acc[5]); pk.w = pack_bf16x2(acc[6], acc[7]);
+                *reinterpret_cast<uint4*>(y16 + o) = pk;
+            } else {
+                float4* op = reinterpret_cast<float4*>(y32 + o);
+                op[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                op[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                if (part) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { ssum[i] += acc[i]; ssq[i] = fmaf(acc[i], acc[i], ssq[i]); }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { r0[k] = r1[k]; r1[k] = r2[k]; }
         }
-#pragma unroll
-        for (int t = 0; t < 9; ++t)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) atomicAdd(&shw[t * C + cg * 4 + i], acc[t][i]);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 9 * C; i += 256) atomicAdd(&dw[i], shw[i]);
+    if (!DGRAD && part) {
+        // per-block partial sums in a FIXED order (deterministic): slot rows in shared memory, column-summed by C threads
+        if (slot < slots) {
+            float* row = shs + (size_t)slot * 2 * C;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { row[cg * 8 + i] = ssum[i]; row[C + cg * 8 + i] = ssq[i]; }
+        }
+        __syncthreads();
+        float* dst = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C;
+        for (int i = threadIdx.x; i < 2 * C; i += 256) {
+            float a = 0.f;
+            for (int sidx = 0; sidx < slots; ++sidx) a += shs[(size_t)sidx * 2 * C + i];
+            dst[i] = a;
+        }
+    }
+}
+
+// wgrad: grid (blocks); a block walks columns blockIdx.x, blockIdx.x + gridDim.x, ... (slots columns at a time)
+__global__ void __launch_bounds__(256)
+dw3x3_wgrad_col_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, int NB, int H,
+                       int W, int C) {
+    extern __shared__ float sh[];                 // [slots][3][C] (one tap row at a time)
+    const int c8 = C >> 3, slots = 256 / c8;
+    const int slot = threadIdx.x / c8, cg = threadIdx.x % c8;
+    const long long cols = (long long)NB * W;
+    float acc[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+    if (slot < slots) {
+        for (long long col = (long long)blockIdx.x * slots + slot; col < cols; col += (long long)gridDim.x * slots) {
+            const int w = (int)(col % W);
+            const long long n = col / W;
+            const __nv_bfloat16* img = x + n * H * W * C;
+            const __nv_bfloat16* gimg = dy + n * H * W * C;
+            const long long rs = (long long)W * C;
+            uint4 r0[3], r1[3], r2[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { r0[k] = make_uint4(0u, 0u, 0u, 0u); r1[k] = ld_px(img, 0, w + k - 1, W, C, cg); }
+            for (int h = 0; h < H; ++h) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) r2[k] = (h + 1 < H) ? ld_px(img, (long long)(h + 1) * rs, w + k - 1, W, C, cg) : make_uint4(0u, 0u, 0u, 0u);
+                float g[8];
+                unpack8f(__ldg(reinterpret_cast<const uint4*>(gimg + (long long)h * rs + (long long)w * C) + cg), g);
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        float v[8];
+                        unpack8f(kh == 0 ? r0[kw] : (kh == 1 ? r1[kw] : r2[kw]), v);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[kh * 3 + kw][i] = fmaf(g[i], v[i], acc[kh * 3 + kw][i]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { r0[k] = r1[k]; r1[k] = r2[k]; }
+            }
+        }
+    }
+    // block reduce, three taps at a time, fixed order; then one atomicAdd per (tap, channel) and block
+    for (int kh = 0; kh < 3; ++kh) {
+        __syncthreads();
+        if (slot < slots) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sh[((size_t)slot * 3 + kw) * C + cg * 8 + i] = acc[kh * 3 + kw][i];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * C; i += 256) {
+            float a = 0.f;
+            for (int sidx = 0; sidx < slots; ++sidx) a += sh[(size_t)sidx * 3 * C + i];
+            atomicAdd(&dw[(size_t)kh * 3 * C + i], a);
+        }
+    }
 }
 
 // frames fp32 [B][T][3][H][W] (or [N][3][H][W] with T=1) -> bf16 NHWC [T*B][H/8][W/8][192], channel = c*64 + dy*8 + dx
@@ -138,28 +188,43 @@ s2d8_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B
     *reinterpret_cast<uint4*>(out + ((n * H8 + i) * W8 + j) * 192 + c * 64 + dy * 8) = pk;
 }
 
-int launch_dw3x3_fwd(const __nv_bfloat16* x, const float* w, float* y, int NB, int H, int W, int C, cudaStream_t st) {
-    SNN_REQUIRE(C % 8 == 0, "dw3x3: C must be a multiple of 8");
-    const long long total = (long long)NB * H * W * (C / 8);
-    dw3x3_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, w, y, NB, H, W, C);
-    return check_cuda(cudaGetLastError(), "dw3x3_fwd_kernel");
+// blocks the column kernels launch per statistics group (also the number of partial rows per timestep)
+long long dw3x3_stats_blocks(int B, int W, int C) {
+    if (C % 8 != 0 || C < 8 || C > 1024 || B < 1 || W < 1) return 0;
+    const int slots = 256 / (C / 8);
+    return ((long long)B * W + slots - 1) / slots;
+}
+
+// groups > 0: per-group (= per-timestep) BatchNorm partial sums -> part [groups][blocks][2][C] (blocks = dw3x3_stats_blocks)
+int launch_dw3x3_fwd(const __nv_bfloat16* x, const float* w, float* y, int NB, int H, int W, int C, float* part, int groups, cudaStream_t st) {
+    SNN_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1024, "dw3x3: C=%d must be a multiple of 8 in [8,1024]", C);
+    if (!part || groups < 1) groups = 1;
+    SNN_REQUIRE(NB % groups == 0, "dw3x3: NB=%d is not a multiple of the %d statistics groups", NB, groups);
+    const int B = NB / groups, slots = 256 / (C / 8);
+    const size_t smem = sizeof(float) * (9 * (size_t)C + (part ? (size_t)slots * 2 * C : 0));
+    static PerDeviceOnce once;
+    SNN_CUDA_OK(once.run([] { return cudaFuncSetAttribute(dw3x3_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
+    dim3 grid((unsigned)dw3x3_stats_blocks(B, W, C), groups);
+    dw3x3_col_kernel<false><<<grid, 256, smem, st>>>(x, w, y, nullptr, part, B, H, W, C);
+    return check_cuda(cudaGetLastError(), "dw3x3_col_kernel<fprop>");
 }
 int launch_dw3x3_dgrad(const __nv_bfloat16* dy, const float* w, __nv_bfloat16* dx, int NB, int H, int W, int C, cudaStream_t st) {
-    SNN_REQUIRE(C % 8 == 0, "dw3x3: C must be a multiple of 8");
-    const long long total = (long long)NB * H * W * (C / 8);
-    dw3x3_dgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dy, w, dx, NB, H, W, C);
-    return check_cuda(cudaGetLastError(), "dw3x3_dgrad_kernel");
+    SNN_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1024, "dw3x3: C=%d must be a multiple of 8 in [8,1024]", C);
+    dim3 grid((unsigned)dw3x3_stats_blocks(NB, W, C), 1);
+    dw3x3_col_kernel<true><<<grid, 256, sizeof(float) * 9 * C, st>>>(dy, w, nullptr, dx, nullptr, NB, H, W, C);
+    return check_cuda(cudaGetLastError(), "dw3x3_col_kernel<dgrad>");
 }
 int launch_dw3x3_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int NB, int H, int W, int C, cudaStream_t st) {
-    SNN_REQUIRE(C % 4 == 0 && C <= 1024, "dw3x3_wgrad: C must be a multiple of 4, <= 1024");
-    const int rows = 256 / (C / 4);
-    const long long P = (long long)NB * H * W;
-    long long want = (long long)num_sms() * 4;
-    long long ppb = (P + want - 1) / want;
-    if (ppb < rows * 4) ppb = rows * 4;
-    ppb = (ppb + rows - 1) / rows * rows;
-    dw3x3_wgrad_kernel<<<(unsigned)((P + ppb - 1) / ppb), 256, sizeof(float) * 9 * C, st>>>(x, dy, dw, NB, H, W, C, (int)ppb);
-    return check_cuda(cudaGetLastError(), "dw3x3_wgrad_kernel");
+    SNN_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1024, "dw3x3_wgrad: C=%d must be a multiple of 8 in [8,1024]", C);
+    const int slots = 256 / (C / 8);
+    long long blocks = ((long long)NB * W + slots - 1) / slots;
+    const long long cap = (long long)num_sms() * 2;
+    if (blocks > cap) blocks = cap;
+    const size_t smem = sizeof(float) * (size_t)slots * 3 * C;
+    static PerDeviceOnce once;
+    SNN_CUDA_OK(once.run([] { return cudaFuncSetAttribute(dw3x3_wgrad_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
+    dw3x3_wgrad_col_kernel<<<(unsigned)blocks, 256, smem, st>>>(x, dy, dw, NB, H, W, C);
+    return check_cuda(cudaGetLastError(), "dw3x3_wgrad_col_kernel");
 }
 // uint8 frames (what the dataset decodes, dataset.py:139-152) -> /255 on the device (the reference divides on the host and
 // ships fp32: 4x the PCIe bytes); `v / 255.0f` in IEEE fp32 is bit-identical to torch's `.float() / 255.0`

@@ -371,14 +371,22 @@ def adamw_step(p, g, m, v, shadow, hp, sumsq, gnorm_out=None, step=None, zero_gr
 GEOM_DW3x3 = 4
 
 
-def dw3x3_fprop(x, w9c):
-    """x bf16 NHWC, w fp32 [9][C] -> y fp32 NHWC."""
+def dw3x3_fprop(x, w9c, T=0):
+    """x bf16 NHWC, w fp32 [9][C] -> y fp32 NHWC.  T > 0: also the per-timestep BatchNorm partial sums of y from the same
+    pass -> (y, partials fp32 [T][blocks][2][C], blocks per timestep)."""
     require_cuda(x, w9c)
     nb, h, w, c = x.shape
     assert x.is_contiguous() and x.dtype == torch.bfloat16 and w9c.is_contiguous() and w9c.numel() == 9 * c
     y = torch.empty((nb, h, w, c), device=x.device, dtype=torch.float32)
-    call("snn_dw3x3_fprop", ptr(x), ptr(w9c), ptr(y), nb, h, w, c, stream_ptr())
-    return y
+    nbytes = 6.0 * y.numel()                # algorithmic: read x bf16, write y fp32
+    if T and nb % T == 0:
+        gpt = int(_lib.lib().snn_dw3x3_stats_blocks(nb // T, w, c))
+        part = torch.empty((T, gpt, 2, c), device=x.device, dtype=torch.float32)
+        call("snn_dw3x3_fprop_stats", ptr(x), ptr(w9c), ptr(y), nb, h, w, c, T, ptr(part), stream_ptr(),
+             work=("byte", nbytes, f"dw fwd+stats nb{nb} {h}x{w} C{c}"))
+        return y, part, gpt
+    call("snn_dw3x3_fprop", ptr(x), ptr(w9c), ptr(y), nb, h, w, c, stream_ptr(), work=("byte", nbytes, f"dw fwd nb{nb} {h}x{w} C{c}"))
+    return (y, None, 0) if T else y
 
 
 def dw3x3_dgrad(dy, w9c, out=None):
@@ -387,7 +395,7 @@ def dw3x3_dgrad(dy, w9c, out=None):
     assert dy.is_contiguous() and dy.dtype == torch.bfloat16
     dx = torch.empty((nb, h, w, c), device=dy.device, dtype=torch.bfloat16) if out is None else out
     assert dx.is_contiguous() and tuple(dx.shape) == (nb, h, w, c) and dx.dtype == torch.bfloat16
-    call("snn_dw3x3_dgrad", ptr(dy), ptr(w9c), ptr(dx), nb, h, w, c, stream_ptr())
+    call("snn_dw3x3_dgrad", ptr(dy), ptr(w9c), ptr(dx), nb, h, w, c, stream_ptr(), work=("byte", 4.0 * dy.numel(), f"dw dgrad nb{nb} {h}x{w} C{c}"))
     return dx
 
 
@@ -395,7 +403,7 @@ def dw3x3_wgrad(x, dy, dw9c):
     require_cuda(x, dy, dw9c)
     nb, h, w, c = x.shape
     assert x.is_contiguous() and dy.is_contiguous() and dw9c.is_contiguous() and dw9c.dtype == torch.float32
-    call("snn_dw3x3_wgrad", ptr(x), ptr(dy), ptr(dw9c), nb, h, w, c, stream_ptr())
+    call("snn_dw3x3_wgrad", ptr(x), ptr(dy), ptr(dw9c), nb, h, w, c, stream_ptr(), work=("byte", 4.0 * x.numel(), f"dw wgrad nb{nb} {h}x{w} C{c}"))
 
 
 def space_to_depth8(frames, B, T):

@@ -52,7 +52,10 @@ class ConvBNActFn(Function):
         if any(ctx.needs_input_grad):
             st.note_use(weight, *((gamma, beta) if training else ()))
         if geom == K.GEOM_DW3x3:
-            y = K.dw3x3_fprop(x0, st.w_master3(weight).view(9, cout))
+            if training:        # per-timestep BatchNorm partial sums from the same pass over y
+                y, part, gpt = K.dw3x3_fprop(x0, st.w_master3(weight).view(9, cout), T=T)
+            else:
+                y = K.dw3x3_fprop(x0, st.w_master3(weight).view(9, cout))
         elif training:
             y, part, gpt = K.conv_fprop_partials(geom, x0, st.w_fprop(weight), cout, T, x1=x1)    # BN partial sums from the epilogue
         else:

@@ -35,6 +35,28 @@ def test_dw3x3_fprop_dgrad_wgrad(nb, h, w, c):
     assert rel_err(dw, 2 * gw_ref.squeeze(1).permute(1, 2, 0).reshape(9, c)) < 1e-5
 
 
+@pytest.mark.parametrize("T,B,h,w,c", [(4, 8, 32, 32, 144), (2, 3, 16, 20, 144), (1, 5, 4, 4, 64), (3, 2, 15, 7, 1024), (4, 64, 8, 8, 144)])
+def test_dw3x3_fprop_with_fused_bn_statistics(T, B, h, w, c):
+    """Column-walking depthwise kernel at head shapes (incl. the configs[1] batch): y == torch's grouped conv, the
+    per-timestep partial sums reduce to the fp64 sums of y (1e-6 of sum |y|), two launches agree bit for bit."""
+    setup_exact()
+    K = _k()
+    x = torch.randn(T * B, h, w, c, device="cuda").to(torch.bfloat16)
+    w9 = torch.randn(9, c, device="cuda") * 0.3
+    wr = w9.reshape(3, 3, c).permute(2, 0, 1).unsqueeze(1).contiguous()
+    yr = F.conv2d(x.float().permute(0, 3, 1, 2), wr, padding=1, groups=c).permute(0, 2, 3, 1)
+    y, part, gpt = K.dw3x3_fprop(x, w9, T=T)
+    assert rel_err(y, yr) < 1e-6 and tuple(part.shape) == (T, gpt, 2, c)
+    assert torch.equal(y, K.dw3x3_fprop(x, w9))
+    yt = y.double().reshape(T, -1, c)
+    want = torch.stack([yt.sum(1), (yt * yt).sum(1)], 1)
+    scale = torch.stack([yt.abs().sum(1), (yt * yt).sum(1)], 1)
+    got = part.double().sum(1)
+    assert bool(((got - want).abs() <= 2e-6 * scale + 1e-9).all()), float(((got - want).abs() / (scale + 1e-9)).max())
+    y2, part2, _ = K.dw3x3_fprop(x, w9, T=T)
+    assert torch.equal(part, part2) and torch.equal(y, y2)
+
+
 def test_space_to_depth8_layout():
     K = _k()
     B, T, H, W = 2, 3, 64, 128
