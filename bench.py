@@ -260,8 +260,8 @@ EXPECT = {
     "snn_bn_finalize": ["bn_finalize_kernel"], "snn_bn_act_fwd": ["bn_act_fwd_kernel"], "snn_bn_act_bwd2": ["bwd2_kernel"],
     "snn_bn_act_bwd": ["bn_act_bwd_kernel"], "snn_bn_bwd_dx": ["bn_bwd_finalize_kernel", "bn_bwd_dx_kernel"],
     "snn_lstm_gates_fwd": ["lstm_gates_fwd_kernel"], "snn_lstm_gates_bwd": ["lstm_gates_bwd_kernel"],
-    "snn_colsum_bf16": ["colsum_bf16_kernel"], "snn_dw3x3_fprop": ["dw3x3_fwd_kernel"], "snn_dw3x3_dgrad": ["dw3x3_dgrad_kernel"],
-    "snn_dw3x3_wgrad": ["dw3x3_wgrad_kernel"], "snn_space_to_depth8": ["s2d8_kernel"], "snn_space_to_depth8_u8": ["s2d8_u8_kernel"],
+    "snn_colsum_bf16": ["colsum_bf16_kernel"], "snn_dw3x3_fprop": ["dw3x3_col_kernel"], "snn_dw3x3_fprop_stats": ["dw3x3_col_kernel"],
+    "snn_dw3x3_dgrad": ["dw3x3_col_kernel"], "snn_dw3x3_wgrad": ["dw3x3_wgrad_col_kernel"], "snn_space_to_depth8": ["s2d8_kernel"], "snn_space_to_depth8_u8": ["s2d8_u8_kernel"],
     "snn_grad_sumsq": ["sumsq_kernel"], "snn_adamw_step": ["adamw_kernel", "step_advance_kernel"],
     "snn_detect_assign_loss_fwd": ["detect_decode_kernel", "tal_metric_topk_kernel", "tal_resolve_kernel", "tal_targets_kernel",
                                    "detect_loss_fwd_kernel"],

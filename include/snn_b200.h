@@ -62,9 +62,11 @@ int snn_conv_fprop_stats(int geom, int NB, int H, int W,
 int snn_bn_stats_from_partials(const float* partials, double* sums /*[T][2][C]*/, int T, int C, int groups_per_step,
                                void* stream);
 /* snn_bn_stats_from_partials + snn_bn_finalize(training) + `num_batches_tracked += T` in ONE launch (same arithmetic, same
- * order of the T running-statistics updates).  `counters`: caller-owned, zero-initialised ceil(C/8) unsigned ints, left
- * zeroed; `sums` [T][2][C] fp64 is scratch that receives the reduced statistics. */
-int snn_bn_finalize_partials(const float* partials, double* sums, const float* gamma, const float* beta,
+ * order of the T running-statistics updates).  `counters`: caller-owned, zero-initialised ceil(C/32) unsigned ints, left
+ * zeroed; `sums` [T][2][C] fp64 receives the reduced statistics; `workspace`: snn_bn_finalize_workspace_doubles(T, C,
+ * groups_per_step) doubles of scratch (per-block partials, combined in a fixed order by the last block of a channel group). */
+long long snn_bn_finalize_workspace_doubles(int T, int C, int groups_per_step);
+int snn_bn_finalize_partials(const float* partials, double* sums, double* workspace, const float* gamma, const float* beta,
                              float* running_mean, float* running_var, long long* num_batches_tracked,
                              float* scale, float* shift, float* mean, float* invstd /*[T][C] each*/,
                              unsigned int* counters, int T, int C, int P, int groups_per_step, float eps, float momentum,

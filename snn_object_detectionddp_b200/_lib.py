@@ -21,7 +21,7 @@ _SIGNATURES = {
     "snn_conv_fprop": [_I, _I, _I, _I, _P, _I, _L, _P, _I, _L, _P, _I, _I, _I, _I, _I, _P, _P, _I, _L, _I, _I, _P],
     "snn_conv_fprop_stats": [_I, _I, _I, _I, _P, _I, _L, _P, _I, _L, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "snn_bn_stats_from_partials": [_P, _P, _I, _I, _I, _P],
-    "snn_bn_finalize_partials": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P],
+    "snn_bn_finalize_partials": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P],
     "snn_conv_dgrad": [_I, _I, _I, _I, _P, _I, _L, _P, _I, _I, _I, _P, _I, _L, _I, _I, _P],
     "snn_conv_wgrad": [_I, _I, _I, _I, _P, _I, _L, _P, _I, _L, _P, _I, _I, _P],
     "snn_weight_prep": [_P, _P, _P, _I, _I, _I, _P],
@@ -66,7 +66,7 @@ class SnnKernelError(RuntimeError):
 
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["snn_last_error", "snn_version", "snn_debug_set", "snn_conv_stats_groups", "snn_bn_stats_workspace_floats", "snn_nms_workspace_keys",
-                                             "snn_tal_workspace_bytes", "snn_dw3x3_stats_blocks"])
+                                             "snn_tal_workspace_bytes", "snn_dw3x3_stats_blocks", "snn_bn_finalize_workspace_doubles"])
 
 
 def lib():
@@ -90,6 +90,8 @@ def lib():
         L.snn_bn_stats_workspace_floats.restype = _L
         L.snn_nms_workspace_keys.argtypes = [_I, _I, _I]
         L.snn_nms_workspace_keys.restype = _L
+        L.snn_bn_finalize_workspace_doubles.argtypes = [_I, _I, _I]
+        L.snn_bn_finalize_workspace_doubles.restype = _L
         L.snn_dw3x3_stats_blocks.argtypes = [_I, _I, _I]
         L.snn_dw3x3_stats_blocks.restype = _L
         L.snn_tal_workspace_bytes.argtypes = [_I, _I, _I]

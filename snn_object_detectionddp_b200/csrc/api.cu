@@ -48,8 +48,9 @@ long long nms_workspace_keys(int, int, int);
 int launch_nms(const float*, int, int, int, float, float, int, int, int, int, float, unsigned long long*, long long, float*, int*,
                int*, cudaStream_t);
 int launch_bn_stats_from_partials(const float*, double*, int, int, int, cudaStream_t);
-int launch_bn_finalize_partials(const float*, double*, const float*, const float*, float*, float*, long long*, float*, float*, float*,
-                                float*, unsigned int*, int, int, int, int, float, float, cudaStream_t);
+int launch_bn_finalize_partials(const float*, double*, double*, const float*, const float*, float*, float*, long long*, float*, float*,
+                                float*, float*, unsigned int*, int, int, int, int, float, float, cudaStream_t);
+long long bn_finalize_workspace_doubles(int, int, int);
 int conv_dgrad(int, int, int, int, const void*, int, long long, const void*, int, int, int, void*, int, long long, int, int,
                cudaStream_t);
 int conv_wgrad(int, int, int, int, const void*, int, long long, const void*, int, long long, float*, int, int, cudaStream_t);
@@ -130,12 +131,13 @@ int snn_nms(const float* pred, int B, int nc, int A, float conf_thres, float iou
     return launch_nms(pred, B, nc, A, conf_thres, iou_thres, multi_label, agnostic, max_det, max_nms, max_wh, keys,
                       keys_per_image, out, out_idx, counts, ST);
 }
-int snn_bn_finalize_partials(const float* partials, double* sums, const float* gamma, const float* beta, float* running_mean,
-                             float* running_var, long long* num_batches_tracked, float* scale, float* shift, float* mean,
-                             float* invstd, unsigned int* counters, int T, int C, int P, int groups_per_step, float eps,
+long long snn_bn_finalize_workspace_doubles(int T, int C, int groups_per_step) { return bn_finalize_workspace_doubles(T, C, groups_per_step); }
+int snn_bn_finalize_partials(const float* partials, double* sums, double* workspace, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, long long* num_batches_tracked, float* scale, float* shift,
+                             float* mean, float* invstd, unsigned int* counters, int T, int C, int P, int groups_per_step, float eps,
                              float momentum, void* stream) {
-    return launch_bn_finalize_partials(partials, sums, gamma, beta, running_mean, running_var, num_batches_tracked, scale, shift,
-                                       mean, invstd, counters, T, C, P, groups_per_step, eps, momentum, ST);
+    return launch_bn_finalize_partials(partials, sums, workspace, gamma, beta, running_mean, running_var, num_batches_tracked, scale,
+                                       shift, mean, invstd, counters, T, C, P, groups_per_step, eps, momentum, ST);
 }
 int snn_bn_stats_from_partials(const float* partials, double* sums, int T, int C, int groups_per_step, void* stream) {
     return launch_bn_stats_from_partials(partials, sums, T, C, groups_per_step, ST);

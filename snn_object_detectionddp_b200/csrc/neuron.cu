@@ -95,87 +95,113 @@ __global__ void __launch_bounds__(kRL * 8) bn_stats_from_partials_kernel(const f
     }
 }
 
-// Fused tail of the train-mode BatchNorm statistics: partial reduce (as above) + per-(t,c) scale/shift/mean/invstd + the
-// T sequential running-stat updates + num_batches_tracked += T, one launch instead of three.  The block that finishes
-// LAST for a channel group (atomic ticket; the result does not depend on which block that is) walks t = 0..T-1 in order.
-// `counters` is a caller-owned, zero-initialised array of ceil(C/8) unsigned ints that the kernel leaves zeroed again.
-__global__ void __launch_bounds__(kRL * 8)
-bn_finalize_partials_kernel(const float* __restrict__ part, double* __restrict__ sums, const float* __restrict__ gamma,
-                            const float* __restrict__ beta, float* running_mean, float* running_var, long long* nbt,
-                            float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
-                            float* __restrict__ invstd_o, unsigned int* counters, int T, int C, int P, int groups_per_t,
+// Fused tail of the train-mode BatchNorm statistics: partial reduce + per-(t,c) scale/shift/mean/invstd + the T sequential
+// running-stat updates + num_batches_tracked += T, ONE launch.
+// Round 1 ran (C/8, T) blocks whose threads each read single floats 32 bytes apart: 12 us for 8 MB of partials, 3.5 % of HBM,
+// 28 launches per step.  Now: grid (C/32 channel groups, S splits of the partial rows); a warp reads 32 consecutive channels
+// (one 128-byte line) per load, 8 row-lanes per block, fp64 accumulation in a FIXED order; each block leaves its [T][2][32]
+// partial in `ws`; the block that finishes LAST for a channel group (atomic ticket -- the result does not depend on which
+// block that is) combines the S partials in split order and walks t = 0..T-1 for the running statistics.
+// `counters`: caller-owned, zero-initialised, >= ceil(C/32) unsigned ints; left zeroed.
+constexpr int kFinLanes = 8;
+constexpr int kFinMaxSplit = 64;
+static int bn_finalize_splits(int groups_per_t) {
+    int s = groups_per_t / (2 * kFinLanes);
+    return s < 1 ? 1 : (s > kFinMaxSplit ? kFinMaxSplit : s);
+}
+long long bn_finalize_workspace_doubles(int T, int C, int groups_per_t) {
+    if (T < 1 || C < 1 || groups_per_t < 1) return 0;
+    return (long long)((C + 31) / 32) * bn_finalize_splits(groups_per_t) * T * 2 * 32;
+}
+
+__global__ void __launch_bounds__(32 * kFinLanes)
+bn_finalize_partials_kernel(const float* __restrict__ part, double* __restrict__ ws, double* __restrict__ sums,
+                            const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
+                            long long* nbt, float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
+                            float* __restrict__ invstd_o, unsigned int* counters, int T, int C, int P, int groups_per_t, int S,
                             float eps, float momentum) {
-    __shared__ double sh[2][kRL][8];
+    __shared__ double sh[kFinLanes][2][32];
     __shared__ unsigned int s_ticket;
-    const int t = blockIdx.y;
-    const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;
-    const int c = blockIdx.x * 8 + cl;
-    double s = 0.0, q = 0.0;
-    if (c < C) {
-        const float* base = part + ((size_t)t * groups_per_t * 2) * C + c;
-        int r = rl;
-        for (; r + 3 * kRL < groups_per_t; r += 4 * kRL) {
-            const float* r0 = base + (size_t)r * 2 * C;
-            const float* r1 = base + (size_t)(r + kRL) * 2 * C;
-            const float* r2 = base + (size_t)(r + 2 * kRL) * 2 * C;
-            const float* r3 = base + (size_t)(r + 3 * kRL) * 2 * C;
-            const float a0 = __ldg(r0), b0 = __ldg(r0 + C), a1 = __ldg(r1), b1 = __ldg(r1 + C);
-            const float a2 = __ldg(r2), b2 = __ldg(r2 + C), a3 = __ldg(r3), b3 = __ldg(r3 + C);
-            s += (double)a0; q += (double)b0; s += (double)a1; q += (double)b1;
-            s += (double)a2; q += (double)b2; s += (double)a3; q += (double)b3;
+    const int cg = blockIdx.x, sp = blockIdx.y;
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = cg * 32 + cl;
+    const int chunk = (groups_per_t + S - 1) / S;
+    const int g0 = sp * chunk, g1 = min(groups_per_t, g0 + chunk);
+    double* my = ws + ((size_t)(cg * S + sp) * T) * 64;
+    for (int t = 0; t < T; ++t) {
+        double a = 0.0, b = 0.0;
+        if (c < C) {
+            const float* base = part + ((size_t)t * groups_per_t * 2) * C + c;
+            int r = g0 + rl;
+            for (; r + 3 * kFinLanes < g1; r += 4 * kFinLanes) {      // 8 independent loads in flight per thread
+                const float* p0 = base + (size_t)r * 2 * C;
+                const float* p1 = p0 + (size_t)kFinLanes * 2 * C;
+                const float* p2 = p1 + (size_t)kFinLanes * 2 * C;
+                const float* p3 = p2 + (size_t)kFinLanes * 2 * C;
+                const float a0 = __ldg(p0), b0 = __ldg(p0 + C), a1 = __ldg(p1), b1 = __ldg(p1 + C);
+                const float a2 = __ldg(p2), b2 = __ldg(p2 + C), a3 = __ldg(p3), b3 = __ldg(p3 + C);
+                a += (double)a0; b += (double)b0; a += (double)a1; b += (double)b1;
+                a += (double)a2; b += (double)b2; a += (double)a3; b += (double)b3;
+            }
+            for (; r < g1; r += kFinLanes) {
+                const float* p0 = base + (size_t)r * 2 * C;
+                a += (double)__ldg(p0); b += (double)__ldg(p0 + C);
+            }
         }
-        for (; r < groups_per_t; r += kRL) {
-            const float* r0 = base + (size_t)r * 2 * C;
-            s += (double)__ldg(r0); q += (double)__ldg(r0 + C);
+        sh[rl][0][cl] = a; sh[rl][1][cl] = b;
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            const int which = threadIdx.x >> 5;
+            double tot = 0.0;
+#pragma unroll
+            for (int i = 0; i < kFinLanes; ++i) tot += sh[i][which][cl];
+            my[(size_t)t * 64 + which * 32 + cl] = tot;
         }
+        __syncthreads();
     }
-    sh[0][rl][cl] = s; sh[1][rl][cl] = q;
+    __threadfence();                               // this block's partial is visible device-wide before its ticket is drawn
     __syncthreads();
-    if (threadIdx.x < 8) {
-        const int co = blockIdx.x * 8 + threadIdx.x;
-        if (co < C) {
-            double a = 0.0, b = 0.0;
-            for (int i = 0; i < kRL; ++i) { a += sh[0][i][threadIdx.x]; b += sh[1][i][threadIdx.x]; }
-            sums[((size_t)t * 2 + 0) * C + co] = a;
-            sums[((size_t)t * 2 + 1) * C + co] = b;
-            const double md = a / P;
-            double vd = b / P - md * md;
-            if (vd < 0) vd = 0;
-            const float m = (float)md, var = (float)vd;
-            const float inv = 1.0f / sqrtf(var + eps);
-            const float g = gamma ? gamma[co] : 1.f, bb = beta ? beta[co] : 0.f;
-            const float sc = g * inv;
-            scale[t * C + co] = sc; shift[t * C + co] = bb - m * sc;
-            mean_o[t * C + co] = m; invstd_o[t * C + co] = inv;
-        }
-        __threadfence();
-    }
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&counters[cg], 1u);
     __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&counters[blockIdx.x], 1u);
-    __syncthreads();
-    if (s_ticket != (unsigned)(T - 1)) return;
-    // last block of this channel group: every timestep's sums are visible
+    if (s_ticket != (unsigned)(S - 1)) return;
     __threadfence();
-    if (threadIdx.x < 8) {
-        const int co = blockIdx.x * 8 + threadIdx.x;
-        if (co < C && running_mean && running_var) {
-            float rm = running_mean[co], rv = running_var[co];
-            for (int tt = 0; tt < T; ++tt) {
-                const double a = __ldcg(&sums[((size_t)tt * 2 + 0) * C + co]), b = __ldcg(&sums[((size_t)tt * 2 + 1) * C + co]);
+    // last block of this channel group: combine the S partials in split order, (t, which) pairs spread over the 8 warps
+    double* tot_sh = &sh[0][0][0];                 // reuse: [T*2][32] needs T <= 8 per round
+    for (int t0 = 0; t0 < T; t0 += 4) {
+        const int pair = t0 * 2 + rl;              // rl in 0..7 -> (t, which) = (t0 + rl/2, rl&1)
+        if (pair < T * 2) {
+            const int t = pair >> 1, which = pair & 1;
+            double tot = 0.0;
+            for (int q = 0; q < S; ++q) tot += __ldcg(ws + ((size_t)(cg * S + q) * T + t) * 64 + which * 32 + cl);
+            tot_sh[rl * 32 + cl] = tot;
+            if (c < C) sums[((size_t)t * 2 + which) * C + c] = tot;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32 && c < C) {
+            for (int k = 0; k < 4 && t0 + k < T; ++k) {
+                const int t = t0 + k;
+                const double a = tot_sh[(2 * k) * 32 + cl], b = tot_sh[(2 * k + 1) * 32 + cl];
                 const double md = a / P;
                 double vd = b / P - md * md;
                 if (vd < 0) vd = 0;
                 const float m = (float)md, var = (float)vd;
-                const float unb = (P > 1) ? (float)(vd * ((double)P / (double)(P - 1))) : var;
-                rm = (1.f - momentum) * rm + momentum * m;
-                rv = (1.f - momentum) * rv + momentum * unb;
+                const float inv = 1.0f / sqrtf(var + eps);
+                const float g = gamma ? gamma[c] : 1.f, bb = beta ? beta[c] : 0.f;
+                const float sc = g * inv;
+                scale[t * C + c] = sc; shift[t * C + c] = bb - m * sc;
+                mean_o[t * C + c] = m; invstd_o[t * C + c] = inv;
+                if (running_mean && running_var) {       // the reference calls the module once per timestep: T updates in order
+                    const float unb = (P > 1) ? (float)(vd * ((double)P / (double)(P - 1))) : var;
+                    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+                    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+                }
             }
-            running_mean[co] = rm; running_var[co] = rv;
         }
+        __syncthreads();
     }
     if (threadIdx.x == 0) {
-        counters[blockIdx.x] = 0u;
-        if (blockIdx.x == 0 && nbt) *nbt += T;
+        counters[cg] = 0u;
+        if (cg == 0 && nbt) *nbt += T;
     }
 }
 
@@ -796,13 +822,15 @@ int launch_bn_stats_from_partials(const float* part, double* sums, int T, int C,
     return check_cuda(cudaGetLastError(), "bn_stats_from_partials_kernel");
 }
 
-int launch_bn_finalize_partials(const float* part, double* sums, const float* gamma, const float* beta, float* rm, float* rv,
-                                long long* nbt, float* scale, float* shift, float* mean, float* invstd, unsigned int* counters,
+int launch_bn_finalize_partials(const float* part, double* sums, double* workspace, const float* gamma, const float* beta, float* rm,
+                                float* rv, long long* nbt, float* scale, float* shift, float* mean, float* invstd, unsigned int* counters,
                                 int T, int C, int P, int groups_per_t, float eps, float momentum, cudaStream_t st) {
-    SNN_REQUIRE(T >= 1 && C >= 1 && groups_per_t >= 1 && counters != nullptr, "bn_finalize_partials: bad arguments");
-    dim3 grid((C + 7) / 8, T);
-    bn_finalize_partials_kernel<<<grid, kRL * 8, 0, st>>>(part, sums, gamma, beta, rm, rv, nbt, scale, shift, mean, invstd, counters,
-                                                          T, C, P, groups_per_t, eps, momentum);
+    SNN_REQUIRE(T >= 1 && C >= 1 && groups_per_t >= 1 && counters != nullptr && workspace != nullptr,
+                "bn_finalize_partials: bad arguments (workspace of snn_bn_finalize_workspace_doubles() doubles required)");
+    const int S = bn_finalize_splits(groups_per_t);
+    dim3 grid((C + 31) / 32, S);
+    bn_finalize_partials_kernel<<<grid, 32 * kFinLanes, 0, st>>>(part, workspace, sums, gamma, beta, rm, rv, nbt, scale, shift, mean, invstd,
+                                                                 counters, T, C, P, groups_per_t, S, eps, momentum);
     return check_cuda(cudaGetLastError(), "bn_finalize_partials_kernel");
 }
 

@@ -107,9 +107,10 @@ def bn_finalize_partials(part, gpt, gamma, beta, running_mean, running_var, num_
     dev = part.device
     scale, shift, mean, invstd = (torch.empty((T, C), device=dev, dtype=torch.float32) for _ in range(4))
     sums = torch.empty((T, 2, C), device=dev, dtype=torch.float64)
-    assert counters.dtype == torch.int32 and counters.numel() >= (C + 7) // 8
+    ws = torch.empty((int(_lib.lib().snn_bn_finalize_workspace_doubles(T, C, gpt)),), device=dev, dtype=torch.float64)
+    assert counters.dtype == torch.int32 and counters.numel() >= (C + 31) // 32
     assert num_batches_tracked is None or num_batches_tracked.dtype == torch.int64
-    call("snn_bn_finalize_partials", ptr(part), ptr(sums), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+    call("snn_bn_finalize_partials", ptr(part), ptr(sums), ptr(ws), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
          ptr(num_batches_tracked), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(counters), T, C, P, gpt, float(eps),
          float(momentum), stream_ptr(), work=("byte", 4.0 * part.numel()))
     return scale, shift, mean, invstd
