@@ -28,9 +28,10 @@ int snn_version(void);
 /* test / A-B timing knobs, all default 0 (never needed in production):
  *   0: 1 = per-thread row-store epilogue instead of swizzled staging + TMA tensor stores (conv fprop/dgrad)
  *   1: cap on the number of shared-memory pipeline stages        2: K chunks per pipeline stage (1, 2, 4)
+ *   3: 1 = a single epilogue warp group also for small-K convs (default: two groups, 320 threads)
  *   4: force the wgrad K-split                                   5: cap on persistent CTAs (pairs)
  *   6: 1 = single-CTA kernels only, 2 = CTA pairs also for small-K convs
- *   7: timing experiments: bit 0 = producer skips the TMA loads, bit 1 = MMA issuer skips the MMAs (results invalid)
+ *   7: (only in -DSNN_TIMING_KNOBS builds) bit 0 = producer skips the TMA loads, bit 1 = MMA issuer skips the MMAs
  *   8: 1 = T == 1 SiLU layers use the generic two-pass BN backward kernel */
 void snn_debug_set(int key, int value);
 

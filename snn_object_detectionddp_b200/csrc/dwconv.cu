@@ -27,13 +27,41 @@ SNN_DEVINL uint4 ld_px(const __nv_bfloat16* __restrict__ base, long long row_off
     return __ldg(reinterpret_cast<const uint4*>(base + row_off + (long long)w * C) + cg);
 }
 
-// grid (ceil(cols_per_group / slots), groups): group = timestep (fprop with statistics) or 1; a column = (image, w)
+// One input row (3 neighbouring pixels x 8 channels) unpacked ONCE to fp32 channel pairs; the 3-row window lives in registers
+// and the row loop is unrolled by three so that the rows rotate by renaming, not by register moves.  The first version of this
+// kernel kept the window packed and unpacked every tap (72 shift/and + 72 scalar FMA per output row): ncu showed 360
+// warp-instructions per row and 42 % issue utilisation at 14 % of DRAM bandwidth -- instruction bound.  Now 24 unpack +
+// 36 packed FFMA2 per row.
+struct DwRow { float2 v[3][2]; };             // 3 neighbouring pixels x 4 channels (two channel pairs)
+// col[k]: this thread's 8-byte piece of pixel (row 0, w + k - 1), or nullptr when that column is outside the map;
+// off: row offset in uint2 units.  (Pointers and validity are hoisted out of the row loop: the first cut recomputed 64-bit
+// addresses and bounds per load and spent 120 warp-instructions per output row.)
+SNN_DEVINL void dw_load_row(DwRow& r, const uint2* const col[3], long long off, bool valid) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        uint2 p = make_uint2(0u, 0u);
+        if (valid && col[k] != nullptr) p = __ldg(col[k] + off);
+        r.v[k][0] = make_float2(bf16_lo(p.x), bf16_hi(p.x));
+        r.v[k][1] = make_float2(bf16_lo(p.y), bf16_hi(p.y));
+    }
+}
+SNN_DEVINL void dw_mac_row(float2 acc[2], const DwRow& r, const float* __restrict__ shw, int kh, int C, int cg) {
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+        const float4 wa = *reinterpret_cast<const float4*>(shw + (kh * 3 + kw) * C + cg * 4);
+        acc[0] = __ffma2_rn(r.v[kw][0], make_float2(wa.x, wa.y), acc[0]);
+        acc[1] = __ffma2_rn(r.v[kw][1], make_float2(wa.z, wa.w), acc[1]);
+    }
+}
+
+// grid (ceil(cols_per_group / slots), groups): group = timestep (fprop with statistics) or 1; a column = (image, w);
+// a thread owns 4 channels of one column (8-byte loads: 36 window registers, 3 blocks of 256 threads per SM)
 template <bool DGRAD>
 __global__ void __launch_bounds__(256)
 dw3x3_col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt, float* __restrict__ y32,
                  __nv_bfloat16* __restrict__ y16, float* __restrict__ part, int imgs_per_group, int H, int W, int C) {
     extern __shared__ float sh[];                 // [9][C] weights, then (statistics) [slots][2][C]
-    const int c8 = C >> 3, slots = 256 / c8;
+    const int c4 = C >> 2, slots = 256 / c4;
     float* shw = sh;
     float* shs = sh + 9 * C;
     for (int i = threadIdx.x; i < 9 * C; i += 256) {
@@ -41,61 +69,67 @@ dw3x3_col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
         shw[i] = wgt[(DGRAD ? 8 - tap : tap) * C + c];            // dgrad: flipped taps
     }
     __syncthreads();
-    const int slot = threadIdx.x / c8, cg = threadIdx.x % c8;
+    const int slot = threadIdx.x / c4, cg = threadIdx.x % c4;
     const int cols = imgs_per_group * W;
     const int col = blockIdx.x * slots + slot;
-    float ssum[8], ssq[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ssum[i] = ssq[i] = 0.f;
+    float2 ssum[2], ssq[2];
+    ssum[0] = ssum[1] = ssq[0] = ssq[1] = make_float2(0.f, 0.f);
     if (slot < slots && col < cols) {
         const int w = col % W;
         const long long n = (long long)blockIdx.y * imgs_per_group + col / W;
-        const __nv_bfloat16* img = x + n * H * W * C;
-        const long long rs = (long long)W * C;
-        uint4 r0[3], r1[3], r2[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { r0[k] = make_uint4(0u, 0u, 0u, 0u); r1[k] = ld_px(img, 0, w + k - 1, W, C, cg); }
-        for (int h = 0; h < H; ++h) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) r2[k] = (h + 1 < H) ? ld_px(img, (long long)(h + 1) * rs, w + k - 1, W, C, cg) : make_uint4(0u, 0u, 0u, 0u);
-            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    float v[8];
-                    unpack8f(kh == 0 ? r0[kw] : (kh == 1 ? r1[kw] : r2[kw]), v);
-                    const float4 wa = *reinterpret_cast<const float4*>(shw + (kh * 3 + kw) * C + cg * 8);
-                    const float4 wb = *reinterpret_cast<const float4*>(shw + (kh * 3 + kw) * C + cg * 8 + 4);
-                    acc[0] += v[0] * wa.x; acc[1] += v[1] * wa.y; acc[2] += v[2] * wa.z; acc[3] += v[3] * wa.w;
-                    acc[4] += v[4] * wb.x; acc[5] += v[5] * wb.y; acc[6] += v[6] * wb.z; acc[7] += v[7] * wb.w;
-                }
-            }
-            const long long o = ((n * H + h) * W + w) * C + cg * 8;
+        const long long rs4 = ((long long)W * C) >> 2;                 // row stride in 4-channel units
+        const long long base4 = (n * H * W + w) * (long long)(C >> 2) + cg;
+        const uint2* xin = reinterpret_cast<const uint2*>(x);
+        const uint2* colp[3] = {w > 0 ? xin + base4 - (C >> 2) : nullptr, xin + base4, w + 1 < W ? xin + base4 + (C >> 2) : nullptr};
+        const bool want_stats = !DGRAD && part != nullptr;
+        long long o4 = base4;                                          // output piece of row h (same layout as the input)
+
+        auto emit = [&](const DwRow& a, const DwRow& b, const DwRow& c) {      // rows h-1, h, h+1 -> output row h
+            float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            dw_mac_row(acc, a, shw, 0, C, cg);
+            dw_mac_row(acc, b, shw, 1, C, cg);
+            dw_mac_row(acc, c, shw, 2, C, cg);
             if (DGRAD) {
-                uint4 pk;
-                pk.x = pack_bf16x2(acc[0], acc[1]); pk.y = pack_bf16x2(acc[2], acc[3]);
-                pk.z = pack_bf16x2(acc[4], acc[5]); pk.w = pack_bf16x2(acc[6], acc[7]);
-                *reinterpret_cast<uint4*>(y16 + o) = pk;
+                reinterpret_cast<uint2*>(y16)[o4] = make_uint2(pack_bf16x2(acc[0].x, acc[0].y), pack_bf16x2(acc[1].x, acc[1].y));
             } else {
-                float4* op = reinterpret_cast<float4*>(y32 + o);
-                op[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                op[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-                if (part) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { ssum[i] += acc[i]; ssq[i] = fmaf(acc[i], acc[i], ssq[i]); }
+                reinterpret_cast<float4*>(y32)[o4] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+                if (want_stats) {
+                    ssum[0] = __fadd2_rn(ssum[0], acc[0]); ssq[0] = __ffma2_rn(acc[0], acc[0], ssq[0]);
+                    ssum[1] = __fadd2_rn(ssum[1], acc[1]); ssq[1] = __ffma2_rn(acc[1], acc[1], ssq[1]);
                 }
             }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { r0[k] = r1[k]; r1[k] = r2[k]; }
+            o4 += rs4;
+        };
+
+        DwRow r0, r1, r2;
+        dw_load_row(r0, colp, 0, false);                               // row -1: zero padding
+        dw_load_row(r1, colp, 0, true);
+        long long off = rs4;                                           // offset of row h + 1
+        int h = 0;
+        for (; h + 2 < H; h += 3) {                                    // rows rotate by renaming
+            dw_load_row(r2, colp, off, true);
+            emit(r0, r1, r2);
+            dw_load_row(r0, colp, off + rs4, true);
+            emit(r1, r2, r0);
+            dw_load_row(r1, colp, off + 2 * rs4, h + 3 < H);
+            emit(r2, r0, r1);
+            off += 3 * rs4;
+        }
+        if (h < H) {                                                   // 1 or 2 rows left; window is (r0, r1) = rows (h-1, h)
+            dw_load_row(r2, colp, off, h + 1 < H);
+            emit(r0, r1, r2);
+            if (h + 1 < H) {
+                dw_load_row(r0, colp, 0, false);                       // row H: zero padding
+                emit(r1, r2, r0);
+            }
         }
     }
     if (!DGRAD && part) {
         // per-block partial sums in a FIXED order (deterministic): slot rows in shared memory, column-summed by C threads
         if (slot < slots) {
             float* row = shs + (size_t)slot * 2 * C;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { row[cg * 8 + i] = ssum[i]; row[C + cg * 8 + i] = ssq[i]; }
+            row[cg * 4 + 0] = ssum[0].x; row[cg * 4 + 1] = ssum[0].y; row[cg * 4 + 2] = ssum[1].x; row[cg * 4 + 3] = ssum[1].y;
+            row[C + cg * 4 + 0] = ssq[0].x; row[C + cg * 4 + 1] = ssq[0].y; row[C + cg * 4 + 2] = ssq[1].x; row[C + cg * 4 + 3] = ssq[1].y;
         }
         __syncthreads();
         float* dst = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C;
@@ -191,7 +225,7 @@ s2d8_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B
 // blocks the column kernels launch per statistics group (also the number of partial rows per timestep)
 long long dw3x3_stats_blocks(int B, int W, int C) {
     if (C % 8 != 0 || C < 8 || C > 1024 || B < 1 || W < 1) return 0;
-    const int slots = 256 / (C / 8);
+    const int slots = 256 / (C / 4);
     return ((long long)B * W + slots - 1) / slots;
 }
 
@@ -200,7 +234,7 @@ int launch_dw3x3_fwd(const __nv_bfloat16* x, const float* w, float* y, int NB, i
     SNN_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1024, "dw3x3: C=%d must be a multiple of 8 in [8,1024]", C);
     if (!part || groups < 1) groups = 1;
     SNN_REQUIRE(NB % groups == 0, "dw3x3: NB=%d is not a multiple of the %d statistics groups", NB, groups);
-    const int B = NB / groups, slots = 256 / (C / 8);
+    const int B = NB / groups, slots = 256 / (C / 4);
     const size_t smem = sizeof(float) * (9 * (size_t)C + (part ? (size_t)slots * 2 * C : 0));
     static PerDeviceOnce once;
     SNN_CUDA_OK(once.run([] { return cudaFuncSetAttribute(dw3x3_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));

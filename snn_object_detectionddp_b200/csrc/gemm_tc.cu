@@ -16,7 +16,7 @@
 //                       (both operands MN-major straight from the NHWC tensors, split-K + fp32 red)
 //
 // Warp roles (192 threads): warp0 = TMA producer + TMEM owner, warp1 = MMA issuer, warps2-5 =
-// epilogue (one TMEM lane quarter each).
+// epilogue (one TMEM lane quarter each); small-K convs launch 320 threads: warps 6-9 = a second epilogue group.
 #include <atomic>
 #include <mutex>
 
@@ -58,6 +58,7 @@ struct ConvGemmParams {
     int cps, chunk_bytes;             // 64-wide K chunks per pipeline stage (1, 2 or 4: narrow-N tiles need more MMA work per
                                       // mbarrier round trip) and bytes of one chunk (A 16 KB + this CTA's B slice)
     int nbuf;                         // epilogue staging tiles per warp (2, or 4 for small-K convs: TMA-store latency bound)
+    int epi_groups;                   // 1: warps 2-5 run the epilogue (192 threads); 2: warps 6-9 too (320 threads, small-K convs)
     int ksplit;                       // K split over the tap segments (fp32 output, TMA reduce-add): fills the GPU on small-M convs
     int dbg;                          // -DSNN_TIMING_KNOBS builds only: bit 0 = producer skips the TMA loads, bit 1 = no MMA issue
     Phase phase[4];
@@ -103,7 +104,7 @@ constexpr int kTmemCols = 256;
 constexpr int kAccCols = 256;
 
 template <bool PAIR>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                  const __grid_constant__ ConvGemmParams p) {
@@ -143,7 +144,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-            mbar_init(smem_u32(&tmem_empty_bar[a]), PAIR ? 8 : 4);   // one arrive per epilogue warp (of both CTAs)
+            mbar_init(smem_u32(&tmem_empty_bar[a]), (PAIR ? 8u : 4u) * (uint32_t)p.epi_groups);   // one arrive per epilogue warp (of both CTAs)
         }
         mbar_fence_init();
     }
@@ -279,11 +280,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
     } else {
         // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+        // epi_groups == 2 (small-K convs, 320 threads): warps 6-9 form a second epilogue group on the same TMEM lane quarters
+        // and take the odd column chunks.  With K <= 8 chunks per tile the epilogue IS the kernel (ncu, profiles/r2: the MMA
+        // warp waits, every epilogue instruction carries equal stall samples = one dependent chain per scheduler); two
+        // warps per scheduler overlap those latencies.
         const int q = warp & 3;
+        const int grp = warp >= 6 ? 1 : 0, ngrp = p.epi_groups;
         const int row = q * 32 + lane;
         const int wl = row % p.bw, hl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
         int lt = 0;
-        uint32_t gcc = 0;     // staging-tile counter across all tiles of this warp: two buffers in rotation
+        uint32_t gcc = 0;     // staging-tile counter across all tiles of this warp: nbuf buffers in rotation
         for (int tile = worker; tile < total_tiles; tile += nworkers, ++lt) {
             const int mt = (tile % m_work) * (PAIR ? 2 : 1) + (int)rank, rest = tile / m_work;
             const int ncol0 = (rest % p.n_blocks) * p.BN;
@@ -302,25 +308,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 // tensor store per warp and chunk.  The v1 epilogue (thread = row writing 64 B pieces 1 KB+ apart) cost
                 // 30k cycles per 128x256 tile in LSU transactions -- more than the MMA main loop (profiles/r1 probe).
                 const int CH = p.out_f32 ? 32 : 64;                       // columns per 128-byte row
+                const int chs = p.out_f32 ? 5 : 6;
                 const int row0 = q * 32;
                 const int bw_ = p.bw, bh_ = p.bh;
                 const int cw = tw * bw_ + row0 % bw_, chh = th * bh_ + (row0 / bw_) % bh_, cn = tn * p.bn + row0 / (bw_ * bh_);
                 const int cbase = (p.os == 2 ? ph.opw * (int)p.out_ld : 0);
                 const int cph = (p.os == 2 ? ph.oph : 0);
-                const uint32_t stg0 = sbase + (uint32_t)stages * stage_bytes + (uint32_t)(q * p.nbuf) * 4096u;
-                const int nch = (min(p.BN, p.n_store - ncol0) + CH - 1) / CH;
-                for (int cc = 0; cc < nch; ++cc, ++gcc) {
-                    const uint32_t buf = stg0 + (gcc % (uint32_t)p.nbuf) * 4096u;
+                const uint32_t stg0 = sbase + (uint32_t)stages * stage_bytes + (uint32_t)((grp * 4 + q) * p.nbuf) * 4096u;
+                const int nch = (min(p.BN, p.n_store - ncol0) + CH - 1) >> chs;
+                const bool has_bias = p.bias != nullptr;
+                for (int cc = grp; cc < nch; cc += ngrp, ++gcc) {
+                    const uint32_t buf = stg0 + (gcc & (uint32_t)(p.nbuf - 1)) * 4096u;       // nbuf is 2 or 4
                     uint32_t r[32];
                     if (p.out_f32) {
                         tmem_ld16(trow + (uint32_t)(cc * 32), r);
                         tmem_ld16(trow + (uint32_t)(cc * 32 + 16), r + 16);
                         tmem_ld_wait();
-                        if (p.bias) {
+                        if (has_bias) {         // the same 32 bias values for every lane: 8 broadcast 16-byte loads
+                            const int c0 = ncol0 + cc * 32;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const int c = ncol0 + cc * 32 + j;
-                                if (c < p.n_store) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(p.bias + c));
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (c0 + 4 * j4 < p.n_store) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j4);   // n_store % 8 == 0
+                                r[4 * j4 + 0] = __float_as_uint(__uint_as_float(r[4 * j4 + 0]) + bv.x);
+                                r[4 * j4 + 1] = __float_as_uint(__uint_as_float(r[4 * j4 + 1]) + bv.y);
+                                r[4 * j4 + 2] = __float_as_uint(__uint_as_float(r[4 * j4 + 2]) + bv.z);
+                                r[4 * j4 + 3] = __float_as_uint(__uint_as_float(r[4 * j4 + 3]) + bv.w);
                             }
                         }
                     } else {
@@ -330,14 +343,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             tmem_ld16(trow + (uint32_t)(cc * 64 + hh * 32), t32);
                             tmem_ld16(trow + (uint32_t)(cc * 64 + hh * 32 + 16), t32 + 16);
                             tmem_ld_wait();
+                            if (has_bias) {
+                                const int c0 = ncol0 + cc * 64 + hh * 32;
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                float a = __uint_as_float(t32[2 * j]), b = __uint_as_float(t32[2 * j + 1]);
-                                if (p.bias) {
-                                    const int c = ncol0 + cc * 64 + hh * 32 + 2 * j;
-                                    if (c < p.n_store) { a += __ldg(p.bias + c); b += __ldg(p.bias + c + 1); }
+                                for (int j4 = 0; j4 < 8; ++j4) {
+                                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (c0 + 4 * j4 < p.n_store) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j4);
+                                    r[hh * 16 + 2 * j4] = pack_bf16x2(__uint_as_float(t32[4 * j4]) + bv.x, __uint_as_float(t32[4 * j4 + 1]) + bv.y);
+                                    r[hh * 16 + 2 * j4 + 1] = pack_bf16x2(__uint_as_float(t32[4 * j4 + 2]) + bv.z, __uint_as_float(t32[4 * j4 + 3]) + bv.w);
                                 }
-                                r[hh * 16 + j] = pack_bf16x2(a, b);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    r[hh * 16 + j] = pack_bf16x2(__uint_as_float(t32[2 * j]), __uint_as_float(t32[2 * j + 1]));
                             }
                         }
                     }
@@ -394,7 +412,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 continue;
             }
             const int nchunks = p.BN >> 4;
-            for (int ch = 0; ch < nchunks; ++ch) {
+            for (int ch = grp; ch < nchunks; ch += ngrp) {
                 uint32_t r[16];
                 tmem_ld16(trow + (uint32_t)(ch * 16), r);
                 tmem_ld_wait();
@@ -826,8 +844,9 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     p.tma_out = g_debug_flags[0] != 1 && !(p.accumulate && !p.out_f32) && ((uintptr_t)obase % 16 == 0) && ((p.out_ld * es) % 16 == 0) &&
                 (p.os == 1 || (p.n_store % CH == 0 && p.Ho % 2 == 0 && p.Wo % 2 == 0));
     SNN_REQUIRE(!p.stats || p.tma_out, "conv_fprop: fused statistics need the TMA-store epilogue (output alignment)");
-    p.nbuf = small_k ? 4 : 2;
-    const int stage_extra = p.tma_out ? 4 * p.nbuf * 4096 : 0;     // 4 epilogue warps x nbuf staging tiles of 32 rows x 128 B
+    p.nbuf = 2;                       // (four staging tiles per warp were measured to change nothing, profiles/README.md)
+    p.epi_groups = (small_k && g_debug_flags[3] != 1) ? 2 : 1;          // knob 3 = 1: one epilogue group everywhere (A/B timing, tests)
+    const int stage_extra = p.tma_out ? 4 * p.epi_groups * p.nbuf * 4096 : 0;     // epilogue warps x nbuf staging tiles of 32 rows x 128 B
     while (p.cps > 1 && (smem_budget() - stage_extra) / (p.cps * p.chunk_bytes) < 3) p.cps >>= 1;   // keep >= 3 stages
     p.stage_bytes = p.cps * p.chunk_bytes;
     int stages = (smem_budget() - stage_extra) / p.stage_bytes;
@@ -855,7 +874,7 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
         int grid = num_sms();
         if (g_debug_flags[5] > 0) grid = g_debug_flags[5];
         if (grid > total_tiles) grid = total_tiles;
-        conv_gemm_kernel<false><<<grid, 192, smem, st>>>(a0, a1, b, o, p);
+        conv_gemm_kernel<false><<<grid, 64 + 128 * p.epi_groups, smem, st>>>(a0, a1, b, o, p);
         return check_cuda(cudaGetLastError(), "conv_gemm_kernel launch");
     }
     const int total_tiles = ((m_tiles + 1) / 2) * p.n_blocks * p.nphase * p.ksplit;
@@ -865,7 +884,7 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * pairs, 1, 1);
-    cfg.blockDim = dim3(192, 1, 1);
+    cfg.blockDim = dim3(64 + 128 * p.epi_groups, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
