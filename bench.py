@@ -234,6 +234,57 @@ def gpu_eager_run(T, HW, batch, steps, warmup, neuron, dev):
     return out
 
 
+def dropin_run(T, HW, batch, steps, warmup, neuron, dev):
+    """The reference's own training-loop body (train.py:58-80: per-frame `model(frame, hidden)` loop, `loss_fn(preds, batch)`,
+    `.sum().backward()`, `clip_grad_norm_`, torch AdamW + OneCycleLR) running UNCHANGED on the drop-in modules -- the
+    "4 import lines" route of INTEGRATION.md section 1.  Every kernel is launched from Python (no CUDA graph, T per-frame
+    passes, NCHW<->NHWC conversions at the module boundary): host-bound, reported next to the fused Trainer path."""
+    import torch
+    from snn_object_detectionddp_b200 import _lib
+    from snn_object_detectionddp_b200.data import synthetic_batch
+    from snn_object_detectionddp_b200.loss import v8DetectionLoss
+    from snn_object_detectionddp_b200.model import YOLOTemporalUNet
+    from snn_object_detectionddp_b200.weight_initialization import initialize_model
+    torch.manual_seed(42)
+    model = YOLOTemporalUNet(num_classes=NUM_CLASSES, yolo_model_name="yolo11m.pt", use_conv_lstm=True, hyp=HYP, neuron=neuron).to(dev)
+    initialize_model(model)
+    loss_fn = v8DetectionLoss(model)
+    optimizer = torch.optim.AdamW(model.parameters(), weight_decay=WEIGHT_DECAY)
+    scheduler = torch.optim.lr_scheduler.OneCycleLR(optimizer, max_lr=MAX_LR, total_steps=1000, pct_start=0.3, anneal_strategy="cos")
+    frames, labels = synthetic_batch(batch, T, HW, HW, nc=NUM_CLASSES, seed=42)
+    image_tensor, labels_tensor = frames.to(dev), labels.to(dev)
+    model.train()
+
+    def step():
+        optimizer.zero_grad(set_to_none=True)
+        hidden_state = None
+        for t in range(T):
+            preds, hidden_state = model(image_tensor[:, t, :, :, :], hidden_state)
+        batch_dict = {"batch_idx": labels_tensor[:, 0], "cls": labels_tensor[:, 1], "bboxes": labels_tensor[:, 2:]}
+        loss_components, _ = loss_fn(preds, batch_dict)
+        loss_components.sum().backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=10.0)
+        optimizer.step()
+        scheduler.step()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": batch / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "gpu_launches_per_step": (_lib.launch_count - l0) / steps,
+           "what": "reference train.py:58-80 loop body verbatim on the drop-in modules (per-frame calls, list-of-maps loss, torch AdamW/OneCycleLR), eager"}
+    del model, optimizer, scheduler, loss_fn
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu_eager(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -376,7 +427,8 @@ def measure_config(args, cfg_idx, dev, rank, local, world, pk, full):
     torch.manual_seed(42)
     model = YOLOTemporalUNet(num_classes=NUM_CLASSES, yolo_model_name="yolo11m.pt", use_conv_lstm=True, hyp=HYP, neuron=args.neuron)
     initialize_model(model)
-    trainer = Trainer(model, max_lr=MAX_LR, weight_decay=WEIGHT_DECAY, total_steps=1000, device=dev)
+    trainer = Trainer(model, max_lr=MAX_LR, weight_decay=WEIGHT_DECAY, total_steps=1000, device=dev,
+                      bucket_mb=int(os.environ.get("SNN_BUCKET_MB", "32")))
     frames_cpu, labels_cpu = synthetic_batch(B, T, HW, HW, nc=NUM_CLASSES, seed=42 + rank)
     frames = frames_cpu.to(dev)
     MAXB = 8                                              # synthetic labels: 0-7 boxes per sample
@@ -560,8 +612,10 @@ def run_ours(args):
 
     B, T, HW = main["B"], main["T"], main["HW"]
     cpu_baseline = gpu_eager = lif = None
+    dropin = None
     if world == 1 and not args.no_gpu_eager:
         gpu_eager = gpu_eager_run(T, HW, B, 3, 2, args.neuron, dev)
+        dropin = dropin_run(T, HW, B, 3, 2, args.neuron, dev)
     if world == 1 and not args.no_lif:
         s2 = ClockSampler(local)
         s2.start()
@@ -583,7 +637,7 @@ def run_ours(args):
                    "l2": "per-step working set (240 MB bf16 weights + GBs of activations) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world}", "feature_extractor": "stand-in frozen pyramid (YOLO11m weights unobtainable offline)"},
         "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["launches"], "roofline": main["roofline"],
-        "cpu_baseline": cpu_baseline, "gpu_eager_baseline": gpu_eager, "cfg3": cfg3, "ranks_in_lockstep": main["lockstep"],
+        "cpu_baseline": cpu_baseline, "gpu_eager_baseline": gpu_eager, "dropin_eager": dropin, "cfg3": cfg3, "ranks_in_lockstep": main["lockstep"],
         "cuda_graph_active": main["graph_active"], "cuda_graph": main["graphed"],
         "kernel_timing": main["timing"], "kernels": main["kernels"], "kernels_by_shape": main["by_shape"],
         "kernel_ms_sum_per_step": main["kernel_ms_sum"], "other_kernels_ms_per_step": main["other_kernels"],
