@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-cfg3", action="store_true", help="skip the configs[2] (T=8, 512x512) sub-record")
     ap.add_argument("--no-lif", action="store_true", help="skip the configs[3] LIF sweep sub-record")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager GPU comparator")
+    ap.add_argument("--dump-trace", default=None, help="write the ABI call sequence of one training step (name, work, shape tag) as JSON")
     return ap.parse_args()
 
 
@@ -441,6 +442,13 @@ def measure_config(args, cfg_idx, dev, rank, local, world, pk, full):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.dump_trace and full and rank == 0:
+        trainer.train_step(frames, batch_dev)
+        _lib.trace = tr_ = []
+        trainer.train_step(frames, batch_dev)
+        _lib.trace = None
+        json.dump([[n, (list(w) if w else None)] for n, w in tr_], open(args.dump_trace, "w"))
 
     # ---------------- device-resident throughput ----------------
     trace = None

@@ -262,6 +262,85 @@ SNN_DEVINL void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, 
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------
+// Dynamic tile scheduler of the persistent GEMM kernels.
+// Round 1 walked tiles statically (tile = worker, worker + nworkers, ...): with gradient all-reduces running beside backward,
+// the SMs that also host NCCL CTAs run their tiles slower and every launch waits for them (conv dgrad 896 -> 810 TF/s from 1
+// to 8 GPUs in SCALE_r01).  Now a worker's first tile is static and every further one comes from a global atomic counter;
+// the leader CTA's producer warp fetches it and hands it to the other warps (and to the peer CTA of a pair, through
+// distributed shared memory) over a 4-slot ring guarded by mbarriers.  The last worker to finish zeroes the counters, so a
+// launch always finds them at 0 (kernels that share a counter pair are stream-ordered).
+// ------------------------------------------------------------------------------------------
+constexpr int kSchedSlots = 4;
+struct __align__(8) SchedRing {
+    uint64_t full[kSchedSlots];
+    uint64_t empty[kSchedSlots];
+    int tile[kSchedSlots];
+};
+SNN_DEVINL uint32_t mapa_u32(uint32_t addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+    return r;
+}
+SNN_DEVINL void st_shared_cluster_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+SNN_DEVINL void mbar_wait_cluster(uint32_t bar, uint32_t parity) {      // acquire at cluster scope (data written by the peer CTA)
+    uint32_t spins = 0, ok = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+SNN_DEVINL void sched_init(SchedRing& r, uint32_t consumers) {           // one thread, before the block/cluster barrier
+    for (int s = 0; s < kSchedSlots; ++s) {
+        mbar_init(smem_u32(&r.full[s]), 1);
+        mbar_init(smem_u32(&r.empty[s]), consumers);
+    }
+}
+// scheduler side: the leader CTA's producer warp (all 32 lanes call; `lead` = the elected lane)
+template <bool PAIR>
+SNN_DEVINL void sched_publish(SchedRing& r, int it, int tile, bool lead) {
+    const int s = it & (kSchedSlots - 1);
+    mbar_wait(smem_u32(&r.empty[s]), (uint32_t)(((it / kSchedSlots) & 1) ^ 1));      // every reader of the slot's previous tile has it
+    if (lead) {
+        *reinterpret_cast<volatile int*>(&r.tile[s]) = tile;
+        if (PAIR) st_shared_cluster_u32(mapa_u32(smem_u32(&r.tile[s]), 1u), (uint32_t)tile);
+        mbar_arrive(smem_u32(&r.full[s]));
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&r.full[s]), 1u));
+    }
+    __syncwarp();
+}
+// reader side: any other role warp of either CTA (all 32 lanes call); returns the tile with sequence number `it`, -1 = done
+template <bool PAIR>
+SNN_DEVINL int sched_next(SchedRing& r, int it, int lane) {
+    const int s = it & (kSchedSlots - 1);
+    if (PAIR) mbar_wait_cluster(smem_u32(&r.full[s]), (uint32_t)((it / kSchedSlots) & 1));
+    else mbar_wait(smem_u32(&r.full[s]), (uint32_t)((it / kSchedSlots) & 1));
+    const int t = *reinterpret_cast<volatile int*>(&r.tile[s]);
+    __syncwarp();
+    if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&r.empty[s]), 0u));           // the LEADER's ring collects all readers
+        else mbar_arrive(smem_u32(&r.empty[s]));
+    }
+    return t;
+}
+// end of kernel, one thread per worker: the last worker to finish leaves both counters at zero for the next launch
+SNN_DEVINL void sched_finish(unsigned int* sched, int nworkers) {
+    __threadfence();
+    const unsigned int old = atomicAdd(sched + 1, 1u);
+    if (old == (unsigned)(nworkers - 1)) {
+        sched[0] = 0u;
+        sched[1] = 0u;
+        __threadfence();
+    }
+}
+
 SNN_DEVINL bool elect_one() {
     uint32_t pred;
     asm volatile(

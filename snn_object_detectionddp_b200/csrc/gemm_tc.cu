@@ -59,6 +59,7 @@ struct ConvGemmParams {
                                       // mbarrier round trip) and bytes of one chunk (A 16 KB + this CTA's B slice)
     int nbuf;                         // epilogue staging tiles per warp (2, or 4 for small-K convs: TMA-store latency bound)
     int epi_groups;                   // 1: warps 2-5 run the epilogue (192 threads); 2: warps 6-9 too (320 threads, small-K convs)
+    unsigned int* sched;              // dynamic tile scheduler: {next tile - nworkers, finished workers}, both 0 at launch
     int ksplit;                       // K split over the tap segments (fp32 output, TMA reduce-add): fills the GPU on small-M convs
     int dbg;                          // -DSNN_TIMING_KNOBS builds only: bit 0 = producer skips the TMA loads, bit 1 = no MMA issue
     Phase phase[4];
@@ -84,6 +85,7 @@ struct WgradParams {
     int stages, stage_bytes;
     int lbo_bytes, sbo_bytes;         // MN-major descriptor strides
     int ntaps;
+    unsigned int* sched;              // dynamic work-item scheduler counters (see SchedRing)
     WTap taps[9];
 };
 
@@ -113,6 +115,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ SchedRing ring;
     __shared__ uint32_t tmem_base_s;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp: provably uniform
@@ -146,6 +149,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_init(smem_u32(&tmem_full_bar[a]), 1);
             mbar_init(smem_u32(&tmem_empty_bar[a]), (PAIR ? 8u : 4u) * (uint32_t)p.epi_groups);   // one arrive per epilogue warp (of both CTAs)
         }
+        // readers of a tile id: MMA warp + epilogue warps of the leader; producer warp + epilogue warps of the peer
+        sched_init(ring, (PAIR ? 2u : 1u) * (1u + 4u * (uint32_t)p.epi_groups));
         mbar_fence_init();
     }
     tc_fence_before();
@@ -158,10 +163,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // thread -- which, not the tensor pipe, bounded v1 at ~635 cycles per 64-wide K chunk -- drops several-fold.
     if (warp == 0) {
         const bool lead = elect_one();
+        const int lead_lane = __ffs(__ballot_sync(0xffffffffu, lead)) - 1;
         int s = 0;
         uint32_t par = 0;
         uint32_t a_s = sbase;
-        for (int tile = worker; tile < total_tiles; tile += nworkers) {
+        int tile = worker, nxt = 0;
+        for (int it = 0;; ++it) {
+            if (rank == 0) {                 // this warp is the tile scheduler of the CTA (pair)
+                if (tile >= total_tiles) tile = -1;
+                sched_publish<PAIR>(ring, it, tile, lead);
+                if (tile < 0) break;
+                if (lead) nxt = (int)atomicAdd(p.sched, 1u) + nworkers;      // next tile id: needed only after this tile's loads
+            } else {
+                tile = sched_next<PAIR>(ring, it, lane);
+                if (tile < 0) break;
+            }
             const int mt = (tile % m_work) * (PAIR ? 2 : 1) + (int)rank, rest = tile / m_work;
             const int ncol0 = p.wn_off + (rest % p.n_blocks) * p.BN + (int)rank * bn_cta;
             const int pk = rest / p.n_blocks;
@@ -215,6 +231,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     if (++s == stages) { s = 0; par ^= 1u; a_s = sbase; }
                 }
             }
+            if (rank == 0) tile = __shfl_sync(0xffffffffu, nxt, lead_lane);
         }
     } else if (warp == 1) {
         if (rank == 0) {
@@ -234,7 +251,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             int s = 0, lt = 0;
             uint32_t par = 0;
             uint32_t a_s = sbase;
-            for (int tile = worker; tile < total_tiles; tile += nworkers, ++lt) {
+            for (;; ++lt) {
+                const int tile = sched_next<PAIR>(ring, lt, lane);
+                if (tile < 0) break;
                 const int pk = (tile / m_work) / p.n_blocks;
                 const Phase& ph = p.phase[pk % p.nphase];
                 const int spp = ph.nseg / p.ksplit, sg0 = (pk / p.nphase) * spp;
@@ -290,7 +309,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int wl = row % p.bw, hl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
         int lt = 0;
         uint32_t gcc = 0;     // staging-tile counter across all tiles of this warp: nbuf buffers in rotation
-        for (int tile = worker; tile < total_tiles; tile += nworkers, ++lt) {
+        for (;; ++lt) {
+            const int tile = sched_next<PAIR>(ring, lt, lane);
+            if (tile < 0) break;
             const int mt = (tile % m_work) * (PAIR ? 2 : 1) + (int)rank, rest = tile / m_work;
             const int ncol0 = (rest % p.n_blocks) * p.BN;
             const Phase& ph = p.phase[(rest / p.n_blocks) % p.nphase];
@@ -480,6 +501,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         __syncthreads();
         if (warp == 0) tmem_dealloc<2 * kAccCols>(tmem_base);
     }
+    if (rank == 0 && threadIdx.x == 0) sched_finish(p.sched, nworkers);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -502,6 +524,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ SchedRing ring;
     __shared__ uint32_t tmem_base_s;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -534,6 +557,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             mbar_init(smem_u32(&tmem_full_bar[a]), 1);
             mbar_init(smem_u32(&tmem_empty_bar[a]), PAIR ? 8 : 4);
         }
+        sched_init(ring, PAIR ? 10u : 5u);        // readers of a work-item id: MMA warp + 4 epilogue warps (leader), producer + 4 (peer)
         mbar_fence_init();
     }
     tc_fence_before();
@@ -544,10 +568,21 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     // warp-uniform role loops (see conv_gemm_kernel): one elected lane issues, loop state stays in uniform registers
     if (warp == 0) {
         const bool lead = elect_one();
+        const int lead_lane = __ffs(__ballot_sync(0xffffffffu, lead)) - 1;
         int s = 0;
         uint32_t par = 0;
         uint32_t g_s = sbase;
-        for (int item = worker; item < total_items; item += nworkers) {
+        int item = worker, nxt = 0;
+        for (int seq = 0;; ++seq) {
+            if (rank == 0) {                 // work-item scheduler of the CTA (pair), see SchedRing
+                if (item >= total_items) item = -1;
+                sched_publish<PAIR>(ring, seq, item, lead);
+                if (item < 0) break;
+                if (lead) nxt = (int)atomicAdd(p.sched, 1u) + nworkers;
+            } else {
+                item = sched_next<PAIR>(ring, seq, lane);
+                if (item < 0) break;
+            }
             const int mi = item % p.m_items, y = (item / p.m_items) % ny, z = item / (p.m_items * ny);
             const int co0 = PAIR ? mi * 256 + (int)rank * 128 : mi * 128;
             const WTap tp = p.taps[y / p.n_ci_tiles];
@@ -580,6 +615,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 if (++s == stages) { s = 0; par ^= 1u; g_s = sbase; }
                 if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
             }
+            if (rank == 0) item = __shfl_sync(0xffffffffu, nxt, lead_lane);
         }
     } else if (warp == 1) {
         if (rank == 0) {
@@ -590,7 +626,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             int s = 0, li = 0;
             uint32_t par = 0;
             uint32_t g_s = sbase;
-            for (int item = worker; item < total_items; item += nworkers, ++li) {
+            for (;; ++li) {
+                const int item = sched_next<PAIR>(ring, li, lane);
+                if (item < 0) break;
                 const int t_begin = (item / (p.m_items * ny)) * p.tiles_per_split;
                 const int total = min(p.total_tiles, t_begin + p.tiles_per_split) - t_begin;
                 const int acc = li & 1;
@@ -625,7 +663,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         const uint32_t stg0 = sbase + (uint32_t)stages * stage_bytes + (uint32_t)q * 8192u;
         uint32_t gcc = 0;
         int li = 0;
-        for (int item = worker; item < total_items; item += nworkers, ++li) {
+        for (;; ++li) {
+            const int item = sched_next<PAIR>(ring, li, lane);
+            if (item < 0) break;
             const int mi = item % p.m_items, y = (item / p.m_items) % ny;
             const int co0 = (PAIR ? mi * 256 + (int)rank * 128 : mi * 128) + q * 32;
             const int wtap = p.taps[y / p.n_ci_tiles].wtap;
@@ -674,6 +714,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         __syncthreads();
         if (warp == 0) tmem_dealloc<2 * kTmemCols>(tmem_base);
     }
+    if (rank == 0 && threadIdx.x == 0) sched_finish(p.sched, nworkers);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -805,6 +846,26 @@ void debug_set(int k, int v) {
 
 static int smem_budget() { return 220 * 1024; }
 
+// Counter pairs of the dynamic tile scheduler: a per-device pool, allocated and zeroed once (library-owned scratch, 32 KB;
+// the only device memory the library holds).  Every launch takes the next pair; a kernel leaves its pair zeroed, launches that
+// share a pair are 4096 launches apart (stream-ordered in every use on the path; a captured graph re-uses its nodes' pairs on
+// every replay).
+constexpr int kSchedPairs = 4096;
+static unsigned int* g_sched_pool[64];
+static std::atomic<unsigned int> g_sched_next{0};
+static int sched_counters(unsigned int** out) {
+    const int dev = current_device();
+    SNN_REQUIRE(dev >= 0 && dev < 64, "bad CUDA device %d", dev);
+    static PerDeviceOnce once;
+    SNN_CUDA_OK(once.run([dev] {
+        cudaError_t e = cudaMalloc(&g_sched_pool[dev], sizeof(unsigned int) * 2 * kSchedPairs);
+        if (e == cudaSuccess) e = cudaMemset(g_sched_pool[dev], 0, sizeof(unsigned int) * 2 * kSchedPairs);
+        return e;
+    }));
+    *out = g_sched_pool[dev] + 2 * (g_sched_next.fetch_add(1u, std::memory_order_relaxed) % kSchedPairs);
+    return 0;
+}
+
 // w / w_dims: the weight tensor behind the B operand (the map is built here because its box depends on PAIR)
 static int make_w_map(CUtensorMap* m, const void* ptr, int wN, int wT, int wK, int box_n);
 struct WDesc { const void* ptr; int wN, wT, wK; };
@@ -856,6 +917,7 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     p.stages = stages;
     const size_t smem = (size_t)stages * p.stage_bytes + stage_extra + 1024;
     p.n_blocks = (p.n_store + p.BN - 1) / p.BN;
+    if (sched_counters(&p.sched)) return 2;
 #ifdef SNN_TIMING_KNOBS
     p.dbg = g_debug_flags[7];
 #else
@@ -1151,6 +1213,7 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
         SNN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(dw) failed: %d (Cout=%d taps=%d K=%d)", (int)r, Cout, taps, w_K);
     }
     const size_t smem = (size_t)p.stages * p.stage_bytes + stage_extra + 1024;
+    if (sched_counters(&p.sched)) return 2;
     const int items = base * p.ksplit;
     int nw = workers < items ? workers : items;
     if (g_debug_flags[5] > 0 && nw > g_debug_flags[5]) nw = g_debug_flags[5];
