@@ -34,6 +34,12 @@ int snn_version(void);
  *   7: (only in -DSNN_TIMING_KNOBS builds) bit 0 = producer skips the TMA loads, bit 1 = MMA issuer skips the MMAs
  *   8: 1 = T == 1 SiLU layers use the generic two-pass BN backward kernel */
 void snn_debug_set(int key, int value);
+/* Tile scheduling of the persistent tensor-core kernels (process-wide, read at launch): 0 (default) = static walk
+ * (tile = worker, worker + nworkers, ...), 1 = dynamic (first tile static, the rest from an atomic counter).  Dynamic is for
+ * data-parallel training: gradient all-reduces run beside backward, the SMs that also host NCCL CTAs are slower, and with a
+ * static walk every launch waits for them.  Dynamic mode uses a library-owned 32 KB counter pool per device (allocated at
+ * the first launch in that mode; launch once eagerly before capturing a CUDA graph). */
+void snn_set_tile_scheduling(int dynamic);
 
 /* conv geometries on the path (reference model.py:13 k3 s1/s2 p1; model.py:119 k1; model.py:36 convT k2 s2) */
 enum { SNN_GEOM_3x3_S1 = 0, SNN_GEOM_3x3_S2 = 1, SNN_GEOM_1x1 = 2, SNN_GEOM_T2x2_S2 = 3 };

@@ -268,10 +268,12 @@ SNN_DEVINL void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, 
 // the SMs that also host NCCL CTAs run their tiles slower and every launch waits for them (conv dgrad 896 -> 810 TF/s from 1
 // to 8 GPUs in SCALE_r01).  Now a worker's first tile is static and every further one comes from a global atomic counter;
 // the leader CTA's producer warp fetches it and hands it to the other warps (and to the peer CTA of a pair, through
-// distributed shared memory) over a 4-slot ring guarded by mbarriers.  The last worker to finish zeroes the counters, so a
-// launch always finds them at 0 (kernels that share a counter pair are stream-ordered).
+// distributed shared memory) over an 8-slot ring guarded by mbarriers, TWO tiles ahead of its own loads (the peer's
+// producer must never wait for an id at a tile boundary: published one tile ahead only, the 128-channel layers lost 25 %).
+// The last worker to finish zeroes the counters, so a launch always finds them at 0 (kernels that share a counter pair are
+// stream-ordered).  sched == nullptr selects the static walk (single-GPU default: nothing to steal from, 3-8 % faster).
 // ------------------------------------------------------------------------------------------
-constexpr int kSchedSlots = 4;
+constexpr int kSchedSlots = 8;
 struct __align__(8) SchedRing {
     uint64_t full[kSchedSlots];
     uint64_t empty[kSchedSlots];
@@ -322,8 +324,8 @@ SNN_DEVINL int sched_next(SchedRing& r, int it, int lane) {
     const int s = it & (kSchedSlots - 1);
     if (PAIR) mbar_wait_cluster(smem_u32(&r.full[s]), (uint32_t)((it / kSchedSlots) & 1));
     else mbar_wait(smem_u32(&r.full[s]), (uint32_t)((it / kSchedSlots) & 1));
-    const int t = *reinterpret_cast<volatile int*>(&r.tile[s]);
-    __syncwarp();
+    int t = *reinterpret_cast<volatile int*>(&r.tile[s]);
+    t = __shfl_sync(0xffffffffu, t, 0);        // provably warp-uniform: the role loops keep their state in uniform registers
     if (lane == 0) {
         if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&r.empty[s]), 0u));           // the LEADER's ring collects all readers
         else mbar_arrive(smem_u32(&r.empty[s]));

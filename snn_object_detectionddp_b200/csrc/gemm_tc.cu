@@ -163,17 +163,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // thread -- which, not the tensor pipe, bounded v1 at ~635 cycles per 64-wide K chunk -- drops several-fold.
     if (warp == 0) {
         const bool lead = elect_one();
-        const int lead_lane = __ffs(__ballot_sync(0xffffffffu, lead)) - 1;
         int s = 0;
         uint32_t par = 0;
         uint32_t a_s = sbase;
-        int tile = worker, nxt = 0;
+        const bool dyn = p.sched != nullptr;
+        // dynamic: this warp of the leader CTA is the tile scheduler.  Ids are published TWO tiles ahead: `tile` is being
+        // loaded, `nxt1` is already in the ring, the atomic for the one after is in flight (`pend`, lane 0).
+        int tile = worker, nxt1 = -1, pend = 0, pub = 0;      // pub: sequence number of the next id to publish; -1 once the end marker is out
+        if (dyn && rank == 0) {
+            if (tile >= total_tiles) tile = -1;
+            sched_publish<PAIR>(ring, pub++, tile, lead);
+            if (tile < 0) pub = -1;
+            if (pub > 0) {
+                if (lane == 0) pend = (int)atomicAdd(p.sched, 1u) + nworkers;
+                nxt1 = __shfl_sync(0xffffffffu, pend, 0);
+                if (nxt1 >= total_tiles) nxt1 = -1;
+                sched_publish<PAIR>(ring, pub++, nxt1, lead);
+                if (nxt1 < 0) pub = -1;
+                else if (lane == 0) pend = (int)atomicAdd(p.sched, 1u) + nworkers;
+            }
+        }
         for (int it = 0;; ++it) {
-            if (rank == 0) {                 // this warp is the tile scheduler of the CTA (pair)
-                if (tile >= total_tiles) tile = -1;
-                sched_publish<PAIR>(ring, it, tile, lead);
+            if (!dyn) {
+                tile = worker + it * nworkers;
+                if (tile >= total_tiles) break;
+            } else if (rank == 0) {
                 if (tile < 0) break;
-                if (lead) nxt = (int)atomicAdd(p.sched, 1u) + nworkers;      // next tile id: needed only after this tile's loads
             } else {
                 tile = sched_next<PAIR>(ring, it, lane);
                 if (tile < 0) break;
@@ -231,7 +246,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     if (++s == stages) { s = 0; par ^= 1u; a_s = sbase; }
                 }
             }
-            if (rank == 0) tile = __shfl_sync(0xffffffffu, nxt, lead_lane);
+            if (dyn && rank == 0) {          // advance: publish the id two tiles ahead, keep one atomic in flight
+                tile = nxt1;
+                if (pub > 0) {
+                    nxt1 = __shfl_sync(0xffffffffu, pend, 0);                    // lane 0: provably warp-uniform
+                    if (nxt1 >= total_tiles) nxt1 = -1;
+                    sched_publish<PAIR>(ring, pub++, nxt1, lead);
+                    if (nxt1 < 0) pub = -1;
+                    else if (lane == 0) pend = (int)atomicAdd(p.sched, 1u) + nworkers;
+                } else {
+                    nxt1 = -1;
+                }
+            }
         }
     } else if (warp == 1) {
         if (rank == 0) {
@@ -251,8 +277,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             int s = 0, lt = 0;
             uint32_t par = 0;
             uint32_t a_s = sbase;
+            const bool dyn = p.sched != nullptr;
             for (;; ++lt) {
-                const int tile = sched_next<PAIR>(ring, lt, lane);
+                const int tile = dyn ? sched_next<PAIR>(ring, lt, lane) : (worker + lt * nworkers < total_tiles ? worker + lt * nworkers : -1);
                 if (tile < 0) break;
                 const int pk = (tile / m_work) / p.n_blocks;
                 const Phase& ph = p.phase[pk % p.nphase];
@@ -309,8 +336,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int wl = row % p.bw, hl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
         int lt = 0;
         uint32_t gcc = 0;     // staging-tile counter across all tiles of this warp: nbuf buffers in rotation
+        const bool dyn = p.sched != nullptr;
         for (;; ++lt) {
-            const int tile = sched_next<PAIR>(ring, lt, lane);
+            const int tile = dyn ? sched_next<PAIR>(ring, lt, lane) : (worker + lt * nworkers < total_tiles ? worker + lt * nworkers : -1);
             if (tile < 0) break;
             const int mt = (tile % m_work) * (PAIR ? 2 : 1) + (int)rank, rest = tile / m_work;
             const int ncol0 = (rest % p.n_blocks) * p.BN;
@@ -501,7 +529,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         __syncthreads();
         if (warp == 0) tmem_dealloc<2 * kAccCols>(tmem_base);
     }
-    if (rank == 0 && threadIdx.x == 0) sched_finish(p.sched, nworkers);
+    if (p.sched != nullptr && rank == 0 && threadIdx.x == 0) sched_finish(p.sched, nworkers);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -568,17 +596,30 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     // warp-uniform role loops (see conv_gemm_kernel): one elected lane issues, loop state stays in uniform registers
     if (warp == 0) {
         const bool lead = elect_one();
-        const int lead_lane = __ffs(__ballot_sync(0xffffffffu, lead)) - 1;
         int s = 0;
         uint32_t par = 0;
         uint32_t g_s = sbase;
-        int item = worker, nxt = 0;
+        const bool dyn = p.sched != nullptr;
+        int item = worker, nxt1 = -1, pend = 0, pub = 0;      // as in conv_gemm_kernel: ids go out two work items ahead
+        if (dyn && rank == 0) {
+            if (item >= total_items) item = -1;
+            sched_publish<PAIR>(ring, pub++, item, lead);
+            if (item < 0) pub = -1;
+            if (pub > 0) {
+                if (lane == 0) pend = (int)atomicAdd(p.sched, 1u) + nworkers;
+                nxt1 = __shfl_sync(0xffffffffu, pend, 0);
+                if (nxt1 >= total_items) nxt1 = -1;
+                sched_publish<PAIR>(ring, pub++, nxt1, lead);
+                if (nxt1 < 0) pub = -1;
+                else if (lane == 0) pend = (int)atomicAdd(p.sched, 1u) + nworkers;
+            }
+        }
         for (int seq = 0;; ++seq) {
-            if (rank == 0) {                 // work-item scheduler of the CTA (pair), see SchedRing
-                if (item >= total_items) item = -1;
-                sched_publish<PAIR>(ring, seq, item, lead);
+            if (!dyn) {
+                item = worker + seq * nworkers;
+                if (item >= total_items) break;
+            } else if (rank == 0) {
                 if (item < 0) break;
-                if (lead) nxt = (int)atomicAdd(p.sched, 1u) + nworkers;
             } else {
                 item = sched_next<PAIR>(ring, seq, lane);
                 if (item < 0) break;
@@ -615,7 +656,18 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 if (++s == stages) { s = 0; par ^= 1u; g_s = sbase; }
                 if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
             }
-            if (rank == 0) item = __shfl_sync(0xffffffffu, nxt, lead_lane);
+            if (dyn && rank == 0) {
+                item = nxt1;
+                if (pub > 0) {
+                    nxt1 = __shfl_sync(0xffffffffu, pend, 0);
+                    if (nxt1 >= total_items) nxt1 = -1;
+                    sched_publish<PAIR>(ring, pub++, nxt1, lead);
+                    if (nxt1 < 0) pub = -1;
+                    else if (lane == 0) pend = (int)atomicAdd(p.sched, 1u) + nworkers;
+                } else {
+                    nxt1 = -1;
+                }
+            }
         }
     } else if (warp == 1) {
         if (rank == 0) {
@@ -626,8 +678,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             int s = 0, li = 0;
             uint32_t par = 0;
             uint32_t g_s = sbase;
+            const bool dyn = p.sched != nullptr;
             for (;; ++li) {
-                const int item = sched_next<PAIR>(ring, li, lane);
+                const int item = dyn ? sched_next<PAIR>(ring, li, lane) : (worker + li * nworkers < total_items ? worker + li * nworkers : -1);
                 if (item < 0) break;
                 const int t_begin = (item / (p.m_items * ny)) * p.tiles_per_split;
                 const int total = min(p.total_tiles, t_begin + p.tiles_per_split) - t_begin;
@@ -663,8 +716,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         const uint32_t stg0 = sbase + (uint32_t)stages * stage_bytes + (uint32_t)q * 8192u;
         uint32_t gcc = 0;
         int li = 0;
+        const bool dyn = p.sched != nullptr;
         for (;; ++li) {
-            const int item = sched_next<PAIR>(ring, li, lane);
+            const int item = dyn ? sched_next<PAIR>(ring, li, lane) : (worker + li * nworkers < total_items ? worker + li * nworkers : -1);
             if (item < 0) break;
             const int mi = item % p.m_items, y = (item / p.m_items) % ny;
             const int co0 = (PAIR ? mi * 256 + (int)rank * 128 : mi * 128) + q * 32;
@@ -714,7 +768,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         __syncthreads();
         if (warp == 0) tmem_dealloc<2 * kTmemCols>(tmem_base);
     }
-    if (rank == 0 && threadIdx.x == 0) sched_finish(p.sched, nworkers);
+    if (p.sched != nullptr && rank == 0 && threadIdx.x == 0) sched_finish(p.sched, nworkers);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -853,7 +907,11 @@ static int smem_budget() { return 220 * 1024; }
 constexpr int kSchedPairs = 4096;
 static unsigned int* g_sched_pool[64];
 static std::atomic<unsigned int> g_sched_next{0};
+static std::atomic<int> g_dynamic_tiles{0};
+void set_dynamic_tiles(int on) { g_dynamic_tiles.store(on ? 1 : 0, std::memory_order_relaxed); }
 static int sched_counters(unsigned int** out) {
+    *out = nullptr;
+    if (!g_dynamic_tiles.load(std::memory_order_relaxed)) return 0;      // static tile walk
     const int dev = current_device();
     SNN_REQUIRE(dev >= 0 && dev < 64, "bad CUDA device %d", dev);
     static PerDeviceOnce once;

@@ -10,6 +10,7 @@ indexes, and loss values are returned as device tensors (the caller decides when
 3-5 times per batch, train.py:81-100).
 """
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -65,6 +66,8 @@ class Trainer:
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.bucketer = None
         if self.world > 1:
+            # NCCL CTAs share SMs with backward: let the persistent conv kernels steal tiles from the slowed-down SMs
+            K._lib.lib().snn_set_tile_scheduling(int(os.environ.get("SNN_DYNAMIC_TILES", "1")))
             broadcast_module_state(model, self.store.flat_p, process_group)
             self.store._versions = None       # masters changed under the bf16 operand copies
             spans = [(e.offset, self._padded(e)) for e in self.store.entries]

@@ -6,7 +6,8 @@ against torch fp32 convolutions of the same bf16 operands.
     These walk 3-14 tiles per persistent CTA pair: shared-memory ring wrap across tiles, TMEM double-buffer hand-off
     (parity first flips at the 3rd tile of a worker), rotating epilogue staging tiles.
 (2) the small cases of tests/test_gpu_conv.py re-run with the persistent grid capped to 1 and 3 workers
-    (snn_debug_set(5, cap)) so that ONE worker walks every tile of the problem.
+    (snn_debug_set(5, cap)) so that ONE worker walks every tile of the problem, with the static and the dynamic
+    (snn_set_tile_scheduling(1)) tile scheduler.
 (3) fused BN statistics on maps the pixel box does not divide (10x10, 12x20 at B=2, 24x40, 15x20): rows of out-of-range
     pixels must not reach the sums.
 
@@ -181,13 +182,18 @@ def test_wgrad_bench_shape(geom, nb, h, w, ci, w_coff, wk, cout, note):
 # ------------------------------------------------------------------------------------------------
 # (2) one / three persistent workers walk the whole problem
 # ------------------------------------------------------------------------------------------------
-@pytest.fixture(params=[1, 3], ids=["cap1", "cap3"])
+@pytest.fixture(params=[(1, 0), (3, 0), (3, 1), (0, 1)], ids=["cap1", "cap3", "cap3-dynamic", "dynamic"])
 def grid_cap(request):
+    """(cap on persistent workers, tile scheduling): the dynamic scheduler (atomic counter + mbarrier ring, DSMEM hand-off
+    to the peer CTA; what data-parallel training runs) must give the same results as the static walk."""
     from snn_object_detectionddp_b200 import _lib
     L = _lib.lib()
-    L.snn_debug_set(5, request.param)
+    cap, dyn = request.param
+    L.snn_debug_set(5, cap)
+    L.snn_set_tile_scheduling(dyn)
     yield request.param
     L.snn_debug_set(5, 0)
+    L.snn_set_tile_scheduling(0)
 
 
 @pytest.mark.parametrize("geom,nb,h,w,cin,cout", FPROP_CASES)
@@ -280,3 +286,38 @@ def test_fused_statistics_on_maps_the_pixel_box_does_not_divide(geom, T, B, h, w
     # and the standalone statistics kernel agrees
     s2 = K.bn_stats(y, T)
     assert bool(((s2 - want).abs() <= 2e-6 * scale + 1e-9).all())
+
+
+@pytest.mark.parametrize("which", ["fprop", "dgrad", "wgrad"])
+def test_dynamic_tile_scheduler_at_bench_shapes(which):
+    """Dynamic tile scheduling == static walk, bit for bit (fprop / non-split dgrad: every output element is produced by
+    exactly one tile) or to summation order (split-K wgrad), on a configs[1] layer with 14 tiles per worker."""
+    setup_exact()
+    K = _k()
+    from snn_object_detectionddp_b200 import _lib
+    L = _lib.lib()
+    x = _mk(256, 16, 16, 256, 81, spikes=True)
+    wgt = _mkw(256, 9, 256, 82)
+    dy = _mk(256, 16, 16, 256, 83)
+    outs = []
+    try:
+        for dyn in (0, 1, 1):
+            L.snn_set_tile_scheduling(dyn)
+            if which == "fprop":
+                y, sums = K.conv_fprop_stats(G31, x, wgt, 256, 4)
+                outs.append((y, sums))
+            elif which == "dgrad":
+                outs.append((K.conv_dgrad(G31, dy, wgt, (16, 16), 256),))
+            else:
+                dw = torch.zeros(256, 9, 256, device="cuda")
+                K.conv_wgrad(G31, x, dy, dw)
+                outs.append((dw,))
+    finally:
+        L.snn_set_tile_scheduling(0)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            if which == "wgrad":
+                assert rel_err(a, b) < 2e-6
+            else:
+                assert torch.equal(a, b)
