@@ -40,6 +40,9 @@ void snn_debug_set(int key, int value);
  * static walk every launch waits for them.  Dynamic mode uses a library-owned 32 KB counter pool per device (allocated at
  * the first launch in that mode; launch once eagerly before capturing a CUDA graph). */
 void snn_set_tile_scheduling(int dynamic);
+/* The library keeps a process-wide, mutex-guarded cache of encoded TMA tensor maps keyed by (device, pointer, shape,
+ * strides, box): hit / miss counters since load (a steady eager training loop re-uses every map of the previous step). */
+void snn_tensor_map_cache_stats(unsigned long long* hits, unsigned long long* misses);
 
 /* conv geometries on the path (reference model.py:13 k3 s1/s2 p1; model.py:119 k1; model.py:36 convT k2 s2) */
 enum { SNN_GEOM_3x3_S1 = 0, SNN_GEOM_3x3_S2 = 1, SNN_GEOM_1x1 = 2, SNN_GEOM_T2x2_S2 = 3 };

@@ -42,6 +42,7 @@ int num_sms() {
 // launchers defined in the other translation units
 void debug_set(int k, int v);
 void set_dynamic_tiles(int on);
+void tmap_cache_stats(unsigned long long*, unsigned long long*);
 int conv_fprop(int, int, int, int, const void*, int, long long, const void*, int, long long, const void*, int, int, int, int,
                int, const float*, void*, int, long long, int, int, cudaStream_t, float*, int);
 long long conv_stats_groups(int, int, int, int, int, int*);
@@ -109,6 +110,7 @@ const char* snn_last_error(void) { return g_err; }
 int snn_version(void) { return 100; }
 void snn_debug_set(int key, int value) { debug_set(key, value); }
 void snn_set_tile_scheduling(int dynamic) { set_dynamic_tiles(dynamic); }
+void snn_tensor_map_cache_stats(unsigned long long* hits, unsigned long long* misses) { tmap_cache_stats(hits, misses); }
 
 int snn_conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long long ld0, const void* x1, int C1,
                    long long ld1, const void* w, int w_rows, int w_K, int w_coff, int Cout, int w_row_off,

@@ -19,6 +19,7 @@
 // epilogue (one TMEM lane quarter each); small-K convs launch 320 threads: warps 6-9 = a second epilogue group.
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -774,20 +775,75 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 // ------------------------------------------------------------------------------------------
 // host side: tensor maps
 // ------------------------------------------------------------------------------------------
+static std::once_flag g_encode_once;
+
+// ------------------------------------------------------------------------------------------
+// Tensor-map (TMA descriptor) cache.  A training step launches ~150 tensor-core kernels with 3-4 maps each and the same
+// (pointer, shape, box) tuples recur every step (PyTorch's caching allocator hands the same blocks back): the encoded
+// 128-byte maps are kept in a process-wide table keyed by every argument of cuTensorMapEncodeTiled (device included),
+// guarded by a mutex, cleared when it reaches kTmapCacheMax entries.  The captured-graph path never re-encodes anyway; this
+// is for the eager per-frame drop-in path, which is host-bound.
+// ------------------------------------------------------------------------------------------
+struct TmapKey {
+    unsigned long long ptr, dims[5], strides[4];
+    unsigned int box[5], dtype, rank, swizzle, l2, dev;
+    bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        const unsigned long long* w = reinterpret_cast<const unsigned long long*>(&k);
+        unsigned long long h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+static_assert(sizeof(TmapKey) % 8 == 0, "TmapKey is hashed as 64-bit words");
+constexpr size_t kTmapCacheMax = 16384;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::mutex g_tmap_mutex;
+static std::atomic<unsigned long long> g_tmap_hits{0}, g_tmap_misses{0};
+void tmap_cache_stats(unsigned long long* hits, unsigned long long* misses) {
+    *hits = g_tmap_hits.load(); *misses = g_tmap_misses.load();
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn g_encode = nullptr;
-static std::once_flag g_encode_once;
+static EncodeTiledFn g_encode_raw = nullptr;
+
+// same signature as cuTensorMapEncodeTiled; interleave NONE and OOB fill NONE are the only values on the path
+static CUresult g_encode(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, void* ptr, const cuuint64_t* dims, const cuuint64_t* strides,
+                         const cuuint32_t* box, const cuuint32_t* es, CUtensorMapInterleave il, CUtensorMapSwizzle sw, CUtensorMapL2promotion l2,
+                         CUtensorMapFloatOOBfill oob) {
+    TmapKey k;
+    memset(&k, 0, sizeof(k));
+    k.ptr = (unsigned long long)(uintptr_t)ptr; k.dtype = (unsigned)dt; k.rank = rank; k.swizzle = (unsigned)sw; k.l2 = (unsigned)l2;
+    k.dev = (unsigned)current_device();
+    for (cuuint32_t i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+    for (cuuint32_t i = 0; i + 1 < rank; ++i) k.strides[i] = strides[i];
+    {
+        std::lock_guard<std::mutex> g(g_tmap_mutex);
+        auto it = g_tmap_cache.find(k);
+        if (it != g_tmap_cache.end()) { *m = it->second; g_tmap_hits.fetch_add(1, std::memory_order_relaxed); return CUDA_SUCCESS; }
+    }
+    const CUresult r = g_encode_raw(m, dt, rank, ptr, dims, strides, box, es, il, sw, l2, oob);
+    if (r == CUDA_SUCCESS) {
+        std::lock_guard<std::mutex> g(g_tmap_mutex);
+        if (g_tmap_cache.size() >= kTmapCacheMax) g_tmap_cache.clear();
+        g_tmap_cache.emplace(k, *m);
+        g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
+    }
+    return r;
+}
 
 static int get_encode() {
     std::call_once(g_encode_once, [] {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) g_encode = (EncodeTiledFn)fn;
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) g_encode_raw = (EncodeTiledFn)fn;
     });
-    SNN_REQUIRE(g_encode != nullptr, "cuTensorMapEncodeTiled not available from the CUDA driver");
+    SNN_REQUIRE(g_encode_raw != nullptr, "cuTensorMapEncodeTiled not available from the CUDA driver");
     return 0;
 }
 

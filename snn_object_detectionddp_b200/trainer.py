@@ -66,8 +66,10 @@ class Trainer:
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.bucketer = None
         if self.world > 1:
-            # NCCL CTAs share SMs with backward: let the persistent conv kernels steal tiles from the slowed-down SMs
-            K._lib.lib().snn_set_tile_scheduling(int(os.environ.get("SNN_DYNAMIC_TILES", "1")))
+            # Dynamic tile scheduling of the persistent conv kernels (work stealing from SMs slowed down by NCCL CTAs) was
+            # measured at 8 GPUs: 11.08 ms/step vs 10.75 ms with the static walk (profiles/README.md, negative results):
+            # the ring hand-off costs more than the stealing recovers.  Kept selectable, off by default.
+            K._lib.lib().snn_set_tile_scheduling(int(os.environ.get("SNN_DYNAMIC_TILES", "0")))
             broadcast_module_state(model, self.store.flat_p, process_group)
             self.store._versions = None       # masters changed under the bf16 operand copies
             spans = [(e.offset, self._padded(e)) for e in self.store.entries]
