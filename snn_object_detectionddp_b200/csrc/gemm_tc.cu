@@ -1016,7 +1016,8 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     // coalesced TMA-store epilogue whenever the output view is expressible as a tensor map
     const int es = p.out_f32 ? 4 : 2, CH = p.out_f32 ? 32 : 64;
     char* obase = reinterpret_cast<char*>(p.out) + (long long)p.out_coff * es;
-    p.tma_out = g_debug_flags[0] != 1 && !(p.accumulate && !p.out_f32) && ((uintptr_t)obase % 16 == 0) && ((p.out_ld * es) % 16 == 0) &&
+    // (accumulating into a bf16 output = cp.reduce.async.bulk.tensor .add on a bf16 tensor map: one rounding of the sum)
+    p.tma_out = g_debug_flags[0] != 1 && ((uintptr_t)obase % 16 == 0) && ((p.out_ld * es) % 16 == 0) &&
                 (p.os == 1 || (p.n_store % CH == 0 && p.Ho % 2 == 0 && p.Wo % 2 == 0));
     SNN_REQUIRE(!p.stats || p.tma_out, "conv_fprop: fused statistics need the TMA-store epilogue (output alignment)");
     p.nbuf = 2;                       // (four staging tiles per warp were measured to change nothing, profiles/README.md)

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import kernels as K
-from .ops import BilinearResizeFn, ConvBiasFn, ConvBNActFn, ConvLSTMSeqFn, NeuronCfg, PadEvenFn
+from .ops import BilinearResizeFn, ConvBiasFn, ConvBNActFn, ConvLSTMSeqFn, GradSlot, NeuronCfg, PadEvenFn
 from .params import store_for
 from ._lib import GEOM_1x1, GEOM_3x3_S1, GEOM_3x3_S2, GEOM_T2x2_S2
 
@@ -83,7 +83,7 @@ class ConvBlock(nn.Module):
             raise NotImplementedError("ConvBlock supports k3/p1/s{1,2}, k1/p0/s1 and depthwise k3 (the shapes on the path)")
         self.last_mask = None
 
-    def forward_seq(self, rc, x0, x1=None, v_init=None, dead_frames_ok=False):
+    def forward_seq(self, rc, x0, x1=None, v_init=None, dead_frames_ok=False, slot_x0=None):
         """dead_frames_ok: the caller guarantees this block's output reaches the loss only through the last rc.live_T
         timesteps and feeds nothing with temporal state (true for the Detect head, NOT for U-Net blocks: the encoder
         feeds the ConvLSTM and LIF blocks carry membranes)."""
@@ -92,6 +92,8 @@ class ConvBlock(nn.Module):
         if dead_frames_ok and rc.live_T is not None and self.neuron.kind == "silu" and rc.live_T < rc.T:
             cfg["live_T"] = rc.live_T
             cfg["dead_grad_unread"] = getattr(rc, "dead_grad_unread", False)
+        if slot_x0 is not None:
+            cfg["slot_x0"] = slot_x0          # (GradSlot, 'first' | 'last'): see ops.GradSlot
         if self.geom == GEOM_3x3_S2 and ((x0.shape[1] | x0.shape[2]) & 1):
             # odd H or W (e.g. the 15x20 P5 level of a 480x640 frame): zero-pad to even -- the extra row / column is exactly
             # the conv's own padding, so Ho = ceil(H/2) and the values equal nn.Conv2d(k3, s2, p1) on the odd-sized map
@@ -118,9 +120,11 @@ class DownBlock(nn.Module):
         self.conv1 = ConvBlock(in_channels, out_channels, stride=2, neuron=neuron)
         self.conv2 = ConvBlock(out_channels, out_channels, neuron=neuron)
 
-    def forward_seq(self, rc, x, v=None):
+    def forward_seq(self, rc, x, v=None, slot_x=None):
         v = v or (None, None)
-        x, v1 = self.conv1.forward_seq(rc, x, None, v[0])
+        if slot_x is not None and ((x.shape[1] | x.shape[2]) & 1):
+            slot_x = None                       # odd map: the consumer of x is the pad op, not the conv
+        x, v1 = self.conv1.forward_seq(rc, x, None, v[0], slot_x0=slot_x)
         x, v2 = self.conv2.forward_seq(rc, x, None, v[1])
         return x, (v1, v2)
 
@@ -138,13 +142,17 @@ class UpBlock(nn.Module):
         self.conv1 = ConvBlock(in_channels // 2 + skip_channels, out_channels, neuron=neuron)
         self.conv2 = ConvBlock(out_channels, out_channels, neuron=neuron)
 
-    def forward_seq(self, rc, x, skip, v=None):
+    def forward_seq(self, rc, x, skip, v=None, slot_x=None, slot_skip=None):
         v = v or (None, None)
-        up = ConvBiasFn.apply(x, self.up.weight, self.up.bias, dict(store=rc.store, geom=GEOM_T2x2_S2))
+        cfg_up = dict(store=rc.store, geom=GEOM_T2x2_S2)
+        if slot_x is not None:
+            cfg_up["slot_x0"] = slot_x
+        up = ConvBiasFn.apply(x, self.up.weight, self.up.bias, cfg_up)
         if up.shape[1:3] != skip.shape[1:3]:
             # reference model.py:43-44: F.interpolate(skip_x, size=x.shape[2:], mode='bilinear', align_corners=False)
             skip = BilinearResizeFn.apply(skip, (up.shape[1], up.shape[2]))
-        x, v1 = self.conv1.forward_seq(rc, skip, up, v[0])      # cat([skip_x, x]) order of model.py:45
+            slot_skip = None                    # the consumer of the skip tensor is the resize op, not the conv
+        x, v1 = self.conv1.forward_seq(rc, skip, up, v[0], slot_x0=slot_skip)      # cat([skip_x, x]) order of model.py:45
         x, v2 = self.conv2.forward_seq(rc, x, None, v[1])
         return x, (v1, v2)
 
@@ -210,23 +218,39 @@ class TemporalUNet(nn.Module):
         p3, p4, p5 = feats
         lstm_state, m = state if state is not None else (None, {})
         nm = {}
+        # Tensors with two consumers (x1, x2, x3: next encoder stage + decoder skip; d1, d2: next decoder stage + output
+        # conv): their two input gradients are summed in the second dgrad's epilogue (ops.GradSlot) instead of by an
+        # autograd add kernel.  'first' = the consumer created later in forward = whose backward runs first.
+        fuse = torch.is_grad_enabled() and self.training
+        s1, s2, s3, sd1, sd2 = (GradSlot() if fuse else None for _ in range(5))
+        role = lambda s_, r_: None if s_ is None else (s_, r_)
         x1, nm["enc1"] = self.enc1.forward_seq(rc, p3, None, m.get("enc1"))
-        d, nm["down1"] = self.down1.forward_seq(rc, x1, m.get("down1"))
+        d, nm["down1"] = self.down1.forward_seq(rc, x1, m.get("down1"), slot_x=role(s1, "last"))
         x2, nm["enc2"] = self.enc2.forward_seq(rc, d, p4, m.get("enc2"))          # cat([down1(x1), p4]) model.py:126
-        d, nm["down2"] = self.down2.forward_seq(rc, x2, m.get("down2"))
+        d, nm["down2"] = self.down2.forward_seq(rc, x2, m.get("down2"), slot_x=role(s2, "last"))
         x3, nm["enc3"] = self.enc3.forward_seq(rc, d, p5, m.get("enc3"))          # model.py:127
-        x, nm["down3"] = self.down3.forward_seq(rc, x3, m.get("down3"))
+        x, nm["down3"] = self.down3.forward_seq(rc, x3, m.get("down3"), slot_x=role(s3, "last"))
         h_all, new_lstm = self.lstm.forward_seq(rc, x, lstm_state)
         x, nm["bottleneck_conv"] = self.bottleneck_conv.forward_seq(rc, h_all, None, m.get("bottleneck_conv"))
-        d1, nm["up1"] = self.up1.forward_seq(rc, x, x3, m.get("up1"))
-        d2, nm["up2"] = self.up2.forward_seq(rc, d1, x2, m.get("up2"))
-        d3, nm["up3"] = self.up3.forward_seq(rc, d2, x1, m.get("up3"))
         od = torch.float32 if rc.fp32_outputs else torch.bfloat16
         live_n = None if (rc.live_T is None or rc.live_T >= rc.T) else rc.live_T * (p3.shape[0] // rc.T)
-        mk = lambda conv, x_: ConvBiasFn.apply(x_, conv.weight, conv.bias,
-                                               dict(store=rc.store, geom=GEOM_1x1, out_dtype=od, live_n=live_n))
-        outs = (mk(self.out_p3, d3), mk(self.out_p4, d2), mk(self.out_p5, d1))
-        return outs, (new_lstm, nm)
+
+        def out_conv(conv, x_, slot):
+            cfg = dict(store=rc.store, geom=GEOM_1x1, out_dtype=od, live_n=live_n)
+            if slot is not None:
+                cfg["slot_x0"] = slot
+            return ConvBiasFn.apply(x_, conv.weight, conv.bias, cfg)
+
+        # each output conv is applied right after its decoder level (model.py:146 applies them at the end; the values are the
+        # same): it is then created BEFORE the next up-block, its backward runs AFTER it and can add its live-frame gradient
+        # into the buffer the up-block's dgrad has written -- no zero-filled full-size gradient for the dead frames.
+        d1, nm["up1"] = self.up1.forward_seq(rc, x, x3, m.get("up1"), slot_skip=role(s3, "first"))
+        o5 = out_conv(self.out_p5, d1, role(sd1, "last"))
+        d2, nm["up2"] = self.up2.forward_seq(rc, d1, x2, m.get("up2"), slot_x=role(sd1, "first"), slot_skip=role(s2, "first"))
+        o4 = out_conv(self.out_p4, d2, role(sd2, "last"))
+        d3, nm["up3"] = self.up3.forward_seq(rc, d2, x1, m.get("up3"), slot_x=role(sd2, "first"), slot_skip=role(s1, "first"))
+        o3 = out_conv(self.out_p3, d3, None)
+        return (o3, o4, o5), (new_lstm, nm)
 
     def forward(self, features, hidden_state=None):
         """Drop-in: features = 3 NCHW fp32 maps; hidden_state = None | (h, c) | (h, c, membranes)."""

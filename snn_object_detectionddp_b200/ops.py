@@ -32,6 +32,19 @@ def _bf16c(g):
     return g.contiguous()
 
 
+class GradSlot:
+    """Gradient of a tensor with TWO consumers, accumulated in the dgrad epilogue instead of by autograd's add kernel.
+
+    The consumer whose backward runs first ('first': the one created LATER in forward) writes its input gradient into a
+    fresh buffer and parks it here; the other ('last') launches its dgrad with accumulate=True into that buffer (bf16 TMA
+    reduce-add, same rounding as adding two bf16 tensors) and returns no gradient of its own.  The producer's backward runs
+    after both (autograd's dependency count), so it sees the complete sum.  One slot per fan-out tensor per forward."""
+    __slots__ = ("buf",)
+
+    def __init__(self):
+        self.buf = None
+
+
 def _dead_padded(x_full, n_live, zero):
     """Full-size input-gradient buffer whose trailing n_live samples the caller fills.  The leading (dead) part is
     zero-filled unless every consumer is known to slice it away (Detect-head internals: cfg['dead_grad_unread'])."""
@@ -146,11 +159,18 @@ class ConvBNActFn(Function):
         in_hw = (x0.shape[1], x0.shape[2])
         zero = not cfg.get("dead_grad_unread", False)
         if ctx.needs_input_grad[0]:
-            tail = None
-            if live_T is not None:
-                gx0, tail = _dead_padded(x0_full, x0.shape[0], zero)
-            r = K.conv_dgrad(geom, dy, st.w_fprop(weight), in_hw, x0.shape[3], ci_off=0, out=tail)
-            gx0 = r if live_T is None else gx0
+            slot, role = cfg.get("slot_x0", (None, None))
+            if slot is not None and live_T is None and role == "last" and slot.buf is not None:
+                # the other consumer of x0 already wrote its gradient: add ours in the epilogue, hand nothing to autograd
+                K.conv_dgrad(geom, dy, st.w_fprop(weight), in_hw, x0.shape[3], ci_off=0, out=slot.buf, accumulate=True)
+            else:
+                tail = None
+                if live_T is not None:
+                    gx0, tail = _dead_padded(x0_full, x0.shape[0], zero)
+                r = K.conv_dgrad(geom, dy, st.w_fprop(weight), in_hw, x0.shape[3], ci_off=0, out=tail)
+                gx0 = r if live_T is None else gx0
+                if slot is not None and live_T is None and role == "first":
+                    slot.buf = gx0
         if ctx.has_x1 and ctx.needs_input_grad[1]:
             tail = None
             if live_T is not None:
@@ -229,12 +249,20 @@ class ConvBiasFn(Function):
             st.grad_done(bias)
         gx0 = None
         if ctx.needs_input_grad[0]:
-            if x0 is x0_full:
-                gx0 = K.conv_dgrad(geom, dy, st.w_fprop(weight), (x0.shape[1], x0.shape[2]), x0.shape[3])
+            slot, role = cfg.get("slot_x0", (None, None))
+            hw = (x0.shape[1], x0.shape[2])
+            if slot is not None and role == "last" and slot.buf is not None:
+                # the other consumer of x0 already wrote the full-size gradient: add ours (live frames only) in the epilogue
+                K.conv_dgrad(geom, dy, st.w_fprop(weight), hw, x0.shape[3], out=slot.buf[x0_full.shape[0] - x0.shape[0]:], accumulate=True)
+            elif x0 is x0_full:
+                gx0 = K.conv_dgrad(geom, dy, st.w_fprop(weight), hw, x0.shape[3])
+                if slot is not None and role == "first":
+                    slot.buf = gx0
             else:
                 gx0 = torch.zeros(x0_full.shape, device=dy.device, dtype=torch.bfloat16)
-                K.conv_dgrad(geom, dy, st.w_fprop(weight), (x0.shape[1], x0.shape[2]), x0.shape[3],
-                             out=gx0[x0_full.shape[0] - x0.shape[0]:])
+                K.conv_dgrad(geom, dy, st.w_fprop(weight), hw, x0.shape[3], out=gx0[x0_full.shape[0] - x0.shape[0]:])
+                if slot is not None and role == "first":
+                    slot.buf = gx0
         return gx0, None, None, None
 
 
