@@ -239,3 +239,23 @@ def test_weight_prep():
     wf, wt = K.weight_prep(w)
     assert torch.equal(wf, w.to(torch.bfloat16))
     assert torch.equal(wt, w.to(torch.bfloat16).permute(2, 1, 0).contiguous())
+
+
+@pytest.mark.parametrize("geom,nb,h,w,cin,cout", [(G31, 4, 16, 16, 128, 128), (G32, 4, 16, 16, 128, 256), (G11, 6, 16, 16, 256, 144), (GT, 4, 8, 8, 256, 128)])
+def test_dgrad_accumulates_into_bf16_buffer(geom, nb, h, w, cin, cout):
+    """Second gradient of a fan-out tensor added in the dgrad epilogue (bf16 TMA reduce-add): G += dgrad(dy) must equal
+    bf16(G + bf16(dgrad)) -- what autograd's add of two bf16 gradients gives -- on plain, stride-2 (phase-view store),
+    1x1 and transposed geometries, and on a tail slice of a larger buffer (live frames only)."""
+    setup_exact()
+    K = _k()
+    taps = {G31: 9, G32: 9, G11: 1, GT: 4}[geom]
+    wgt = _mkw(cout, taps, cin, 91)
+    ho, wo = K.out_hw(geom, h, w)
+    dy = _mk(nb, ho, wo, cout, 92)
+    g0 = _mk(nb + 2, h, w, cin, 93)
+    ref = (g0[2:].float() + K.conv_dgrad(geom, dy, wgt, (h, w), cin).float()).to(torch.bfloat16)
+    buf = g0.clone()
+    K.conv_dgrad(geom, dy, wgt, (h, w), cin, out=buf[2:], accumulate=True)
+    torch.cuda.synchronize()
+    assert torch.equal(buf[:2], g0[:2])
+    assert torch.equal(buf[2:], ref), describe_mismatch(buf[2:].float(), ref.float())
