@@ -647,6 +647,7 @@ def run_ours(args):
         "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["launches"], "roofline": main["roofline"],
         "cpu_baseline": cpu_baseline, "gpu_eager_baseline": gpu_eager, "dropin_eager": dropin, "cfg3": cfg3, "ranks_in_lockstep": main["lockstep"],
         "cuda_graph_active": main["graph_active"], "cuda_graph": main["graphed"],
+        "dependent_launch": bool(_lib.lib().snn_get_dependent_launch()),
         "kernel_timing": main["timing"], "kernels": main["kernels"], "kernels_by_shape": main["by_shape"],
         "kernel_ms_sum_per_step": main["kernel_ms_sum"], "other_kernels_ms_per_step": main["other_kernels"],
         "lif_microbench": lif, "last_loss_items": main["last_loss"],

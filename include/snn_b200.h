@@ -40,6 +40,13 @@ void snn_debug_set(int key, int value);
  * static walk every launch waits for them.  Dynamic mode uses a library-owned 32 KB counter pool per device (allocated at
  * the first launch in that mode; launch once eagerly before capturing a CUDA graph). */
 void snn_set_tile_scheduling(int dynamic);
+/* Programmatic dependent launch (process-wide, read at launch; default 0): 1 = every kernel of the library is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, so it may become resident -- and run its barrier / TMEM / table
+ * set-up -- while its predecessor on the stream drains; each kernel executes griddepcontrol.wait before its first global
+ * memory access, so results are identical to serialized launches.  Also honoured under CUDA-graph stream capture
+ * (programmatic edges between consecutive kernel nodes). */
+void snn_set_dependent_launch(int on);
+int snn_get_dependent_launch(void);
 /* The library keeps a process-wide, mutex-guarded cache of encoded TMA tensor maps keyed by (device, pointer, shape,
  * strides, box): hit / miss counters since load (a steady eager training loop re-uses every map of the previous step). */
 void snn_tensor_map_cache_stats(unsigned long long* hits, unsigned long long* misses);

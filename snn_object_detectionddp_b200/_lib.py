@@ -65,7 +65,7 @@ class SnnKernelError(RuntimeError):
 
 
 def exported_symbols():
-    return sorted(list(_SIGNATURES) + ["snn_last_error", "snn_version", "snn_debug_set", "snn_set_tile_scheduling", "snn_tensor_map_cache_stats", "snn_conv_stats_groups", "snn_bn_stats_workspace_floats", "snn_nms_workspace_keys",
+    return sorted(list(_SIGNATURES) + ["snn_last_error", "snn_version", "snn_debug_set", "snn_set_tile_scheduling", "snn_set_dependent_launch", "snn_get_dependent_launch", "snn_tensor_map_cache_stats", "snn_conv_stats_groups", "snn_bn_stats_workspace_floats", "snn_nms_workspace_keys",
                                              "snn_tal_workspace_bytes", "snn_dw3x3_stats_blocks", "snn_bn_finalize_workspace_doubles"])
 
 
@@ -100,6 +100,11 @@ def lib():
         L.snn_debug_set.restype = None
         L.snn_set_tile_scheduling.argtypes = [_I]
         L.snn_set_tile_scheduling.restype = None
+        L.snn_set_dependent_launch.argtypes = [_I]
+        L.snn_set_dependent_launch.restype = None
+        L.snn_get_dependent_launch.argtypes = []
+        L.snn_get_dependent_launch.restype = _I
+        L.snn_set_dependent_launch(int(os.environ.get("SNN_DEPENDENT_LAUNCH", "0")))
         L.snn_tensor_map_cache_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
         L.snn_tensor_map_cache_stats.restype = None
         _lib = L

@@ -39,6 +39,10 @@ int num_sms() {
     return n;
 }
 
+static std::atomic<int> g_pdl{0};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+void set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
+
 // launchers defined in the other translation units
 void debug_set(int k, int v);
 void set_dynamic_tiles(int on);
@@ -110,6 +114,8 @@ const char* snn_last_error(void) { return g_err; }
 int snn_version(void) { return 100; }
 void snn_debug_set(int key, int value) { debug_set(key, value); }
 void snn_set_tile_scheduling(int dynamic) { set_dynamic_tiles(dynamic); }
+void snn_set_dependent_launch(int on) { set_pdl(on); }
+int snn_get_dependent_launch(void) { return pdl_enabled() ? 1 : 0; }
 void snn_tensor_map_cache_stats(unsigned long long* hits, unsigned long long* misses) { tmap_cache_stats(hits, misses); }
 
 int snn_conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long long ld0, const void* x1, int C1,

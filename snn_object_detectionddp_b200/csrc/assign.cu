@@ -71,6 +71,8 @@ tal_metric_topk_kernel(const float* __restrict__ probs /*[B,A,nc]*/, const float
                        float img_w, float img_h, int A, int M, int nc, int topk,
                        float* __restrict__ align /*[B,M,A]*/, float* __restrict__ ovl /*[B,M,A]*/, int* __restrict__ sel /*[B,M,kTopkMax]*/,
                        unsigned int* __restrict__ pos /*[B,M,2]*/) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float s_v[8];
     __shared__ int s_i[8];
     __shared__ int s_sel[kTopkMax];
@@ -139,6 +141,8 @@ __global__ void __launch_bounds__(128)
 tal_resolve_kernel(const long long* __restrict__ gt_cls, const float* __restrict__ gt_box, const uint8_t* __restrict__ gt_valid,
                    float img_w, float img_h, int A, int M, const float* __restrict__ align, const float* __restrict__ ovl,
                    const int* __restrict__ sel, unsigned int* __restrict__ pos, int* __restrict__ tgt /*[B,A]*/) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ int s_sel[];      // [M][kTopkMax] then ok flags [M]
     int* s_ok = s_sel + M * kTopkMax;
     const int b = blockIdx.y;
@@ -179,6 +183,8 @@ tal_targets_kernel(const long long* __restrict__ gt_cls, const float* __restrict
                    float img_w, float img_h, int A, int M, int nc, const float* __restrict__ align, const unsigned int* __restrict__ pos,
                    const int* __restrict__ tgt, float* __restrict__ tbox /*[B,A,4]*/, float* __restrict__ tscores /*[B,A,nc]*/,
                    uint8_t* __restrict__ fg /*[B,A]*/, float* __restrict__ tss_part /*[B*gridDim.x]*/) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sh[4];
     const int b = blockIdx.y;
     const int a = blockIdx.x * 128 + threadIdx.x;
@@ -228,7 +234,7 @@ int launch_tal_assign(const float* probs, const float* pboxes, const float* anch
     unsigned int* pos = reinterpret_cast<unsigned int*>(sel + (long long)B * M * kTopkMax);
     int* tgt = reinterpret_cast<int*>(pos + 2LL * B * M);
     float* tss_part = reinterpret_cast<float*>(tgt + (long long)B * A);
-    tal_metric_topk_kernel<<<dim3(M, B), 256, 0, st>>>(probs, pboxes, anchors, stride, gt_cls, gt_box, gt_valid, img_w, img_h, A, M, nc,
+    launch_pdl(tal_metric_topk_kernel, dim3(M, B), dim3(256), 0, st, probs, pboxes, anchors, stride, gt_cls, gt_box, gt_valid, img_w, img_h, A, M, nc,
                                                        topk, align, ovl, sel, pos);
     SNN_CUDA_OK(cudaGetLastError());
     const size_t smem = sizeof(int) * ((size_t)M * kTopkMax + M);
@@ -236,9 +242,9 @@ int launch_tal_assign(const float* probs, const float* pboxes, const float* anch
         static PerDeviceOnce once;
         SNN_CUDA_OK(once.run([] { return cudaFuncSetAttribute(tal_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
     }
-    tal_resolve_kernel<<<dim3(blocks, B), 128, smem, st>>>(gt_cls, gt_box, gt_valid, img_w, img_h, A, M, align, ovl, sel, pos, tgt);
+    launch_pdl(tal_resolve_kernel, dim3(blocks, B), dim3(128), smem, st, gt_cls, gt_box, gt_valid, img_w, img_h, A, M, align, ovl, sel, pos, tgt);
     SNN_CUDA_OK(cudaGetLastError());
-    tal_targets_kernel<<<dim3(blocks, B), 128, 0, st>>>(gt_cls, gt_box, gt_valid, img_w, img_h, A, M, nc, align, pos, tgt, tbox, tscores, fg,
+    launch_pdl(tal_targets_kernel, dim3(blocks, B), dim3(128), 0, st, gt_cls, gt_box, gt_valid, img_w, img_h, A, M, nc, align, pos, tgt, tbox, tscores, fg,
                                                         tss_part);
     if (tss_part_out) *tss_part_out = tss_part;
     if (tss_parts) *tss_parts = B * blocks;

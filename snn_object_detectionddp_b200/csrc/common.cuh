@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <mutex>
+#include <utility>
 
 #define SNN_DEVINL __device__ __forceinline__
 
@@ -32,6 +33,35 @@ int check_cuda(cudaError_t e, const char* what);
 
 int num_sms();          // SM count of the CURRENT device (cached per device ordinal)
 int current_device();   // cudaGetDevice, -1 on error
+
+// ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol): a kernel launched through launch_pdl() may become resident while its
+// predecessor on the stream is still draining -- launch latency, CTA scheduling and its own barrier / TMEM / table set-up
+// overlap the predecessor's tail.  CONTRACT: every kernel launched this way executes pdl_wait() before its first access
+// to global memory (reads AND writes: the predecessor may still be reading what this kernel overwrites); the wait returns
+// once the preceding grid has completed and its writes are visible.  pdl_launch_dependents() at the top lets the NEXT
+// kernel do the same with respect to this one (it still waits for this grid's completion at its own pdl_wait()).
+// Without the launch attribute both instructions are no-ops.  Process-wide switch: set_pdl() / snn_set_pdl().
+// ------------------------------------------------------------------------------------------
+SNN_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+SNN_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+void set_pdl(int on);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // One-time initialisation PER DEVICE (function attributes such as the dynamic shared-memory limit live in the device's
 // context: a process that touches cuda:3 after cuda:0 must set them again).  Thread-safe; remembers the first error.

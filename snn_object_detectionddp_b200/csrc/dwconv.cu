@@ -60,6 +60,8 @@ template <bool DGRAD>
 __global__ void __launch_bounds__(256)
 dw3x3_col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt, float* __restrict__ y32,
                  __nv_bfloat16* __restrict__ y16, float* __restrict__ part, int imgs_per_group, int H, int W, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sh[];                 // [9][C] weights, then (statistics) [slots][2][C]
     const int c4 = C >> 2, slots = 256 / c4;
     float* shw = sh;
@@ -145,6 +147,8 @@ dw3x3_col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 dw3x3_wgrad_col_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, int NB, int H,
                        int W, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sh[];                 // [slots][3][C] (one tap row at a time)
     const int c8 = C >> 3, slots = 256 / c8;
     const int slot = threadIdx.x / c8, cg = threadIdx.x % c8;
@@ -205,6 +209,8 @@ dw3x3_wgrad_col_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
 // frames fp32 [B][T][3][H][W] (or [N][3][H][W] with T=1) -> bf16 NHWC [T*B][H/8][W/8][192], channel = c*64 + dy*8 + dx
 __global__ void __launch_bounds__(256)
 s2d8_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int T, int H, int W) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int H8 = H >> 3, W8 = W >> 3;
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;  // over (n, c, dy, i, j) with j fastest
     const long long total = (long long)B * T * 3 * 8 * H8 * W8;
@@ -239,13 +245,13 @@ int launch_dw3x3_fwd(const __nv_bfloat16* x, const float* w, float* y, int NB, i
     static PerDeviceOnce once;
     SNN_CUDA_OK(once.run([] { return cudaFuncSetAttribute(dw3x3_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
     dim3 grid((unsigned)dw3x3_stats_blocks(B, W, C), groups);
-    dw3x3_col_kernel<false><<<grid, 256, smem, st>>>(x, w, y, nullptr, part, B, H, W, C);
+    launch_pdl(dw3x3_col_kernel<false>, grid, dim3(256), smem, st, x, w, y, nullptr, part, B, H, W, C);
     return check_cuda(cudaGetLastError(), "dw3x3_col_kernel<fprop>");
 }
 int launch_dw3x3_dgrad(const __nv_bfloat16* dy, const float* w, __nv_bfloat16* dx, int NB, int H, int W, int C, cudaStream_t st) {
     SNN_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1024, "dw3x3: C=%d must be a multiple of 8 in [8,1024]", C);
     dim3 grid((unsigned)dw3x3_stats_blocks(NB, W, C), 1);
-    dw3x3_col_kernel<true><<<grid, 256, sizeof(float) * 9 * C, st>>>(dy, w, nullptr, dx, nullptr, NB, H, W, C);
+    launch_pdl(dw3x3_col_kernel<true>, grid, dim3(256), sizeof(float) * 9 * C, st, dy, w, nullptr, dx, nullptr, NB, H, W, C);
     return check_cuda(cudaGetLastError(), "dw3x3_col_kernel<dgrad>");
 }
 int launch_dw3x3_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int NB, int H, int W, int C, cudaStream_t st) {
@@ -257,13 +263,15 @@ int launch_dw3x3_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* d
     const size_t smem = sizeof(float) * (size_t)slots * 3 * C;
     static PerDeviceOnce once;
     SNN_CUDA_OK(once.run([] { return cudaFuncSetAttribute(dw3x3_wgrad_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
-    dw3x3_wgrad_col_kernel<<<(unsigned)blocks, 256, smem, st>>>(x, dy, dw, NB, H, W, C);
+    launch_pdl(dw3x3_wgrad_col_kernel, dim3((unsigned)blocks), dim3(256), smem, st, x, dy, dw, NB, H, W, C);
     return check_cuda(cudaGetLastError(), "dw3x3_wgrad_col_kernel");
 }
 // uint8 frames (what the dataset decodes, dataset.py:139-152) -> /255 on the device (the reference divides on the host and
 // ships fp32: 4x the PCIe bytes); `v / 255.0f` in IEEE fp32 is bit-identical to torch's `.float() / 255.0`
 __global__ void __launch_bounds__(256)
 s2d8_u8_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int T, int H, int W) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int H8 = H >> 3, W8 = W >> 3;
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long total = (long long)B * T * 3 * 8 * H8 * W8;
@@ -289,13 +297,13 @@ s2d8_u8_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out, 
 int launch_s2d8_u8(const uint8_t* in, __nv_bfloat16* out, int B, int T, int H, int W, cudaStream_t st) {
     SNN_REQUIRE(H % 8 == 0 && W % 8 == 0, "space_to_depth8: H, W must be multiples of 8");
     const long long total = (long long)B * T * 3 * 8 * (H / 8) * (W / 8);
-    s2d8_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, B, T, H, W);
+    launch_pdl(s2d8_u8_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, in, out, B, T, H, W);
     return check_cuda(cudaGetLastError(), "s2d8_u8_kernel");
 }
 int launch_s2d8(const float* in, __nv_bfloat16* out, int B, int T, int H, int W, cudaStream_t st) {
     SNN_REQUIRE(H % 8 == 0 && W % 8 == 0, "space_to_depth8: H, W must be multiples of 8");
     const long long total = (long long)B * T * 3 * 8 * (H / 8) * (W / 8);
-    s2d8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, B, T, H, W);
+    launch_pdl(s2d8_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, in, out, B, T, H, W);
     return check_cuda(cudaGetLastError(), "s2d8_kernel");
 }
 

@@ -119,6 +119,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __shared__ SchedRing ring;
     __shared__ uint32_t tmem_base_s;
 
+    pdl_launch_dependents();      // the next kernel may start its own set-up; it waits for this grid at its pdl_wait()
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp: provably uniform
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int stages = p.stages;
@@ -158,6 +159,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();                   // barriers, TMEM and descriptor prefetch above overlapped the previous kernel's tail
 
     // Both role loops below run WARP-UNIFORM (all 32 lanes walk the loop, one elected lane issues the TMA / MMA
     // instructions): loop state then lives in uniform registers and the per-chunk instruction count of the issuing
@@ -556,6 +558,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     __shared__ SchedRing ring;
     __shared__ uint32_t tmem_base_s;
 
+    pdl_launch_dependents();
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int stages = p.stages;
@@ -593,6 +596,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();                   // barriers, TMEM and descriptor prefetch above overlapped the previous kernel's tail
 
     // warp-uniform role loops (see conv_gemm_kernel): one elected lane issues, loop state stays in uniform registers
     if (warp == 0) {
@@ -1051,8 +1055,8 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
         int grid = num_sms();
         if (g_debug_flags[5] > 0) grid = g_debug_flags[5];
         if (grid > total_tiles) grid = total_tiles;
-        conv_gemm_kernel<false><<<grid, 64 + 128 * p.epi_groups, smem, st>>>(a0, a1, b, o, p);
-        return check_cuda(cudaGetLastError(), "conv_gemm_kernel launch");
+        return check_cuda(launch_pdl(conv_gemm_kernel<false>, dim3(grid), dim3(64 + 128 * p.epi_groups), smem, st, a0, a1, b, o, p),
+                          "conv_gemm_kernel launch");
     }
     const int total_tiles = ((m_tiles + 1) / 2) * p.n_blocks * p.nphase * p.ksplit;
     int pairs = num_sms() / 2;
@@ -1064,11 +1068,13 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     cfg.blockDim = dim3(64 + 128 * p.epi_groups, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     return check_cuda(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, a0, a1, b, o, p), "conv_gemm_kernel<pair> launch");
 }
 
@@ -1333,8 +1339,7 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
     int nw = workers < items ? workers : items;
     if (g_debug_flags[5] > 0 && nw > g_debug_flags[5]) nw = g_debug_flags[5];
     if (!pair) {
-        wgrad_gemm_kernel<false><<<nw, 192, smem, st>>>(mg, mx, mw, p);
-        return check_cuda(cudaGetLastError(), "wgrad_gemm_kernel launch");
+        return check_cuda(launch_pdl(wgrad_gemm_kernel<false>, dim3(nw), dim3(192), smem, st, mg, mx, mw, p), "wgrad_gemm_kernel launch");
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1342,11 +1347,13 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
     cfg.blockDim = dim3(192, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     return check_cuda(cudaLaunchKernelEx(&cfg, wgrad_gemm_kernel<true>, mg, mx, mw, p), "wgrad_gemm_kernel<pair> launch");
 }
 

@@ -172,6 +172,8 @@ detect_loss_fwd_kernel(const float* __restrict__ distri, const float* __restrict
                        const float* __restrict__ stride, const float* __restrict__ tbox_px, const float* __restrict__ tscores,
                        const uint8_t* __restrict__ fg, long long N, int A, int nc, double* __restrict__ sums, const RowMap rm,
                        const LossFinal fin) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sh[4];
     __shared__ unsigned int s_ticket;
     const long long n = (long long)blockIdx.x * 128 + threadIdx.x;
@@ -224,6 +226,8 @@ detect_loss_bwd_kernel(const float* __restrict__ distri, const float* __restrict
                        const float* __restrict__ stride, const float* __restrict__ tbox_px, const float* __restrict__ tscores,
                        const uint8_t* __restrict__ fg, long long N, int A, int nc, const float* __restrict__ coef,
                        const float* __restrict__ gout, TG* __restrict__ g_distri, TG* __restrict__ g_scores, const RowMap rm) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long n = (long long)blockIdx.x * 128 + threadIdx.x;
     if (n >= N) return;
     const int a = (int)(n % A);
@@ -263,6 +267,8 @@ __global__ void __launch_bounds__(128)
 detect_decode_kernel(const float* __restrict__ distri, const float* __restrict__ scores, const float* __restrict__ anchors,
                      const float* __restrict__ stride, long long N, int A, int nc, int xywh, float* __restrict__ boxes,
                      float* __restrict__ probs, const RowMap rm) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long n = (long long)blockIdx.x * 128 + threadIdx.x;
     if (n >= N) return;
     const int a = (int)(n % A);
@@ -313,7 +319,7 @@ int launch_detect_decode(const float* distri, const float* scores, const float* 
     if (N == 0) return 0;
     RowMap rm;
     if (make_rowmap(&rm, nl, a_off, B, A)) return 2;
-    detect_decode_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(distri, scores, anchors, stride, N, A, nc, xywh, boxes, probs, rm);
+    launch_pdl(detect_decode_kernel, dim3((unsigned)((N + 127) / 128)), dim3(128), 0, st, distri, scores, anchors, stride, N, A, nc, xywh, boxes, probs, rm);
     return check_cuda(cudaGetLastError(), "detect_decode_kernel");
 }
 
@@ -329,7 +335,7 @@ int launch_detect_loss_fwd(const float* distri, const float* scores, const float
     if (make_rowmap(&rm, nl, a_off, B, A)) return 2;
     LossFinal fin = {tss_part, n_parts, gains, counter, out6, coef3, (float)B};
     if (tss_part) SNN_REQUIRE(gains && counter && out6 && coef3 && n_parts >= 1, "detect_loss_fwd: fused finalisation needs gains/counter/out6/coef3");
-    detect_loss_fwd_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(distri, scores, anchors, stride, tbox_px, tscores, fg,
+    launch_pdl(detect_loss_fwd_kernel, dim3((unsigned)((N + 127) / 128)), dim3(128), 0, st, distri, scores, anchors, stride, tbox_px, tscores, fg,
                                                                         N, A, nc, sums, rm, fin);
     return check_cuda(cudaGetLastError(), "detect_loss_fwd_kernel");
 }
@@ -345,10 +351,10 @@ int launch_detect_loss_bwd(const float* distri, const float* scores, const float
     if (make_rowmap(&rm, nl, a_off, B, A)) return 2;
     const unsigned grid = (unsigned)((N + 127) / 128);
     if (out_bf16)
-        detect_loss_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(distri, scores, anchors, stride, tbox_px, tscores, fg, N, A, nc, coef, gout,
+        launch_pdl(detect_loss_bwd_kernel<__nv_bfloat16>, grid, dim3(128), 0, st, distri, scores, anchors, stride, tbox_px, tscores, fg, N, A, nc, coef, gout,
                                                                     (__nv_bfloat16*)g_distri, (__nv_bfloat16*)g_scores, rm);
     else
-        detect_loss_bwd_kernel<float><<<grid, 128, 0, st>>>(distri, scores, anchors, stride, tbox_px, tscores, fg, N, A, nc, coef, gout,
+        launch_pdl(detect_loss_bwd_kernel<float>, grid, dim3(128), 0, st, distri, scores, anchors, stride, tbox_px, tscores, fg, N, A, nc, coef, gout,
                                                             (float*)g_distri, (float*)g_scores, rm);
     return check_cuda(cudaGetLastError(), "detect_loss_bwd_kernel");
 }

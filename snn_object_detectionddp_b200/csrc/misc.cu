@@ -9,6 +9,8 @@ namespace snn {
 // ------------------------------------------------------------------------------------------
 __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                    __nv_bfloat16* __restrict__ wt, int N, int T, int K) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int t = blockIdx.z;
     const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
@@ -34,7 +36,7 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* _
 
 int launch_weight_prep(const float* w, __nv_bfloat16* wf, __nv_bfloat16* wt, int N, int T, int K, cudaStream_t st) {
     dim3 grid((K + 31) / 32, (N + 31) / 32, T), block(32, 8);
-    weight_prep_kernel<<<grid, block, 0, st>>>(w, wf, wt, N, T, K);
+    launch_pdl(weight_prep_kernel, grid, block, 0, st, w, wf, wt, N, T, K);
     return check_cuda(cudaGetLastError(), "weight_prep_kernel");
 }
 
@@ -44,6 +46,8 @@ int launch_weight_prep(const float* w, __nv_bfloat16* wf, __nv_bfloat16* wt, int
 template <typename TOut>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, TOut* __restrict__ out, int C, int HW, long long out_ld,
                                     int out_coff) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -62,6 +66,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, TOut* __restri
 template <typename TIn>
 __global__ void nhwc_to_nchw_kernel(const TIn* __restrict__ in, float* __restrict__ out, int C, int HW, long long in_ld,
                                     int in_coff) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -81,9 +87,9 @@ int launch_nchw_to_nhwc(const float* in, void* out, int out_bf16, int NB, int C,
                         cudaStream_t st) {
     dim3 grid((HW + 31) / 32, (C + 31) / 32, NB), block(32, 8);
     if (out_bf16)
-        nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(in, (__nv_bfloat16*)out, C, HW, out_ld, out_coff);
+        launch_pdl(nchw_to_nhwc_kernel<__nv_bfloat16>, grid, block, 0, st, in, (__nv_bfloat16*)out, C, HW, out_ld, out_coff);
     else
-        nchw_to_nhwc_kernel<float><<<grid, block, 0, st>>>(in, (float*)out, C, HW, out_ld, out_coff);
+        launch_pdl(nchw_to_nhwc_kernel<float>, grid, block, 0, st, in, (float*)out, C, HW, out_ld, out_coff);
     return check_cuda(cudaGetLastError(), "nchw_to_nhwc_kernel");
 }
 
@@ -91,9 +97,9 @@ int launch_nhwc_to_nchw(const void* in, int in_bf16, float* out, int NB, int C, 
                         cudaStream_t st) {
     dim3 grid((HW + 31) / 32, (C + 31) / 32, NB), block(32, 8);
     if (in_bf16)
-        nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, out, C, HW, in_ld, in_coff);
+        launch_pdl(nhwc_to_nchw_kernel<__nv_bfloat16>, grid, block, 0, st, (const __nv_bfloat16*)in, out, C, HW, in_ld, in_coff);
     else
-        nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>((const float*)in, out, C, HW, in_ld, in_coff);
+        launch_pdl(nhwc_to_nchw_kernel<float>, grid, block, 0, st, (const float*)in, out, C, HW, in_ld, in_coff);
     return check_cuda(cudaGetLastError(), "nhwc_to_nchw_kernel");
 }
 
@@ -107,6 +113,8 @@ SNN_DEVINL float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 __global__ void __launch_bounds__(256)
 lstm_gates_fwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, float* __restrict__ c_next,
                       float* __restrict__ h_next, __nv_bfloat16* __restrict__ h_bf16, long long n4, int Ch) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= n4) return;
     const int ch4 = Ch >> 2;
@@ -139,6 +147,8 @@ __global__ void __launch_bounds__(256)
 lstm_gates_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_next,
                       const float* __restrict__ dh, const __nv_bfloat16* __restrict__ dh_bf16, const float* __restrict__ dc_in,
                       __nv_bfloat16* __restrict__ dgates, float* __restrict__ dc_prev, long long n4, int Ch) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= n4) return;
     const int ch4 = Ch >> 2;
@@ -185,7 +195,7 @@ int launch_lstm_gates_fwd(const float* gates, const float* c_prev, float* c_next
                           long long P, int Ch, cudaStream_t st) {
     SNN_REQUIRE(Ch % 4 == 0, "lstm_gates: Ch must be a multiple of 4");
     const long long n4 = P * Ch / 4;
-    lstm_gates_fwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(gates, c_prev, c_next, h_next, h_bf16, n4, Ch);
+    launch_pdl(lstm_gates_fwd_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, gates, c_prev, c_next, h_next, h_bf16, n4, Ch);
     return check_cuda(cudaGetLastError(), "lstm_gates_fwd_kernel");
 }
 
@@ -193,7 +203,7 @@ int launch_lstm_gates_bwd(const float* gates, const float* c_prev, const float* 
                           const float* dc_in, __nv_bfloat16* dgates, float* dc_prev, long long P, int Ch, cudaStream_t st) {
     SNN_REQUIRE(Ch % 4 == 0, "lstm_gates: Ch must be a multiple of 4");
     const long long n4 = P * Ch / 4;
-    lstm_gates_bwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(gates, c_prev, c_next, dh, dh_bf16, dc_in, dgates, dc_prev, n4, Ch);
+    launch_pdl(lstm_gates_bwd_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, gates, c_prev, c_next, dh, dh_bf16, dc_in, dgates, dc_prev, n4, Ch);
     return check_cuda(cudaGetLastError(), "lstm_gates_bwd_kernel");
 }
 
@@ -203,6 +213,8 @@ int launch_lstm_gates_bwd(const float* gates, const float* c_prev, const float* 
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ acc, long long P, int C, int cblk,
                    int pix_per_block) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float shc[];  // [cblk]
     const int c_base = blockIdx.y * cblk;
     const int cw = min(cblk, C - c_base);
@@ -236,7 +248,7 @@ int launch_colsum_bf16(const __nv_bfloat16* dy, float* acc, long long P, int C, 
     if (ppb < rows * 4) ppb = rows * 4;
     ppb = (ppb + rows - 1) / rows * rows;
     dim3 grid((unsigned)((P + ppb - 1) / ppb), (C + cblk - 1) / cblk);
-    colsum_bf16_kernel<<<grid, 256, sizeof(float) * cblk, st>>>(dy, acc, P, C, cblk, (int)ppb);
+    launch_pdl(colsum_bf16_kernel, grid, dim3(256), sizeof(float) * cblk, st, dy, acc, P, C, cblk, (int)ppb);
     return check_cuda(cudaGetLastError(), "colsum_bf16_kernel");
 }
 
@@ -248,6 +260,8 @@ int launch_colsum_bf16(const __nv_bfloat16* dy, float* acc, long long P, int C, 
 // OneCycle schedule never forces a host sync:  hp = {lr, beta1, beta2, eps, wd, bc1, bc2, max_norm}
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n4, double* __restrict__ acc) {
+    pdl_launch_dependents();
+    pdl_wait();
     float s = 0.f;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
@@ -268,6 +282,8 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              __nv_bfloat16* __restrict__ shadow, long long n4, const float* __restrict__ hp_table,
              const double* __restrict__ sumsq, float* __restrict__ gnorm_out, const int* __restrict__ step_ptr, int n_rows) {
+    pdl_launch_dependents();
+    pdl_wait();
     // row of the tabulated schedule: picked by a DEVICE step counter so a captured CUDA graph advances on replay
     const float* hp = hp_table + (step_ptr ? (size_t)min(*step_ptr, n_rows - 1) * 8 : 0);
     const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], bc1 = hp[5], bc2 = hp[6], max_norm = hp[7];
@@ -312,11 +328,13 @@ int launch_sumsq(const float* g, long long n, double* acc, int zero_first, cudaS
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    sumsq_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, n4, acc);
+    launch_pdl(sumsq_kernel, dim3((unsigned)blocks), dim3(256), 0, st, g, n4, acc);
     return check_cuda(cudaGetLastError(), "sumsq_kernel");
 }
 
-__global__ void step_advance_kernel(int* step) { *step += 1; }
+__global__ void step_advance_kernel(int* step) {
+    pdl_launch_dependents();
+    pdl_wait(); *step += 1; }
 
 int launch_adamw(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, long long n, const float* hp,
                  const double* sumsq, float* gnorm_out, int* step_ptr, int n_rows, int zero_grad, cudaStream_t st) {
@@ -326,13 +344,13 @@ int launch_adamw(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, 
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, shadow, n4, hp, sumsq, gnorm_out, step_ptr, n_rows);
+    launch_pdl(adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, st, p, g, m, v, shadow, n4, hp, sumsq, gnorm_out, step_ptr, n_rows);
     SNN_CUDA_OK(cudaGetLastError());
     // zero_grad: the gradient has been consumed; leave it zeroed for the next step's accumulating wgrad kernels
     // (optimizer.zero_grad() of train.py:61).  A memset node right behind the kernel: 67 us for 481 MB.  Storing the zeros
     // from inside the kernel (to the line it has just loaded) was measured 4x slower for the WHOLE pass (0.58 -> 2.35 ms).
     if (zero_grad) SNN_CUDA_OK(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)n, st));
-    if (step_ptr) step_advance_kernel<<<1, 1, 0, st>>>(step_ptr);
+    if (step_ptr) launch_pdl(step_advance_kernel, dim3(1), dim3(1), 0, st, step_ptr);
     return check_cuda(cudaGetLastError(), "adamw_kernel");
 }
 
@@ -365,6 +383,8 @@ SNN_DEVINL void unpack8(const uint4 v, float* f) {
 __global__ void __launch_bounds__(256)
 bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int NB, int Hi, int Wi, int Ho, int Wo,
                     int C, float sh, float sw) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int c8 = C >> 3;
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long total = (long long)NB * Ho * Wo * c8;
@@ -400,6 +420,8 @@ bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
 __global__ void __launch_bounds__(256)
 bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ gy, __nv_bfloat16* __restrict__ gx, int NB, int Hi, int Wi, int Ho, int Wo,
                     int C, float sh, float sw) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int c8 = C >> 3;
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long total = (long long)NB * Hi * Wi * c8;
@@ -447,10 +469,10 @@ int launch_bilinear(int backward, const __nv_bfloat16* src, __nv_bfloat16* dst, 
     const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;     // ATen area_pixel_compute_scale (align_corners=False)
     if (!backward) {
         const long long total = (long long)NB * Ho * Wo * (C / 8);
-        bilinear_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, NB, Hi, Wi, Ho, Wo, C, sh, sw);
+        launch_pdl(bilinear_fwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, src, dst, NB, Hi, Wi, Ho, Wo, C, sh, sw);
     } else {
         const long long total = (long long)NB * Hi * Wi * (C / 8);
-        bilinear_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, NB, Hi, Wi, Ho, Wo, C, sh, sw);
+        launch_pdl(bilinear_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, src, dst, NB, Hi, Wi, Ho, Wo, C, sh, sw);
     }
     return check_cuda(cudaGetLastError(), "bilinear_kernel");
 }
@@ -463,6 +485,8 @@ int launch_bilinear(int backward, const __nv_bfloat16* src, __nv_bfloat16* dst, 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pad_crop_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int NB, int Hs, int Ws, int Hd, int Wd, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int c8 = C >> 3;
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long total = (long long)NB * Hd * Wd * c8;
@@ -481,7 +505,7 @@ int launch_pad_crop(const __nv_bfloat16* src, __nv_bfloat16* dst, int NB, int Hs
     SNN_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "pad_crop: pointers must be 16-byte aligned");
     const long long total = (long long)NB * Hd * Wd * (C / 8);
     if (total == 0) return 0;
-    pad_crop_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, NB, Hs, Ws, Hd, Wd, C);
+    launch_pdl(pad_crop_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, src, dst, NB, Hs, Ws, Hd, Wd, C);
     return check_cuda(cudaGetLastError(), "pad_crop_kernel");
 }
 

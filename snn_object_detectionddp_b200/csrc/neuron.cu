@@ -19,6 +19,8 @@ enum { ACT_LIF = 0, ACT_SILU = 1 };
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, float* __restrict__ part /*[T][gridDim.x][2][C]*/,
                                                         int P, int C, int pix_per_block) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float shs[];  // [rows][2][C] per-row partials, combined in a fixed order (deterministic)
     const int t = blockIdx.y;
     const int tpp = C >> 2;  // threads per pixel (float4 each)
@@ -61,6 +63,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 constexpr int kRL = 128;   // row-lanes per block of the partial reducer (x 8 channels = 1024 threads)
 __global__ void __launch_bounds__(kRL * 8) bn_stats_from_partials_kernel(const float* __restrict__ part, double* __restrict__ sums,
                                                                           int C, int groups_per_t) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ double sh[2][kRL][8];
     const int t = blockIdx.y;
     const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;
@@ -120,6 +124,8 @@ bn_finalize_partials_kernel(const float* __restrict__ part, double* __restrict__
                             long long* nbt, float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
                             float* __restrict__ invstd_o, unsigned int* counters, int T, int C, int P, int groups_per_t, int S,
                             float eps, float momentum) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ double sh[kFinLanes][2][32];
     __shared__ unsigned int s_ticket;
     const int cg = blockIdx.x, sp = blockIdx.y;
@@ -212,6 +218,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
                                    float* __restrict__ invstd_o, int T, int C, int P, float eps, float momentum,
                                    int training) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
@@ -249,6 +257,8 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
                                                           __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ mask,
                                                           float* __restrict__ v_final, int T, long long n8, int C,
                                                           int ss_stride_t, float beta, float theta) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= n8) return;
     const int c0 = (int)((idx * 8) % C);
@@ -317,6 +327,8 @@ bn_act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ scale, 
                   const __nv_bfloat16* __restrict__ gs, const float* __restrict__ gv_final, float* __restrict__ gx_out,
                   __nv_bfloat16* __restrict__ dy_out, float* __restrict__ gv_init, float* __restrict__ red /*[T][2][C]*/,
                   int T, int P, int C, int ss_stride_t, int pix_per_block, float beta, float theta, float alpha) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float shf[];  // TRAIN: [T][2][C]
     const int tpp = C >> 2;
     const int rows = 256 / tpp;
@@ -442,6 +454,8 @@ bn_act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ scale, 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ red, const float* __restrict__ scale,
                                        float* __restrict__ coef /*[T][2][C]*/, float* dgamma, float* dbeta,
                                        const float* __restrict__ gamma, int T, int C, int P) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float dg = 0.f, db = 0.f;
@@ -461,6 +475,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_dx_kernel(const float* __restrict__ gx, const float* __restrict__ y, const float* __restrict__ scale,
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ coef,
                  __nv_bfloat16* __restrict__ dy, int T, long long n4, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= n4) return;
     const int t = blockIdx.y;
@@ -515,6 +531,8 @@ bn_act_bwd2_kernel(const float* __restrict__ y, const float* __restrict__ scale,
                    const float* __restrict__ gv_final, __nv_bfloat16* __restrict__ dy_out, float* __restrict__ gv_init,
                    float* __restrict__ red_out, float* dgamma, float* dbeta, int T_rt, int P, int C, int Cb, int pix_per_block,
                    float beta, float theta, float alpha, float invP) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float4 shc4[];
     constexpr int PITCH = TMAX | 1;
     const int T = EXACT ? TMAX : T_rt;
@@ -684,6 +702,8 @@ silu_t1_bwd2_kernel(const float* __restrict__ y, const float* __restrict__ scale
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ beta_bn,
                     const float* __restrict__ red_in, const __nv_bfloat16* __restrict__ gs, __nv_bfloat16* __restrict__ dy_out,
                     float* __restrict__ red_out, float* dgamma, float* dbeta, int P, int C, int Cb, int pix_per_block, float invP) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float4 sht[];
     constexpr int PU = 4;
     const int c_base = blockIdx.y * Cb;
@@ -810,7 +830,7 @@ int launch_bn_stats(const float* y, double* sums, float* workspace, int T, int P
     const int nblk = bn_stats_blocks(P, C, &ppb);
     const int rows = 256 / (C / 4);
     dim3 grid(nblk, T);
-    bn_stats_kernel<<<grid, 256, sizeof(float) * 2 * C * rows, st>>>(y, workspace, P, C, ppb);
+    launch_pdl(bn_stats_kernel, grid, dim3(256), sizeof(float) * 2 * C * rows, st, y, workspace, P, C, ppb);
     SNN_CUDA_OK(cudaGetLastError());
     return launch_bn_stats_from_partials(workspace, sums, T, C, nblk, st);
 }
@@ -818,7 +838,7 @@ int launch_bn_stats(const float* y, double* sums, float* workspace, int T, int P
 int launch_bn_stats_from_partials(const float* part, double* sums, int T, int C, int groups_per_t, cudaStream_t st) {
     SNN_REQUIRE(T >= 1 && C >= 1 && groups_per_t >= 1, "bn_stats_from_partials: bad sizes");
     dim3 grid((C + 7) / 8, T);
-    bn_stats_from_partials_kernel<<<grid, kRL * 8, 0, st>>>(part, sums, C, groups_per_t);
+    launch_pdl(bn_stats_from_partials_kernel, grid, dim3(kRL * 8), 0, st, part, sums, C, groups_per_t);
     return check_cuda(cudaGetLastError(), "bn_stats_from_partials_kernel");
 }
 
@@ -829,7 +849,7 @@ int launch_bn_finalize_partials(const float* part, double* sums, double* workspa
                 "bn_finalize_partials: bad arguments (workspace of snn_bn_finalize_workspace_doubles() doubles required)");
     const int S = bn_finalize_splits(groups_per_t);
     dim3 grid((C + 31) / 32, S);
-    bn_finalize_partials_kernel<<<grid, 32 * kFinLanes, 0, st>>>(part, workspace, sums, gamma, beta, rm, rv, nbt, scale, shift, mean, invstd,
+    launch_pdl(bn_finalize_partials_kernel, grid, dim3(32 * kFinLanes), 0, st, part, workspace, sums, gamma, beta, rm, rv, nbt, scale, shift, mean, invstd,
                                                                  counters, T, C, P, groups_per_t, S, eps, momentum);
     return check_cuda(cudaGetLastError(), "bn_finalize_partials_kernel");
 }
@@ -837,7 +857,7 @@ int launch_bn_finalize_partials(const float* part, double* sums, double* workspa
 int launch_bn_finalize(const double* sums, const float* gamma, const float* beta, float* rm, float* rv, float* scale,
                        float* shift, float* mean, float* invstd, int T, int C, int P, float eps, float momentum,
                        int training, cudaStream_t st) {
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, gamma, beta, rm, rv, scale, shift, mean, invstd, T, C, P,
+    launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, st, sums, gamma, beta, rm, rv, scale, shift, mean, invstd, T, C, P,
                                                         eps, momentum, training);
     return check_cuda(cudaGetLastError(), "bn_finalize_kernel");
 }
@@ -850,10 +870,10 @@ int launch_bn_act_fwd(int act, const float* y, const float* scale, const float* 
     const long long n8 = n_per_t / 8;
     const unsigned blocks = (unsigned)((n8 + 255) / 256);
     if (act == ACT_LIF)
-        bn_act_fwd_kernel<ACT_LIF><<<blocks, 256, 0, st>>>(y, scale, shift, v_init, out, mask, v_final, T, n8, C,
+        launch_pdl(bn_act_fwd_kernel<ACT_LIF>, dim3(blocks), dim3(256), 0, st, y, scale, shift, v_init, out, mask, v_final, T, n8, C,
                                                            ss_stride_t, beta, theta);
     else
-        bn_act_fwd_kernel<ACT_SILU><<<blocks, 256, 0, st>>>(y, scale, shift, v_init, out, mask, v_final, T, n8, C,
+        launch_pdl(bn_act_fwd_kernel<ACT_SILU>, dim3(blocks), dim3(256), 0, st, y, scale, shift, v_init, out, mask, v_final, T, n8, C,
                                                             ss_stride_t, beta, theta);
     return check_cuda(cudaGetLastError(), "bn_act_fwd_kernel");
 }
@@ -868,7 +888,7 @@ static int launch_bwd_t(const float* y, const float* scale, const float* shift, 
     const size_t smem = TRAIN ? sizeof(float) * T * 2 * C : 0;
     auto kern = bn_act_bwd_kernel<ACT, TMAX, TRAIN>;
     if (smem > 48 * 1024) SNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(P + ppb - 1) / ppb, 256, smem, st>>>(y, scale, shift, mean, invstd, v_init, gs, gv_final, gx, dy, gv_init,
+    launch_pdl(kern, dim3((P + ppb - 1) / ppb), dim3(256), smem, st, y, scale, shift, mean, invstd, v_init, gs, gv_final, gx, dy, gv_init,
                                                  red, T, P, C, ss, ppb, beta, theta, alpha);
     return check_cuda(cudaGetLastError(), "bn_act_bwd_kernel");
 }
@@ -919,7 +939,7 @@ static int launch_bwd2_t(const float* y, const float* scale, const float* shift,
     do {                                                                                                                   \
         auto kern = bn_act_bwd2_kernel<ACT, TMAX, REDUCE, EX>;                                                             \
         if (smem > 48 * 1024) SNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<grid, 256, smem, st>>>(y, scale, shift, mean, invstd, beta_bn, red_in, v_init, gs, gv_final, dy, gv_init,   \
+        launch_pdl(kern, grid, dim3(256), smem, st, y, scale, shift, mean, invstd, beta_bn, red_in, v_init, gs, gv_final, dy, gv_init,   \
                                       red_out, dgamma, dbeta, T, P, C, Cb, ppb, beta, theta, alpha, 1.0f / (float)P);      \
     } while (0)
     if (T == TMAX) SNN_GO(true); else SNN_GO(false);
@@ -952,10 +972,10 @@ int launch_bn_act_bwd2(int pass, int act, const float* y, const float* scale, co
         const size_t smem = (size_t)(Cb / 2) * 32 + (pass == 0 ? (size_t)2 * Cb * 4 : 0);
         dim3 grid((P + ppb - 1) / ppb, nyb);
         if (pass == 0)
-            silu_t1_bwd2_kernel<true><<<grid, 256, smem, st>>>(y, scale, shift, mean, invstd, beta_bn, nullptr, gs, nullptr, red, nullptr,
+            launch_pdl(silu_t1_bwd2_kernel<true>, grid, dim3(256), smem, st, y, scale, shift, mean, invstd, beta_bn, nullptr, gs, nullptr, red, nullptr,
                                                                nullptr, P, C, Cb, ppb, 1.0f / (float)P);
         else
-            silu_t1_bwd2_kernel<false><<<grid, 256, smem, st>>>(y, scale, shift, mean, invstd, beta_bn, red, gs, dy, nullptr, dgamma, dbeta,
+            launch_pdl(silu_t1_bwd2_kernel<false>, grid, dim3(256), smem, st, y, scale, shift, mean, invstd, beta_bn, red, gs, dy, nullptr, dgamma, dbeta,
                                                                 P, C, Cb, ppb, 1.0f / (float)P);
         return check_cuda(cudaGetLastError(), "silu_t1_bwd2_kernel");
     }
@@ -975,11 +995,11 @@ int launch_bn_act_bwd2(int pass, int act, const float* y, const float* scale, co
 int launch_bn_bwd_dx(const float* red, const float* gamma, const float* gx, const float* y, const float* scale,
                      const float* mean, const float* invstd, float* coef, float* dgamma, float* dbeta,
                      __nv_bfloat16* dy, int T, int P, int C, cudaStream_t st) {
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, scale, coef, dgamma, dbeta, gamma, T, C, P);
+    launch_pdl(bn_bwd_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, st, red, scale, coef, dgamma, dbeta, gamma, T, C, P);
     SNN_CUDA_OK(cudaGetLastError());
     const long long n4 = (long long)P * C / 4;
     dim3 grid((unsigned)((n4 + 255) / 256), T);
-    bn_bwd_dx_kernel<<<grid, 256, 0, st>>>(gx, y, scale, mean, invstd, coef, dy, T, n4, C);
+    launch_pdl(bn_bwd_dx_kernel, grid, dim3(256), 0, st, gx, y, scale, mean, invstd, coef, dy, T, n4, C);
     return check_cuda(cudaGetLastError(), "bn_bwd_dx_kernel");
 }
 

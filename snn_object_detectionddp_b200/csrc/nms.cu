@@ -77,6 +77,8 @@ SNN_DEVINL bool nms_overlap(const OBox& a, const OBox& b, float thr) {
 }
 
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ unsigned long long skeys[];     // kNmsSmemKeys keys when the image's candidates fit
     __shared__ int s_scan[kNmsThreads];
     __shared__ int s_total, s_nkept;
@@ -235,7 +237,7 @@ int launch_nms(const float* pred, int B, int nc, int A, float conf, float iou, i
     SNN_CUDA_OK(once.run([] {
         return cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsSmemKeys * (int)sizeof(unsigned long long));
     }));
-    nms_kernel<<<B, kNmsThreads, kNmsSmemKeys * sizeof(unsigned long long), st>>>(p);
+    launch_pdl(nms_kernel, dim3(B), dim3(kNmsThreads), kNmsSmemKeys * sizeof(unsigned long long), st, p);
     return check_cuda(cudaGetLastError(), "nms_kernel");
 }
 
