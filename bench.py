@@ -340,6 +340,8 @@ def cupti_graph_accounting(replay_fn, trace, replays):
     if not evs:
         return None, "no CUDA kernel records from torch.profiler (CUPTI unavailable)"
     evs.sort(key=lambda e: e.time_range.start)
+    comm = comm_overlap(evs, replays)
+    evs = [e for e in evs if not e.name.startswith("nccl")]
     seq = [(name, work, sub, k == 0) for name, work in trace for k, sub in enumerate(EXPECT.get(name, []))]
     agg, shapes, other = {}, {}, {}
     j, total = 0, 0.0
@@ -372,7 +374,49 @@ def cupti_graph_accounting(replay_fn, trace, replays):
         other[evs[j].name[:80]] = other.get(evs[j].name[:80], 0.0) + d
         total += d
         j += 1
+    if comm:
+        other["__comm__"] = comm
     return (agg, shapes, other, total), None
+
+
+def comm_overlap(evs, replays):
+    """Timeline of the gradient exchange inside the replayed graph (N > 1): NCCL kernels by name, the time they are
+    resident, and how much of it no compute kernel overlaps (= exposed communication), per step.  From the same CUPTI
+    records as the kernel accounting (hardware timestamps), so it needs no separate profiler run."""
+    nccl = [(e.time_range.start, e.time_range.end, e.name) for e in evs if e.name.startswith("nccl")]
+    if not nccl:
+        return None
+    comp = sorted((e.time_range.start, e.time_range.end) for e in evs if not e.name.startswith("nccl"))
+
+    def union(iv):
+        out = []
+        for a, b in sorted(iv):
+            if out and a <= out[-1][1]:
+                out[-1][1] = max(out[-1][1], b)
+            else:
+                out.append([a, b])
+        return out
+    cu, nu = union(comp), union((a, b) for a, b, _ in nccl)
+    exposed, j = 0.0, 0
+    for a, b in nu:                      # NCCL time minus its intersection with compute time
+        covered = 0.0
+        while j < len(cu) and cu[j][1] <= a:
+            j += 1
+        k = j
+        while k < len(cu) and cu[k][0] < b:
+            covered += max(0.0, min(b, cu[k][1]) - max(a, cu[k][0]))
+            k += 1
+        exposed += (b - a) - covered
+    names = {}
+    for a, b, n in nccl:
+        d = names.setdefault(n[:90], [0, 0.0])
+        d[0] += 1
+        d[1] += (b - a) * 1e-3
+    return {"nccl_kernels": {n: {"launches_per_step": c / replays, "ms_per_step": round(ms / replays, 4)} for n, (c, ms) in names.items()},
+            "nccl_resident_ms_per_step": round(sum(b - a for a, b in nu) * 1e-3 / replays, 4),
+            "compute_busy_ms_per_step": round(sum(b - a for a, b in cu) * 1e-3 / replays, 4),
+            "exposed_comm_ms_per_step": round(exposed * 1e-3 / replays, 4),
+            "how": "CUPTI kernel records of the replayed step graph; exposed = NCCL-resident time with no compute kernel running"}
 
 
 def events_accounting(records):
@@ -484,13 +528,14 @@ def measure_config(args, cfg_idx, dev, rank, local, world, pk, full):
     # (done right after the timed region, before the e2e leg re-captures the graph for uint8 host frames)
     res = dict(B=B, T=T, HW=HW, value=world * B * args.steps / (ms_total * 1e-3), ms_per_step=ms_total / args.steps, e2e=None, clocks=None,
                launches=launches, last_loss=last_loss, lockstep=None, graphed=graphed, kernels=None, by_shape=None, roofline=None,
-               timing=None, kernel_ms_sum=None, other_kernels=None)
+               timing=None, kernel_ms_sum=None, other_kernels=None, comm_timeline=None)
     if full and not args.no_profile:
         acc, timing, kernel_sum, other = None, None, None, None
         if graphed:
             got, why = cupti_graph_accounting(lambda: trainer.train_step_graphed(frames, batch_dev), trace, 3)
             if got is not None:
                 agg, shapes, other_d, total = got
+                res["comm_timeline"] = other_d.pop("__comm__", None)
                 acc, timing, kernel_sum = (agg, shapes, 3), "CUPTI activity records of 3 extra replays of the captured graph, matched to the ABI calls in launch order", total / 3
                 other = {k: round(v / 3, 4) for k, v in sorted(other_d.items(), key=lambda kv: -kv[1])[:12]}
             else:
@@ -650,7 +695,7 @@ def run_ours(args):
         "dependent_launch": bool(_lib.lib().snn_get_dependent_launch()),
         "kernel_timing": main["timing"], "kernels": main["kernels"], "kernels_by_shape": main["by_shape"],
         "kernel_ms_sum_per_step": main["kernel_ms_sum"], "other_kernels_ms_per_step": main["other_kernels"],
-        "lif_microbench": lif, "last_loss_items": main["last_loss"],
+        "comm_timeline": main["comm_timeline"], "lif_microbench": lif, "last_loss_items": main["last_loss"],
     }
     print(json.dumps(line), flush=True)
     shutdown()

@@ -17,6 +17,7 @@ Two entry styles:
 `neuron='silu'` reproduces the reference network itself.
 """
 import math
+import os
 from types import SimpleNamespace
 
 import torch
@@ -202,6 +203,8 @@ class TemporalUNet(nn.Module):
         self.use_conv_lstm = use_conv_lstm
         nr = make_neuron(neuron)
         self.neuron = nr
+        # fan-out gradients (skips, decoder -> output conv) summed in the second dgrad's epilogue (ops.GradSlot); False = autograd adds
+        self.fuse_fanout_grads = os.environ.get("SNN_FUSE_FANOUT_GRADS", "1") != "0"
         self.enc1, self.down1 = ConvBlock(ch_p3, w1, neuron=nr), DownBlock(w1, w2, neuron=nr)
         self.enc2, self.down2 = ConvBlock(w2 + ch_p4, w2, neuron=nr), DownBlock(w2, w3, neuron=nr)
         self.enc3, self.down3 = ConvBlock(w3 + ch_p5, w3, neuron=nr), DownBlock(w3, w4, neuron=nr)
@@ -221,7 +224,7 @@ class TemporalUNet(nn.Module):
         # Tensors with two consumers (x1, x2, x3: next encoder stage + decoder skip; d1, d2: next decoder stage + output
         # conv): their two input gradients are summed in the second dgrad's epilogue (ops.GradSlot) instead of by an
         # autograd add kernel.  'first' = the consumer created later in forward = whose backward runs first.
-        fuse = torch.is_grad_enabled() and self.training
+        fuse = torch.is_grad_enabled() and self.training and self.fuse_fanout_grads
         s1, s2, s3, sd1, sd2 = (GradSlot() if fuse else None for _ in range(5))
         role = lambda s_, r_: None if s_ is None else (s_, r_)
         x1, nm["enc1"] = self.enc1.forward_seq(rc, p3, None, m.get("enc1"))

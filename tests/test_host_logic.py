@@ -288,3 +288,23 @@ def test_gradient_readiness_counts_every_use_of_a_parameter():
     assert ready == ["weight", "bias"]
     st.grad_done(lin.bias)                       # a use that was never announced (no_grad forward): fires immediately
     assert ready[-1] == "bias"
+
+
+def test_bench_comm_overlap_accounting():
+    """bench.comm_overlap: exposed communication = NCCL-resident time that no compute kernel overlaps."""
+    import bench
+
+    class _TR:
+        def __init__(self, a, b):
+            self.start, self.end = a, b
+
+    class _EV:
+        def __init__(self, n, a, b):
+            self.name, self.time_range = n, _TR(a, b)
+
+    evs = [_EV("snn::a", 0, 100), _EV("snn::b", 150, 200), _EV("ncclDevKernel_AllReduce_Sum_f32", 50, 180),
+           _EV("ncclDevKernel_AllReduce_Sum_f32", 300, 320)]
+    c = bench.comm_overlap(evs, 2)
+    assert c["exposed_comm_ms_per_step"] == pytest.approx(0.035) and c["nccl_resident_ms_per_step"] == pytest.approx(0.075)
+    assert c["nccl_kernels"]["ncclDevKernel_AllReduce_Sum_f32"]["launches_per_step"] == 1.0
+    assert bench.comm_overlap(evs[:2], 1) is None
