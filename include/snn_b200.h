@@ -32,7 +32,8 @@ int snn_version(void);
  *   4: force the wgrad K-split                                   5: cap on persistent CTAs (pairs)
  *   6: 1 = single-CTA kernels only, 2 = CTA pairs also for small-K convs
  *   7: (only in -DSNN_TIMING_KNOBS builds) bit 0 = producer skips the TMA loads, bit 1 = MMA issuer skips the MMAs
- *   8: 1 = T == 1 SiLU layers use the generic two-pass BN backward kernel */
+ *   8: 1 = T == 1 SiLU layers use the generic two-pass BN backward kernel
+ *   9: 1 = T == 16 uses the one-chunk two-pass BN backward kernel instead of the two-chunk one */
 void snn_debug_set(int key, int value);
 /* Tile scheduling of the persistent tensor-core kernels (process-wide, read at launch): 0 (default) = static walk
  * (tile = worker, worker + nworkers, ...), 1 = dynamic (first tile static, the rest from an atomic counter).  Dynamic is for

@@ -692,6 +692,206 @@ bn_act_bwd2_kernel(const float* __restrict__ y, const float* __restrict__ scale,
 }
 
 // ------------------------------------------------------------------------------------------
+// T == 16.  The one-chunk kernel above holds 16 steps of y, gs and u plus 4 x 16 accumulators per thread: 186 (reduce) / 165
+// (dx) registers -> one 256-thread block per SM and 3.6 / 4.0 TB/s (profiles/r2, LIF sweep).  Here a thread walks its 16
+// steps as TWO CHUNKS of 8: a forward-only scan of steps 0..7 yields the membrane entering t = 8; chunk 1 (t = 8..15) is
+// recomputed and scanned backward; then chunk 0 from v_init (its y read a second time: an L1/L2 hit, no DRAM traffic), the
+// surrogate state gv carried across the chunk boundary.  Per-step arithmetic is the same instruction sequence as above,
+// so spikes, gx and dy are the same bits; live state per thread halves -> two blocks per SM, each with 8-step loads in flight.
+// ------------------------------------------------------------------------------------------
+struct Bwd2Consts {
+    float2 kz2, nkzth2, one2, ka2, beta2;
+    float theta;
+};
+
+template <int ACT, bool REDUCE, int T0>
+SNN_DEVINL void bwd2_chunk8(const float2* __restrict__ yp, const uint32_t* __restrict__ gp, uint32_t* __restrict__ dp, size_t nt2,
+                            const float4* tA, const float4* tB, float2 v, float2& gv, float2 nbb, const Bwd2Consts& k,
+                            float4* acc /* REDUCE: this thread's [16] accumulator slots in shared memory, stride 256 */) {
+    constexpr int TC = 8;
+    float2 yv[TC];
+    uint32_t gr[TC];
+    yp += (size_t)T0 * nt2;           // running pointers: per-step 64-bit offsets would cost 3 x 16 registers
+    gp += (size_t)T0 * nt2;
+    dp += (size_t)(T0 + TC - 1) * nt2;
+#pragma unroll
+    for (int t = 0; t < TC; ++t) {
+        yv[t] = REDUCE ? __ldg(yp) : __ldcs(yp);
+        gr[t] = REDUCE ? __ldg(gp) : __ldcs(gp);
+        yp += nt2; gp += nt2;
+    }
+    float2 u[TC];
+#pragma unroll
+    for (int t = 0; t < TC; ++t) {
+        const float4 a = tA[T0 + t];
+        const float2 xm = __fmul2_rn(yv[t], f2(a.x, a.y));
+        const float2 x = f2(__fadd_rn(xm.x, a.z), __fadd_rn(xm.y, a.w));
+        if (!REDUCE) yv[t] = x;
+        if (ACT == ACT_LIF) {
+            const float2 um = __fmul2_rn(k.beta2, v);
+            const float2 uu = f2(__fadd_rn(um.x, x.x), __fadd_rn(um.y, x.y));
+            u[t] = uu;
+            v.x = (uu.x >= k.theta) ? 0.f : uu.x;
+            v.y = (uu.y >= k.theta) ? 0.f : uu.y;
+        } else {
+            u[t] = x;
+        }
+    }
+#pragma unroll
+    for (int t = TC - 1; t >= 0; --t) {
+        const float2 g = f2(bf16_lo(gr[t]), bf16_hi(gr[t]));
+        const float2 uu = u[t];
+        float2 gx;
+        if (ACT == ACT_LIF) {
+            const float2 z = __ffma2_rn(k.kz2, uu, k.nkzth2);
+            const float2 den = __ffma2_rn(z, z, k.one2);
+            const float2 sg = __fmul2_rn(k.ka2, f2(rcp_approx(den.x), rcp_approx(den.y)));
+            const float2 keep = f2((uu.x >= k.theta) ? 0.f : 1.f, (uu.y >= k.theta) ? 0.f : 1.f);
+            const float2 w = __ffma2_rn(f2(-uu.x, -uu.y), sg, keep);
+            gx = __ffma2_rn(g, sg, __fmul2_rn(gv, w));
+            gv = __fmul2_rn(k.beta2, gx);
+        } else {
+            const float2 e = f2(ex2_approx(-1.4426950408889634f * uu.x), ex2_approx(-1.4426950408889634f * uu.y));
+            const float2 d1 = __fadd2_rn(e, k.one2);
+            const float2 sgm = f2(rcp_approx(d1.x), rcp_approx(d1.y));
+            const float2 oms = __fadd2_rn(k.one2, f2(-sgm.x, -sgm.y));
+            gx = __fmul2_rn(g, __fmul2_rn(sgm, __ffma2_rn(uu, oms, k.one2)));
+        }
+        const float4 kb = tB[T0 + t];
+        if (REDUCE) {
+            float4 a4 = acc[(T0 + t) * 256];
+            const float2 s2 = __fadd2_rn(f2(a4.x, a4.y), gx);
+            const float2 d2 = __ffma2_rn(gx, __fadd2_rn(yv[t], f2(kb.x, kb.y)), f2(a4.z, a4.w));
+            acc[(T0 + t) * 256] = make_float4(s2.x, s2.y, d2.x, d2.y);
+        } else {
+            const float4 a = tA[T0 + t];
+            const float2 t1 = __ffma2_rn(f2(a.x, a.y), gx, f2(kb.x, kb.y));
+            const float2 d = __ffma2_rn(__fadd2_rn(yv[t], nbb), f2(kb.z, kb.w), t1);
+            *dp = pack_bf16x2(d.x, d.y);
+            dp -= nt2;
+        }
+    }
+}
+
+template <int ACT, bool REDUCE>
+__global__ void __launch_bounds__(256, 2)
+bn_act_bwd2_t16_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                       const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ beta_bn,
+                       const float* __restrict__ red_in, const float* __restrict__ v_init, const __nv_bfloat16* __restrict__ gs,
+                       const float* __restrict__ gv_final, __nv_bfloat16* __restrict__ dy_out, float* __restrict__ gv_init,
+                       float* __restrict__ red_out, float* dgamma, float* dbeta, int T_rt, int P, int C, int Cb, int pix_per_block,
+                       float beta, float theta, float alpha, float invP) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float4 shc4[];
+    constexpr int T = 16, PITCH = T | 1;
+    const int c_base = blockIdx.y * Cb;
+    const int tpp = Cb >> 1;
+    const int rows = 256 / tpp;
+    const int cg = threadIdx.x % tpp, row = threadIdx.x / tpp;
+    float4* tabA = shc4;
+    float4* tabB = shc4 + tpp * PITCH;
+    float* accum = reinterpret_cast<float*>(tabB + tpp * PITCH);
+    for (int i = threadIdx.x; i < T * tpp; i += 256) {
+        const int t = i / tpp, j = i % tpp, gc = t * C + c_base + 2 * j;
+        const float2 sc = *reinterpret_cast<const float2*>(scale + gc), sh = *reinterpret_cast<const float2*>(shift + gc);
+        tabA[j * PITCH + t] = make_float4(sc.x, sc.y, sh.x, sh.y);
+        if (REDUCE) {
+            const float2 m = *reinterpret_cast<const float2*>(mean + gc);
+            tabB[j * PITCH + t] = make_float4(-m.x, -m.y, 0.f, 0.f);
+        } else {
+            const float2 r0 = *reinterpret_cast<const float2*>(red_in + (t * 2 + 0) * C + c_base + 2 * j);
+            const float2 r1 = *reinterpret_cast<const float2*>(red_in + (t * 2 + 1) * C + c_base + 2 * j);
+            const float2 is = *reinterpret_cast<const float2*>(invstd + gc);
+            tabB[j * PITCH + t] = make_float4(-(sc.x * (r0.x * invP)), -(sc.y * (r0.y * invP)), -(r1.x * invP * is.x), -(r1.y * invP * is.y));
+        }
+    }
+    if (REDUCE) {
+        for (int i = threadIdx.x; i < T * 2 * Cb; i += 256) accum[i] = 0.f;
+    } else if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < Cb; c += 256) {
+            float dg = 0.f, db = 0.f;
+            for (int t = 0; t < T; ++t) { db += red_in[(t * 2 + 0) * C + c_base + c]; dg += red_in[(t * 2 + 1) * C + c_base + c]; }
+            if (dgamma) dgamma[c_base + c] += dg;
+            if (dbeta) dbeta[c_base + c] += db;
+        }
+    }
+    __syncthreads();
+    const float ka = 0.5f * alpha, kz = 1.5707963267948966f * alpha;
+    Bwd2Consts k;
+    k.kz2 = f2(kz, kz); k.nkzth2 = f2(-kz * theta, -kz * theta); k.one2 = f2(1.f, 1.f); k.ka2 = f2(ka, ka); k.beta2 = f2(beta, beta);
+    k.theta = theta;
+    const int C2 = C >> 1;
+    const size_t nt2 = (size_t)P * C2;
+    // REDUCE: the 4 x 16 running sums of a thread live in its own float4 slots of shared memory ([t][thread]: conflict-free
+    // LDS.128 / STS.128), not in 64 registers
+    float4* acc = reinterpret_cast<float4*>(accum + (size_t)T * 2 * Cb) + threadIdx.x;
+    if (REDUCE) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc[t * 256] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (row < rows) {
+        float2 nbb = f2(0.f, 0.f);
+        if (!REDUCE && beta_bn) {
+            const float2 b = *reinterpret_cast<const float2*>(beta_bn + c_base + 2 * cg);
+            nbb = f2(-b.x, -b.y);
+        }
+        const float4* tA = tabA + cg * PITCH;
+        const float4* tB = tabB + cg * PITCH;
+        const int xb = REDUCE ? (int)blockIdx.x : (int)(gridDim.x - 1 - blockIdx.x);
+        const int p0 = xb * pix_per_block, p1 = min(P, p0 + pix_per_block);
+        size_t e2 = (size_t)(p0 + row) * C2 + (c_base >> 1) + cg;
+        const size_t e2_step = (size_t)rows * C2;
+        for (int p = p0 + row; p < p1; p += rows, e2 += e2_step) {
+            const float2* yp = reinterpret_cast<const float2*>(y) + e2;
+            const uint32_t* gp = reinterpret_cast<const uint32_t*>(gs) + e2;
+            uint32_t* dp = reinterpret_cast<uint32_t*>(dy_out) + e2;
+            float2 v0 = f2(0.f, 0.f);
+            if (ACT == ACT_LIF && v_init) v0 = __ldg(reinterpret_cast<const float2*>(v_init) + e2);
+            float2 v8 = v0;
+            if (ACT == ACT_LIF) {
+                // forward only over t = 0..7: the membrane entering chunk 1 (default caching: chunk 0 reads these again)
+                float2 y0[8];
+#pragma unroll
+                { const float2* q = yp; for (int t = 0; t < 8; ++t) { y0[t] = __ldg(q); q += nt2; } }
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const float4 a = tA[t];
+                    const float2 xm = __fmul2_rn(y0[t], f2(a.x, a.y));
+                    const float2 x = f2(__fadd_rn(xm.x, a.z), __fadd_rn(xm.y, a.w));
+                    const float2 um = __fmul2_rn(k.beta2, v8);
+                    const float2 uu = f2(__fadd_rn(um.x, x.x), __fadd_rn(um.y, x.y));
+                    v8.x = (uu.x >= theta) ? 0.f : uu.x;
+                    v8.y = (uu.y >= theta) ? 0.f : uu.y;
+                }
+            }
+            float2 gv = f2(0.f, 0.f);
+            if (ACT == ACT_LIF && gv_final) gv = __ldg(reinterpret_cast<const float2*>(gv_final) + e2);
+            bwd2_chunk8<ACT, REDUCE, 8>(yp, gp, dp, nt2, tA, tB, v8, gv, nbb, k, acc);
+            bwd2_chunk8<ACT, REDUCE, 0>(yp, gp, dp, nt2, tA, tB, v0, gv, nbb, k, acc);
+            if (!REDUCE && ACT == ACT_LIF && gv_init) *(reinterpret_cast<float2*>(gv_init) + e2) = gv;
+        }
+        if (REDUCE) {
+            const int cl = cg * 2;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const float4 a4 = acc[t * 256];
+                atomicAdd(&accum[(t * 2 + 0) * Cb + cl], a4.x); atomicAdd(&accum[(t * 2 + 0) * Cb + cl + 1], a4.y);
+                atomicAdd(&accum[(t * 2 + 1) * Cb + cl], a4.z); atomicAdd(&accum[(t * 2 + 1) * Cb + cl + 1], a4.w);
+            }
+        }
+    }
+    if (REDUCE) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < T * Cb; i += 256) {
+            const int t = i / Cb, c = i % Cb;
+            atomicAdd(&red_out[(t * 2 + 0) * C + c_base + c], accum[(t * 2 + 0) * Cb + c]);
+            atomicAdd(&red_out[(t * 2 + 1) * C + c_base + c], accum[(t * 2 + 1) * Cb + c] * invstd[t * C + c_base + c]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // T == 1 SiLU layers (Detect head: only the last frame carries gradient): no scan, so the generic kernel would keep a
 // single 12-byte operand pair in flight per thread (1.4 TB/s measured).  Same two passes, four pixels per thread and
 // iteration.  Arithmetic identical to bn_act_bwd2_kernel<ACT_SILU, 1, ...>.
@@ -912,6 +1112,7 @@ int launch_bn_act_bwd(int act, int training, const float* y, const float* scale,
 #undef SNN_BWD
 }
 
+static int g_t16_chunked = 1; // 0: T == 16 uses the one-chunk kernel (A/B timing, snn_debug_set(9, 1))
 template <int ACT, int TMAX, bool REDUCE>
 static int launch_bwd2_t(const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                          const float* beta_bn, const float* red_in, const float* v_init, const __nv_bfloat16* gs,
@@ -919,21 +1120,24 @@ static int launch_bwd2_t(const float* y, const float* scale, const float* shift,
                          int T, int P, int C, float beta, float theta, float alpha, cudaStream_t st) {
     // bytes of shared memory per channel: two float4 tables per channel PAIR with pitch (TMAX|1), + REDUCE accumulators
     const int per_c = (TMAX | 1) * 16 + (REDUCE ? T * 8 : 0);
+    const bool chunked = TMAX == 16 && T == 16 && g_t16_chunked;
+    const size_t acc_slots = (chunked && REDUCE) ? (size_t)16 * 256 * 16 : 0;      // per-thread accumulator slots (t16 kernel)
     // channel range per block: largest C / 2^k (multiple of 4) whose tables fit in ~48 KB of shared memory
+    const size_t table_cap = acc_slots ? 40 * 1024 : 48 * 1024;                     // t16 reduce: 2 x (40 + 64) KB per SM
     int Cb = C;
-    while (((size_t)Cb * per_c > 48 * 1024 || Cb > 512) && Cb % 4 == 0) Cb >>= 1;
+    while (((size_t)Cb * per_c > table_cap || Cb > 512) && Cb % 4 == 0) Cb >>= 1;
     SNN_REQUIRE(C % Cb == 0 && Cb % 2 == 0 && Cb <= 512 && (size_t)Cb * per_c <= 200 * 1024,
                 "bn_act_bwd2: cannot tile C=%d (T=%d) into shared memory", C, T);
     const int rows = 256 / (Cb / 2);
     const int nyb = C / Cb;
-    const int occ = TMAX <= 4 ? 4 : (TMAX <= 8 ? 2 : 1);
+    const int occ = TMAX <= 4 ? 4 : ((TMAX <= 8 || chunked) ? 2 : 1);
     long long want_blocks = (long long)num_sms() * occ * (REDUCE ? 1 : 2) / nyb;    // REDUCE: one full wave; DX: two
     if (want_blocks < 1) want_blocks = 1;
     int ppb = (int)((P + want_blocks - 1) / want_blocks);
     const int min_ppb = rows * (REDUCE ? 8 : 2);
     if (ppb < min_ppb) ppb = min_ppb;
     ppb = ((ppb + rows - 1) / rows) * rows;
-    const size_t smem = (size_t)Cb * per_c;
+    const size_t smem = (size_t)Cb * per_c + acc_slots;
     dim3 grid((P + ppb - 1) / ppb, nyb);
 #define SNN_GO(EX)                                                                                                         \
     do {                                                                                                                   \
@@ -942,13 +1146,21 @@ static int launch_bwd2_t(const float* y, const float* scale, const float* shift,
         launch_pdl(kern, grid, dim3(256), smem, st, y, scale, shift, mean, invstd, beta_bn, red_in, v_init, gs, gv_final, dy, gv_init,   \
                                       red_out, dgamma, dbeta, T, P, C, Cb, ppb, beta, theta, alpha, 1.0f / (float)P);      \
     } while (0)
-    if (T == TMAX) SNN_GO(true); else SNN_GO(false);
+    if (chunked) {
+        auto kern = bn_act_bwd2_t16_kernel<ACT, REDUCE>;
+        if (smem > 48 * 1024) SNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        launch_pdl(kern, grid, dim3(256), smem, st, y, scale, shift, mean, invstd, beta_bn, red_in, v_init, gs, gv_final, dy, gv_init,
+                   red_out, dgamma, dbeta, T, P, C, Cb, ppb, beta, theta, alpha, 1.0f / (float)P);
+    } else if (T == TMAX) SNN_GO(true); else SNN_GO(false);
 #undef SNN_GO
     return check_cuda(cudaGetLastError(), REDUCE ? "bn_act_bwd2_kernel<reduce>" : "bn_act_bwd2_kernel<dx>");
 }
 
 static int g_t1_fast = 1;     // 0: T == 1 SiLU layers go through the generic kernel (A/B timing)
-void neuron_debug_set(int k, int v) { if (k == 0) g_t1_fast = v ? 0 : 1; }
+void neuron_debug_set(int k, int v) {
+    if (k == 0) g_t1_fast = v ? 0 : 1;
+    if (k == 1) g_t16_chunked = v ? 0 : 1;
+}
 
 // pass = 0: reduce (writes red [T][2][C], zeroed here); pass = 1: dx (reads red; writes dy, gv_init; dgamma/dbeta +=)
 int launch_bn_act_bwd2(int pass, int act, const float* y, const float* scale, const float* shift, const float* mean,

@@ -302,3 +302,39 @@ def test_silu_t1_fast_backward_equals_generic_kernel(B, H, W, C):
     (dy0, red0, dg0, db0), (dy1, red1, dg1, db1) = outs
     assert rel_err(red0, red1) < 1e-5 and rel_err(dg0, dg1) < 1e-5 and rel_err(db0, db1) < 1e-5
     assert rel_err(dy0, dy1) < 1e-4 and float((dy0 != dy1).float().mean()) < 1e-3
+
+
+@pytest.mark.parametrize("act", [LIF, SILU])
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 64), (3, 9, 5, 144), (1, 8, 8, 512), (2, 4, 4, 1024)])
+def test_t16_chunked_backward_equals_one_chunk_kernel(act, B, H, W, C):
+    """T == 16 walks the steps as two chunks of 8 (forward-only scan of steps 0..7 for the membrane entering t = 8, then
+    chunk 1 and chunk 0 backward with the surrogate state carried across): per-step arithmetic is the same instruction
+    sequence as the one-chunk kernel (snn_debug_set(9, 1)) -> gv_init bit-equal; the BN reductions differ by the fp32-atomic
+    order only (1e-5), hence dy (which reads them) by a handful of bf16 rounding flips."""
+    setup_exact()
+    K = _k()
+    from snn_object_detectionddp_b200 import _lib
+    T, P = 16, B * H * W
+    y, gamma, beta = _data(T, B, H, W, C, seed=23)
+    y = y + 0.4
+    gs = torch.randn(T * B, H, W, C, device="cuda").to(torch.bfloat16)
+    v0 = torch.rand(B, H, W, C, device="cuda") * 0.5 if act == LIF else None
+    gvf = torch.randn(B, H, W, C, device="cuda") if act == LIF else None
+    sums = K.bn_stats(y, T)
+    scale, shift, mean, invstd = K.bn_finalize(sums, gamma, beta, None, None, T, C, P, 1e-5, 0.1, True)
+    outs = []
+    try:
+        for one_chunk in (0, 1):
+            _lib.lib().snn_debug_set(9, one_chunk)
+            dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+            dy, gv0, red = K.bn_act_bwd_train(act, y, scale, shift, mean, invstd, beta, gs, T, dg, db, v_init=v0,
+                                              gv_final=None if gvf is None else gvf.reshape(-1), want_gv_init=act == LIF)
+            outs.append((dy.float(), red.clone(), dg, db, None if gv0 is None else gv0.clone()))
+    finally:
+        _lib.lib().snn_debug_set(9, 0)
+    (dy0, red0, dg0, db0, gv00), (dy1, red1, dg1, db1, gv01) = outs
+    assert rel_err(red0, red1) < 1e-5 and rel_err(dg0, dg1) < 1e-5 and rel_err(db0, db1) < 1e-5
+    assert rel_err(dy0, dy1) < 1e-4 and float((dy0 != dy1).float().mean()) < 1e-3
+    if act == LIF:
+        # gv_init = beta * gx[0] depends on gs, gv_final and the recomputed membranes only -- not on the reductions
+        assert torch.equal(gv00, gv01)
