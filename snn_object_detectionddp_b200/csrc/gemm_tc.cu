@@ -63,6 +63,11 @@ struct ConvGemmParams {
     unsigned int* sched;              // dynamic tile scheduler: {next tile - nworkers, finished workers}, both 0 at launch
     int ksplit;                       // K split over the tap segments (fp32 output, TMA reduce-add): fills the GPU on small-M convs
     int dbg;                          // -DSNN_TIMING_KNOBS builds only: bit 0 = producer skips the TMA loads, bit 1 = no MMA issue
+    // Row-strip mode (3x3 stride-1, ntap == 3): a segment is one COLUMN of the 3x3 stencil.  Its A operand is ONE box of
+    // bh + 2 rows (a_bytes); the three taps kh = 0..2 are views of it shifted by bw rows (a_tap_off bytes, a multiple of the
+    // 1024-byte swizzle atom), each with its own weight slice (b_bytes; weight tap = seg.wtap + tap * tap_wstep).  Operand
+    // bytes per flop drop by a third to a half -- these layers sit on the L2->SM fabric cap, not on the tensor pipe.
+    int ntap, a_bytes, a_tap_off, b_bytes, tap_wstep;
     Phase phase[4];
 };
 
@@ -223,11 +228,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             for (int j = 0; j < nsub; ++j) {
                                 const uint32_t c_s = a_s + (uint32_t)(j * p.chunk_bytes);
                                 tma_load_5d(c_s, tmA, fb, ca + 64 * j, cw, g.dhp, chh, n0);
-                                if (!p.b_mn) {
-                                    tma_load_3d(c_s + 16384u, &tmB, fb, cb + 64 * j, g.wtap, ncol0);
-                                } else {  // [64 K rows] x [64 N] boxes, one per 64 output columns
-                                    for (int nb = 0; nb < p.b_boxes; ++nb)
-                                        tma_load_3d(c_s + 16384u + (uint32_t)nb * 8192u, &tmB, fb, ncol0 + nb * 64, g.wtap, cb + 64 * j);
+                                for (int tp = 0; tp < p.ntap; ++tp) {
+                                    const uint32_t b_s = c_s + (uint32_t)(p.a_bytes + tp * p.b_bytes);
+                                    const int wt = g.wtap + tp * p.tap_wstep;
+                                    if (!p.b_mn) {
+                                        tma_load_3d(b_s, &tmB, fb, cb + 64 * j, wt, ncol0);
+                                    } else {  // [64 K rows] x [64 N] boxes, one per 64 output columns
+                                        for (int nb = 0; nb < p.b_boxes; ++nb)
+                                            tma_load_3d(b_s + (uint32_t)nb * 8192u, &tmB, fb, ncol0 + nb * 64, wt, cb + 64 * j);
+                                    }
                                 }
                             }
                         } else {
@@ -235,11 +244,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             for (int j = 0; j < nsub; ++j) {
                                 const uint32_t c_s = a_s + (uint32_t)(j * p.chunk_bytes);
                                 tma_load_5d_pair(c_s, tmA, fb, ca + 64 * j, cw, g.dhp, chh, n0);
-                                if (!p.b_mn) {
-                                    tma_load_3d_pair(c_s + 16384u, &tmB, fb, cb + 64 * j, g.wtap, ncol0);
-                                } else {
-                                    for (int nb = 0; nb < p.b_boxes; ++nb)
-                                        tma_load_3d_pair(c_s + 16384u + (uint32_t)nb * 8192u, &tmB, fb, ncol0 + nb * 64, g.wtap, cb + 64 * j);
+                                for (int tp = 0; tp < p.ntap; ++tp) {
+                                    const uint32_t b_s = c_s + (uint32_t)(p.a_bytes + tp * p.b_bytes);
+                                    const int wt = g.wtap + tp * p.tap_wstep;
+                                    if (!p.b_mn) {
+                                        tma_load_3d_pair(b_s, &tmB, fb, cb + 64 * j, wt, ncol0);
+                                    } else {
+                                        for (int nb = 0; nb < p.b_boxes; ++nb)
+                                            tma_load_3d_pair(b_s + (uint32_t)nb * 8192u, &tmB, fb, ncol0 + nb * 64, wt, cb + 64 * j);
+                                    }
                                 }
                             }
                         }
@@ -303,15 +316,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             if (!dbg_nomma) {
                                 for (int j = 0; j < nsub; ++j) {
                                     const uint32_t c_s = a_s + (uint32_t)(j * p.chunk_bytes);
-                                    const uint32_t a_lo = a_lo_c | ((c_s & 0x3FFFFu) >> 4);
-                                    const uint32_t b_lo = b_lo_c | (((c_s + 16384u) & 0x3FFFFu) >> 4);
+                                    for (int tp = 0; tp < p.ntap; ++tp) {       // row-strip mode: three row-shifted views of one A box
+                                        const uint32_t a_lo = a_lo_c | (((c_s + (uint32_t)(tp * p.a_tap_off)) & 0x3FFFFu) >> 4);
+                                        const uint32_t b_lo = b_lo_c | (((c_s + (uint32_t)(p.a_bytes + tp * p.b_bytes)) & 0x3FFFFu) >> 4);
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
-                                        const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + b_kstep * k);
-                                        const uint32_t accf = (k | j) ? 1u : (first ^ 1u);
-                                        if (PAIR) umma_bf16_pair(tacc, adesc, bdesc, idesc, accf);
-                                        else umma_bf16(tacc, adesc, bdesc, idesc, accf);
+                                        for (int k = 0; k < 4; ++k) {
+                                            const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
+                                            const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + b_kstep * k);
+                                            const uint32_t accf = (k | j | tp) ? 1u : (first ^ 1u);
+                                            if (PAIR) umma_bf16_pair(tacc, adesc, bdesc, idesc, accf);
+                                            else umma_bf16(tacc, adesc, bdesc, idesc, accf);
+                                        }
                                     }
                                 }
                             }
@@ -948,13 +963,13 @@ struct DebugFlag {
     std::atomic<int> v{0};
     operator int() const { return v.load(std::memory_order_relaxed); }
 };
-static DebugFlag g_debug_flags[8];
+static DebugFlag g_debug_flags[16];
 void neuron_debug_set(int k, int v);
 void debug_set(int k, int v) {
 #ifndef SNN_TIMING_KNOBS
     if (k == 7) return;
 #endif
-    if (k >= 0 && k < 8) g_debug_flags[k].v.store(v, std::memory_order_relaxed);
+    if ((k >= 0 && k < 8) || (k >= 12 && k < 16)) g_debug_flags[k].v.store(v, std::memory_order_relaxed);
     else if (k >= 8 && k < 12) neuron_debug_set(k - 8, v);
 }
 
@@ -988,6 +1003,28 @@ static int sched_counters(unsigned int** out) {
 static int make_w_map(CUtensorMap* m, const void* ptr, int wN, int wT, int wK, int box_n);
 struct WDesc { const void* ptr; int wN, wT, wK; };
 
+// CTA pairs need an even split of the B tile: K-major rows in multiples of 8 and N % 16 == 0 (cta_group::2),
+// MN-major 64-column boxes; g_debug_flags[6] == 1 forces the single-CTA kernel (tests / A-B timing)
+static bool pair_possible(const ConvGemmParams& p) {
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    if (m_tiles < 2 || g_debug_flags[6] == 1) return false;
+    return p.b_mn ? (p.BN % 128 == 0) : (p.BN % 16 == 0);
+}
+
+// Row-strip mode for a 3x3 stride-1 conv (see ConvGemmParams::ntap)?  Needs the 128-pixel box inside ONE image (bn == 1; the
+// three row-shifted views of a [bh + 2][bw] box are then contiguous 128-row ranges), bw a multiple of 8 (view shift = whole
+// 1024-byte swizzle atoms) and room for the deeper stages: >= 3 of them (knob 12 == 2: >= 2, which admits the 256-column
+// tiles); knob 12 == 1 turns the mode off.  Set domain, BN and b_mn before calling.
+static bool strip_mode_ok(const ConvGemmParams& p) {
+    if (g_debug_flags[12] == 1) return false;
+    if (p.bn != 1 || p.bw % 8 != 0 || p.Hd * p.Wd < 128) return false;
+    const int bn_cta = pair_possible(p) ? p.BN / 2 : p.BN;
+    const int b_bytes = p.b_mn ? ((bn_cta + 63) / 64) * 8192 : bn_cta * 128;
+    const int chunk = (p.bh + 2) * p.bw * 128 + 3 * b_bytes;
+    const int stages = (220 * 1024 - 4 * 2 * 4096) / chunk;          // epilogue staging of the TMA-store path taken out
+    return stages >= (g_debug_flags[12] == 2 ? 2 : 3);
+}
+
 static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const WDesc& wd, ConvGemmParams& p, cudaStream_t st) {
     static PerDeviceOnce once;
     SNN_CUDA_OK(once.run([] {
@@ -996,23 +1033,26 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
         return e;
     }));
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    // CTA pairs need an even split of the B tile: K-major rows in multiples of 8 and N % 16 == 0 (cta_group::2),
-    // MN-major 64-column boxes; g_debug_flags[6] == 1 forces the single-CTA kernel (tests / A-B timing)
-    bool pair = m_tiles >= 2 && g_debug_flags[6] != 1;
-    if (pair) pair = p.b_mn ? (p.BN % 128 == 0) : (p.BN % 16 == 0);
+    bool pair = pair_possible(p);
     // K chunks per work item: small-K convs (1x1, transposed) are bound by per-tile latencies, not by operand traffic:
     // single-CTA tiles (no cluster handshakes) and four epilogue staging tiles instead of two
     if (p.ksplit < 1) p.ksplit = 1;
+    const bool strip = p.ntap > 1;            // set by the caller after strip_mode_ok()
+    if (!strip) { p.ntap = 1; p.tap_wstep = 0; }
     int chunks_per_item = 0;
-    for (int i = 0; i < p.phase[0].nseg; ++i) chunks_per_item += p.phase[0].seg[i].nchunk;
+    for (int i = 0; i < p.phase[0].nseg; ++i) chunks_per_item += p.phase[0].seg[i].nchunk * p.ntap;
     chunks_per_item /= p.ksplit;
     const bool small_k = chunks_per_item <= 8;
     if (small_k && g_debug_flags[6] != 2) pair = false;
+    SNN_REQUIRE(!(strip && small_k), "conv_gemm: row-strip mode on a small-K conv");
     const int bn_cta = pair ? p.BN / 2 : p.BN;
     p.b_boxes = (bn_cta + 63) / 64;
-    p.chunk_bytes = p.b_mn ? 16384 + p.b_boxes * 8192 : 16384 + bn_cta * 128;
+    p.b_bytes = p.b_mn ? p.b_boxes * 8192 : bn_cta * 128;
+    p.a_bytes = strip ? (p.bh + 2) * p.bw * 128 : 16384;
+    p.a_tap_off = strip ? p.bw * 128 : 0;
+    p.chunk_bytes = p.a_bytes + p.ntap * p.b_bytes;
     // chunks per stage: keep >= ~512 MMA cycles behind every mbarrier round trip (N = 256: 1 chunk, 128: 2, <= 64: 4)
-    p.cps = small_k ? 1 : (p.BN > 128 ? 1 : (p.BN > 64 ? 2 : 4));
+    p.cps = (small_k || strip) ? 1 : (p.BN > 128 ? 1 : (p.BN > 64 ? 2 : 4));
     for (int ph = 0; ph < p.nphase && p.cps > 1; ++ph)          // ragged segments (e.g. 144 channels = 3 chunks) would leave
         for (int i = 0; i < p.phase[ph].nseg; ++i)               // half-empty stages behind: fall back to one chunk per stage
             while (p.cps > 1 && p.phase[ph].seg[i].nchunk % p.cps != 0) p.cps >>= 1;
@@ -1146,9 +1186,11 @@ int conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long long
     p.BN = pick_bn(Cout);
     p.n_store = Cout; p.wn_off = w_row_off;
     p.out = out; p.bias = bias; p.out_f32 = out_f32; p.accumulate = accumulate; p.out_ld = out_ld; p.out_coff = out_coff;
+    const bool strip = geom == GEOM_3x3_S1 && strip_mode_ok(p);
+    const int box_h = strip ? p.bh + 2 : p.bh;
     CUtensorMap a0, a1;
-    if (make_act_map(&a0, x0, NB, H, W, C0, ld0, phase_view, p.bn, p.bh, p.bw)) return 2;
-    if (x1) { if (make_act_map(&a1, x1, NB, H, W, C1, ld1, phase_view, p.bn, p.bh, p.bw)) return 2; } else a1 = a0;
+    if (make_act_map(&a0, x0, NB, H, W, C0, ld0, phase_view, p.bn, box_h, p.bw)) return 2;
+    if (x1) { if (make_act_map(&a1, x1, NB, H, W, C1, ld1, phase_view, p.bn, box_h, p.bw)) return 2; } else a1 = a0;
     const WDesc wd = {w, w_rows, taps, w_K};
     if (stats) {
         int gpt = 0;
@@ -1165,6 +1207,15 @@ int conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long long
                 ph.seg[ph.nseg++] = mkseg(0, 0, 0, 0, 0, a * 2 + bb, w_coff, C0);
                 if (x1) ph.seg[ph.nseg++] = mkseg(1, 0, 0, 0, 0, a * 2 + bb, w_coff + C0, C1);
             }
+    } else if (strip) {
+        // one segment per stencil column kw: box rows h0 - 1 .. h0 + bh, taps kh = 0..2 = weight taps kw, kw + 3, kw + 6
+        p.nphase = 1; p.ntap = 3; p.tap_wstep = 3;
+        Phase& ph = p.phase[0];
+        ph.nseg = 0;
+        for (int kw = 0; kw < 3; ++kw) {
+            ph.seg[ph.nseg++] = mkseg(0, 0, kw - 1, 0, -1, kw, w_coff, C0);
+            if (x1) ph.seg[ph.nseg++] = mkseg(1, 0, kw - 1, 0, -1, kw, w_coff + C0, C1);
+        }
     } else {
         p.nphase = 1;
         Phase& ph = p.phase[0];
@@ -1201,10 +1252,17 @@ int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long lo
     p.BN = pick_bn(Ci);
     p.n_store = Ci; p.wn_off = ci_off; p.b_mn = 1;
     p.out = dx; p.bias = nullptr; p.out_f32 = dx_f32; p.accumulate = accumulate; p.out_ld = dx_ld; p.out_coff = dx_coff;
+    const bool strip = geom == GEOM_3x3_S1 && strip_mode_ok(p);
     CUtensorMap a0;
-    if (make_act_map(&a0, dy, NB, Hy, Wy, Cout, ld_dy, phase_view, p.bn, p.bh, p.bw)) return 2;
+    if (make_act_map(&a0, dy, NB, Hy, Wy, Cout, ld_dy, phase_view, p.bn, strip ? p.bh + 2 : p.bh, p.bw)) return 2;
     const WDesc wd = {wt, Cout, taps, w_K};                  // box = 64 input channels x 1 tap x 64 output-channel rows
-    if (geom == GEOM_3x3_S1 || geom == GEOM_1x1) {
+    if (strip) {
+        // dx[h, w] = sum dy[h + 1 - kh, w + 1 - kw] * W[kh, kw]: column offset d = 1 - kw; box row r = 0..2 reads dy row
+        // h - 1 + r, i.e. kh = 2 - r -> weight taps (2 - r) * 3 + kw = 6 + kw, 3 + kw, kw
+        p.nphase = 1; p.ntap = 3; p.tap_wstep = -3;
+        Phase& ph = p.phase[0];
+        for (int kw = 0; kw < 3; ++kw) ph.seg[ph.nseg++] = mkseg(0, 0, 1 - kw, 0, -1, 6 + kw, 0, Cout);
+    } else if (geom == GEOM_3x3_S1 || geom == GEOM_1x1) {
         p.nphase = 1;
         Phase& ph = p.phase[0];
         const int k = geom == GEOM_1x1 ? 1 : 3;
@@ -1236,7 +1294,7 @@ int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long lo
     }
     // Small-M convs (ConvLSTM recurrent dgrad: 8 pixel tiles x 4 column blocks = 16 work items for 74 CTA pairs) split K
     // over the taps; the partial products meet in the fp32 output through TMA reduce-add (zero-filled first).
-    if (dx_f32 && !accumulate && p.nphase == 1 && dx_coff == 0 && dx_ld == Ci && g_debug_flags[0] != 1) {
+    if (dx_f32 && !accumulate && p.nphase == 1 && p.ntap <= 1 && dx_coff == 0 && dx_ld == Ci && g_debug_flags[0] != 1) {
         const int m_work = (p.tiles_w * p.tiles_h * p.tiles_n + 1) / 2;
         const int items = m_work * ((Ci + p.BN - 1) / p.BN);
         const int nseg = p.phase[0].nseg, pairs = num_sms() / 2;

@@ -20,3 +20,11 @@ try:
 except Exception as e:
     print("ERR", e)
 PY
+python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/$tag/bench_n$n.json").read().strip().splitlines()[-1])
+    print("comm", json.dumps(d.get("comm_timeline"), indent=1))
+except Exception as e:
+    print("ERR", e)
+PY
