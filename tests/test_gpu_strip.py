@@ -41,7 +41,7 @@ CASES = [
     # nb, h, w, c0, c1, cout
     (6, 32, 32, 128, 0, 128),      # enc / decoder 128-channel layers
     (5, 32, 32, 144, 0, 64),       # head cv2[0]: ragged K (144 = 2*64 + 16), N = 64
-    (3, 16, 16, 256, 144, 256),    # concat of two sources, 256-column tile (strip only with knob 12 = 2)
+    (3, 16, 16, 256, 144, 256),    # concat of two sources, 256-column tile (two 72 KB stages; tap-by-tap with knob 12 = 2)
     (4, 16, 16, 64, 0, 144),       # N = 144
     (2, 64, 64, 128, 0, 128),      # bw = 64, bh = 2
     (3, 12, 20, 128, 0, 128),      # non power-of-two map: partly out-of-bounds boxes
