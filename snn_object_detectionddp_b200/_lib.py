@@ -98,6 +98,10 @@ def lib():
         L.snn_tal_workspace_bytes.restype = _L
         L.snn_debug_set.argtypes = [_I, _I]
         L.snn_debug_set.restype = None
+        if "SNN_WGRAD_STRIP" in os.environ:        # A/B timing: 1 = tap-by-tap wgrad
+            L.snn_debug_set(13, int(os.environ["SNN_WGRAD_STRIP"]))
+        if "SNN_WGRAD_ROUNDS" in os.environ:
+            L.snn_debug_set(14, int(os.environ["SNN_WGRAD_ROUNDS"]))
         if "SNN_ROW_STRIP" in os.environ:          # A/B timing: 1 = row-strip mode off, 2 = not for 256-column tiles
             L.snn_debug_set(12, int(os.environ["SNN_ROW_STRIP"]))
         L.snn_set_tile_scheduling.argtypes = [_I]

@@ -91,6 +91,10 @@ struct WgradParams {
     int stages, stage_bytes;
     int lbo_bytes, sbo_bytes;         // MN-major descriptor strides
     int ntaps;
+    // Row-strip mode (3x3 stride-1): an item covers the three taps kh = 0..2 of ONE stencil column (taps[] holds the 3 columns).
+    // dY is staged once per 64-pixel step, X as a box of bh + 2 rows (x_box_bytes per 64 channels) whose row-shifted views
+    // (x_tap_off bytes apart) feed three accumulators of NT columns each (3 * NT <= 512 TMEM columns, single-buffered).
+    int strip, x_box_bytes, x_tap_off;
     unsigned int* sched;              // dynamic work-item scheduler counters (see SchedRing)
     WTap taps[9];
 };
@@ -585,6 +589,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     const int ny = p.n_ci_tiles * p.ntaps;
     const int total_items = p.m_items * ny * p.ksplit;        // item = (m, tap x cin tile, pixel range), m fastest
     const int nxb = (PAIR ? p.NT >> 1 : p.NT) >> 6;           // X boxes staged by this CTA
+    const uint32_t xbb = p.strip ? (uint32_t)p.x_box_bytes : kBox;    // bytes of one X box (64 channels)
+    const int ntp = p.strip ? 3 : 1;                          // taps (accumulators) per item
     const int tiles_hw = p.tiles_w * p.tiles_h;
 
     if (warp == 0) {
@@ -663,13 +669,13 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                         tma_load_5d(g_s, &tmG, fb, gc0, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
                         tma_load_5d(g_s + kBox, &tmG, fb, gc0 + 64, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
                         for (int b = 0; b < nxb; ++b)
-                            tma_load_5d(x_s + b * kBox, &tmX, fb, xc0 + b * 64, w0 + tp.x_dw, tp.x_dhp, h0 + tp.x_dh, n0);
+                            tma_load_5d(x_s + b * xbb, &tmX, fb, xc0 + b * 64, w0 + tp.x_dw, tp.x_dhp, h0 + tp.x_dh, n0);
                     } else {
                         if (rank == 0) mbar_expect_tx(fb, 2u * stage_bytes);
                         tma_load_5d_pair(g_s, &tmG, fb, gc0, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
                         tma_load_5d_pair(g_s + kBox, &tmG, fb, gc0 + 64, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
                         for (int b = 0; b < nxb; ++b)
-                            tma_load_5d_pair(x_s + b * kBox, &tmX, fb, xc0 + b * 64, w0 + tp.x_dw, tp.x_dhp, h0 + tp.x_dh, n0);
+                            tma_load_5d_pair(x_s + b * xbb, &tmX, fb, xc0 + b * 64, w0 + tp.x_dw, tp.x_dhp, h0 + tp.x_dh, n0);
                     }
                 }
                 g_s += stage_bytes;
@@ -695,6 +701,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, p.NT, 1, 1);
             const uint32_t desc_hi = ((uint32_t)p.sbo_bytes >> 4) | (1u << 14) | (2u << 29);
             const uint32_t lo_c = (((uint32_t)p.lbo_bytes >> 4) & 0x3FFFu) << 16;
+            const uint32_t lo_cb = p.strip ? ((((uint32_t)p.x_box_bytes >> 4) & 0x3FFFu) << 16) : lo_c;   // X: 64-channel blocks one box apart
             int s = 0, li = 0;
             uint32_t par = 0;
             uint32_t g_s = sbase;
@@ -704,8 +711,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 if (item < 0) break;
                 const int t_begin = (item / (p.m_items * ny)) * p.tiles_per_split;
                 const int total = min(p.total_tiles, t_begin + p.tiles_per_split) - t_begin;
-                const int acc = li & 1;
-                mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((li >> 1) & 1) ^ 1));
+                // strip mode: ONE accumulator set of 3 x NT columns (no double buffering: the K loops are long)
+                const int acc = p.strip ? 0 : (li & 1);
+                mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((p.strip ? li : (li >> 1)) & 1) ^ 1));
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(acc * kTmemCols);
                 for (int it = 0; it < total; ++it) {
@@ -713,13 +721,16 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                     tc_fence_after();
                     if (lead) {
                         const uint32_t a_lo = lo_c | ((g_s & 0x3FFFFu) >> 4);
-                        const uint32_t b_lo = lo_c | (((g_s + 2 * kBox) & 0x3FFFFu) >> 4);
+                        for (int t3 = 0; t3 < ntp; ++t3) {     // strip mode: three row-shifted views of the X box
+                            const uint32_t b_lo = lo_cb | (((g_s + 2 * kBox + (uint32_t)(t3 * p.x_tap_off)) & 0x3FFFFu) >> 4);
+                            const uint32_t tcol = tacc + (uint32_t)(t3 * p.NT);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {  // 16 pixels (rows of 128 B) per MMA
-                            const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (2048u >> 4) * k);
-                            const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (2048u >> 4) * k);
-                            if (PAIR) umma_bf16_pair(tacc, adesc, bdesc, idesc, k ? 1u : (uint32_t)(it != 0));
-                            else umma_bf16(tacc, adesc, bdesc, idesc, k ? 1u : (uint32_t)(it != 0));
+                            for (int k = 0; k < 4; ++k) {  // 16 pixels (rows of 128 B) per MMA
+                                const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (2048u >> 4) * k);
+                                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (2048u >> 4) * k);
+                                if (PAIR) umma_bf16_pair(tcol, adesc, bdesc, idesc, k ? 1u : (uint32_t)(it != 0));
+                                else umma_bf16(tcol, adesc, bdesc, idesc, k ? 1u : (uint32_t)(it != 0));
+                            }
                         }
                         if (PAIR) umma_commit_pair(smem_u32(&empty_bar[s])); else umma_commit(smem_u32(&empty_bar[s]));
                         if (it == total - 1) {
@@ -744,16 +755,17 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             const int co0 = (PAIR ? mi * 256 + (int)rank * 128 : mi * 128) + q * 32;
             const int wtap = p.taps[y / p.n_ci_tiles].wtap;
             const int ci0 = (y % p.n_ci_tiles) * p.NT;
-            const int acc = li & 1;
-            mbar_wait(smem_u32(&tmem_full_bar[acc]), (uint32_t)((li >> 1) & 1));
+            const int acc = p.strip ? 0 : (li & 1);
+            mbar_wait(smem_u32(&tmem_full_bar[acc]), (uint32_t)((p.strip ? li : (li >> 1)) & 1));
             tc_fence_after();
             const uint32_t trow = tmem_base + (uint32_t)(acc * kTmemCols) + ((uint32_t)(q * 32) << 16);
             const int nch = (min(p.NT, p.Ci - ci0) + 31) >> 5;
-            for (int cc = 0; cc < nch; ++cc, ++gcc) {
+            for (int c3 = 0; c3 < nch * ntp; ++c3, ++gcc) {
+                const int t3 = c3 / nch, cc = c3 - t3 * nch;           // strip mode: tap kh = t3 (weight tap + 3 * t3), accumulator t3
                 const uint32_t buf = stg0 + (gcc & 1u) * 4096u;
                 uint32_t r[32];
-                tmem_ld16(trow + (uint32_t)(cc * 32), r);
-                tmem_ld16(trow + (uint32_t)(cc * 32 + 16), r + 16);
+                tmem_ld16(trow + (uint32_t)(t3 * p.NT + cc * 32), r);
+                tmem_ld16(trow + (uint32_t)(t3 * p.NT + cc * 32 + 16), r + 16);
                 tmem_ld_wait();
                 if (gcc >= 2) {
                     if (lane == 0) bulk_wait_group_read<1>();
@@ -766,7 +778,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0 && co0 < p.Cout) {   // rows >= Cout / columns >= wK are clipped by the tensor map
-                    tma_reduce_add_3d(&tmW, buf, p.w_coff + ci0 + cc * 32, wtap, co0);
+                    tma_reduce_add_3d(&tmW, buf, p.w_coff + ci0 + cc * 32, wtap + 3 * t3, co0);
                     bulk_commit_group();
                 }
             }
@@ -1344,16 +1356,33 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
         p.n_ci_tiles = (Ci + p.NT - 1) / p.NT;
     }
     p.Cout = Cout; p.Ci = Ci; p.dw = dw; p.dw_ld = (long long)taps * w_K; p.wK = w_K; p.w_coff = w_coff;
+    // Row-strip mode (WgradParams::strip): 3x3 stride-1, the 64-pixel box inside one image, rows of >= 8 pixels, cin in tiles of
+    // 128 without padding (64 for a 64-channel input): dY is read once per stencil column instead of once per tap and X once
+    // per three taps -- 32 KB instead of 72 KB of operands per CTA and three taps of a 128-wide cin tile.  Knob 13 = 1: off.
+    p.strip = geom == GEOM_3x3_S1 && p.bn == 1 && p.bw % 8 == 0 && Hd * Wd >= 64 && (Ci % 128 == 0 || Ci == 64) && g_debug_flags[13] != 1;
+    if (p.strip) {
+        p.NT = Ci == 64 ? 64 : 128;
+        p.n_ci_tiles = (Ci + p.NT - 1) / p.NT;
+        p.x_box_bytes = (p.bh + 2) * p.bw * 128;
+        p.x_tap_off = p.bw * 128;
+    }
     const bool pair = Cout > 128 && p.NT % 128 == 0 && g_debug_flags[6] != 1;
-    p.stage_bytes = (2 + (pair ? p.NT / 2 : p.NT) / 64) * 8192;
+    p.stage_bytes = p.strip ? 2 * 8192 + ((pair ? p.NT / 2 : p.NT) / 64) * p.x_box_bytes : (2 + (pair ? p.NT / 2 : p.NT) / 64) * 8192;
     const int stage_extra = 4 * 8192;      // epilogue staging: 4 warps x 2 tiles of 32 x 32 fp32
     int stages = (smem_budget() - stage_extra) / p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
     p.lbo_bytes = 8192;     // MN-major operands: 64-channel blocks 8192 B apart, 8-row (pixel) groups 1024 B apart
     p.sbo_bytes = 1024;
-    p.ntaps = taps;
+    p.ntaps = p.strip ? 3 : taps;
     const int k = geom == GEOM_1x1 ? 1 : (geom == GEOM_T2x2_S2 ? 2 : 3);
+    if (p.strip) {
+        for (int kw = 0; kw < 3; ++kw) {          // one entry per stencil column: X box rows h0 - 1 .. h0 + bh, weight taps kw, kw + 3, kw + 6
+            WTap& t = p.taps[kw];
+            memset(&t, 0, sizeof(t));
+            t.wtap = kw; t.x_dw = kw - 1; t.x_dh = -1;
+        }
+    } else
     for (int kh = 0; kh < k; ++kh)
         for (int kw = 0; kw < k; ++kw) {
             WTap& t = p.taps[kh * k + kw];
@@ -1364,7 +1393,7 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
             if (geom == GEOM_T2x2_S2) { t.g_dhp = kh; t.g_dc = (int)(kw * ld_dy); }
         }
     p.m_items = pair ? (Cout + 255) / 256 : (Cout + 127) / 128;
-    const int base = p.m_items * p.n_ci_tiles * taps;             // work items before splitting K
+    const int base = p.m_items * p.n_ci_tiles * p.ntaps;          // work items before splitting K
     const int workers = pair ? num_sms() / 2 : num_sms();
     // split K (pixel tiles) so that the item count is just below one or two full rounds of the persistent workers; every
     // item keeps >= 16 pipeline stages when two rounds are used (more items = more reduce-add traffic into dW)
@@ -1372,6 +1401,8 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
     if (base < workers) {
         const int k2 = (2 * workers) / base, k1 = workers / base;
         ksplit = (k2 >= 1 && p.total_tiles / k2 >= 16) ? k2 : (k1 >= 1 ? k1 : 1);
+        // strip mode: the epilogue (3 accumulators, not overlapped with the next item's K loop) favours ONE round of long items
+        if (p.strip && k1 >= 1 && g_debug_flags[14] != 1) ksplit = k1;
     }
     const int max_split = (p.total_tiles + 3) / 4;  // >= 4 pixel tiles per item
     if (ksplit > max_split) ksplit = max_split;
@@ -1381,7 +1412,7 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
     p.ksplit = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
     CUtensorMap mg, mx, mw;
     if (make_act_map(&mg, dy, NB, Hy, Wy, Cout, ld_dy, g_phase, p.bn, p.bh, p.bw)) return 2;
-    if (make_act_map(&mx, x, NB, H, W, Ci, ld_x, x_phase, p.bn, p.bh, p.bw)) return 2;
+    if (make_act_map(&mx, x, NB, H, W, Ci, ld_x, x_phase, p.bn, p.strip ? p.bh + 2 : p.bh, p.bw)) return 2;
     {   // dW fp32 [Cout][taps][w_K] -> 3-D reduce-add map (k, tap, n), box 32 x 1 x 32
         if (get_encode()) return 2;
         SNN_REQUIRE(((uintptr_t)dw & 15) == 0, "conv_wgrad: dw must be 16-byte aligned");

@@ -33,7 +33,7 @@ def knobs():
     from snn_object_detectionddp_b200 import _lib
     L = _lib.lib()
     yield L
-    for k in (5, 6, 12):
+    for k in (4, 5, 6, 12, 13):
         L.snn_debug_set(k, 0)
 
 
@@ -111,3 +111,62 @@ def test_dgrad_strip_mode(knobs, nb, h, w, cin, cout, single, cap):
         ob = K.conv_dgrad(G31, dy, wgt, (h, w), cin)
         assert rel_err(ob, ref) < 4e-3, mode
     assert rel_err(outs[0], outs[1]) < 1e-5 and rel_err(outs[2], outs[1]) < 1e-5
+
+
+WGRAD_CASES = [
+    # nb, h, w, cin, cout
+    (8, 32, 32, 128, 128),     # single-CTA (Cout <= 128), two X boxes per stage
+    (6, 16, 16, 256, 256),     # CTA pair, two cin tiles
+    (8, 8, 8, 512, 512),       # 8x8 maps: box = one whole image, bw = 8
+    (4, 32, 32, 256, 128),     # decoder conv on the concatenated input's first source
+    (3, 16, 16, 64, 144),      # 64-channel input: NT = 64; Cout = 144 (pair with a ragged second CTA)
+    (2, 64, 64, 128, 256),     # bw = 64, bh = 1
+    (5, 12, 20, 128, 128),     # non power-of-two map
+    (4, 16, 16, 144, 128),     # cin not a multiple of 128: stays tap-by-tap (same result either way)
+]
+
+
+@pytest.mark.parametrize("nb,h,w,cin,cout", WGRAD_CASES)
+@pytest.mark.parametrize("single,cap,ks", [(0, 0, 0), (1, 0, 0), (0, 3, 0), (0, 0, 5)])
+def test_wgrad_strip_mode(knobs, nb, h, w, cin, cout, single, cap, ks):
+    """dW of one stencil column (three taps) per work item from ONE staged dY tile and the row-shifted views of one X box.
+    Same products as the tap-by-tap kernel; fp32 sums differ by the split-K order only (2e-5 vs torch fp32, 1e-5 between the
+    two modes); accumulating twice doubles the result."""
+    setup_exact()
+    K = _k()
+    wgt = _mkw(cout, cin, 13).float().requires_grad_(True)
+    x = _mk(nb, h, w, cin, 14, spikes=(cin % 128 == 0))
+    y = ref_conv(G31, x, wgt)
+    dy = torch.randn(y.shape, device="cuda").to(torch.bfloat16)
+    (gw_ref,) = torch.autograd.grad(y, wgt, dy.float())
+    knobs.snn_debug_set(6, single)
+    knobs.snn_debug_set(5, cap)
+    knobs.snn_debug_set(4, ks)
+    outs = {}
+    try:
+        for off in (1, 0):
+            knobs.snn_debug_set(13, off)
+            dw = torch.zeros(cout, 9, cin, device="cuda")
+            K.conv_wgrad(G31, x, dy, dw)
+            assert rel_err(dw, gw_ref) < 2e-5, (off, describe_mismatch(dw, gw_ref))
+            outs[off] = dw.clone()
+            K.conv_wgrad(G31, x, dy, dw)
+            assert rel_err(dw, 2 * gw_ref) < 2e-5, off
+    finally:
+        knobs.snn_debug_set(13, 0)
+        knobs.snn_debug_set(4, 0)
+    assert rel_err(outs[0], outs[1]) < 1e-5
+
+
+def test_wgrad_strip_mode_into_channel_offset(knobs):
+    """Second source of a concatenated input: gradient lands at its channel offset of the weight, nothing else is touched."""
+    setup_exact()
+    K = _k()
+    x = _mk(3, 16, 16, 128, 15)
+    dy = _mk(3, 16, 16, 256, 16)
+    dw = torch.zeros(256, 9, 384, device="cuda")
+    K.conv_wgrad(G31, x, dy, dw, w_coff=256)
+    w0 = torch.zeros(256, 9, 128, device="cuda", requires_grad=True)
+    (ref,) = torch.autograd.grad(ref_conv(G31, x, w0), w0, dy.float())
+    assert rel_err(dw[:, :, 256:], ref) < 2e-5
+    assert float(dw[:, :, :256].abs().max()) == 0
