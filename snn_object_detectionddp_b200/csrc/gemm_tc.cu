@@ -68,6 +68,8 @@ struct ConvGemmParams {
     // 1024-byte swizzle atom), each with its own weight slice (b_bytes; weight tap = seg.wtap + tap * tap_wstep).  Operand
     // bytes per flop drop by a third to a half -- these layers sit on the L2->SM fabric cap, not on the tensor pipe.
     int ntap, a_bytes, a_tap_off, b_bytes, tap_wstep;
+    int hnw;                          // rows of a pixel box ordered (h, n, w) instead of (n, h, w): tensor maps with the image
+                                      // dimension BELOW h, so a one-row shift is bn * bw rows also when a box spans bn > 1 images
     Phase phase[4];
 };
 
@@ -95,6 +97,7 @@ struct WgradParams {
     // dY is staged once per 64-pixel step, X as a box of bh + 2 rows (x_box_bytes per 64 channels) whose row-shifted views
     // (x_tap_off bytes apart) feed three accumulators of NT columns each (3 * NT <= 512 TMEM columns, single-buffered).
     int strip, x_box_bytes, x_tap_off;
+    int hnw;                          // pixel boxes ordered (h, n, w): see ConvGemmParams::hnw
     unsigned int* sched;              // dynamic work-item scheduler counters (see SchedRing)
     WTap taps[9];
 };
@@ -231,7 +234,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             mbar_expect_tx(fb, (uint32_t)(nsub * p.chunk_bytes));
                             for (int j = 0; j < nsub; ++j) {
                                 const uint32_t c_s = a_s + (uint32_t)(j * p.chunk_bytes);
-                                tma_load_5d(c_s, tmA, fb, ca + 64 * j, cw, g.dhp, chh, n0);
+                                tma_load_5d(c_s, tmA, fb, ca + 64 * j, cw, g.dhp, p.hnw ? n0 : chh, p.hnw ? chh : n0);
                                 for (int tp = 0; tp < p.ntap; ++tp) {
                                     const uint32_t b_s = c_s + (uint32_t)(p.a_bytes + tp * p.b_bytes);
                                     const int wt = g.wtap + tp * p.tap_wstep;
@@ -247,7 +250,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             if (rank == 0) mbar_expect_tx(fb, 2u * (uint32_t)(nsub * p.chunk_bytes));   // both CTAs' bytes land on the leader's barrier
                             for (int j = 0; j < nsub; ++j) {
                                 const uint32_t c_s = a_s + (uint32_t)(j * p.chunk_bytes);
-                                tma_load_5d_pair(c_s, tmA, fb, ca + 64 * j, cw, g.dhp, chh, n0);
+                                tma_load_5d_pair(c_s, tmA, fb, ca + 64 * j, cw, g.dhp, p.hnw ? n0 : chh, p.hnw ? chh : n0);
                                 for (int tp = 0; tp < p.ntap; ++tp) {
                                     const uint32_t b_s = c_s + (uint32_t)(p.a_bytes + tp * p.b_bytes);
                                     const int wt = g.wtap + tp * p.tap_wstep;
@@ -355,7 +358,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int q = warp & 3;
         const int grp = warp >= 6 ? 1 : 0, ngrp = p.epi_groups;
         const int row = q * 32 + lane;
-        const int wl = row % p.bw, hl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
+        const int wl = row % p.bw;
+        const int hl = p.hnw ? row / (p.bw * p.bn) : (row / p.bw) % p.bh, nl = p.hnw ? (row / p.bw) % p.bn : row / (p.bw * p.bh);
         int lt = 0;
         uint32_t gcc = 0;     // staging-tile counter across all tiles of this warp: nbuf buffers in rotation
         const bool dyn = p.sched != nullptr;
@@ -382,7 +386,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const int chs = p.out_f32 ? 5 : 6;
                 const int row0 = q * 32;
                 const int bw_ = p.bw, bh_ = p.bh;
-                const int cw = tw * bw_ + row0 % bw_, chh = th * bh_ + (row0 / bw_) % bh_, cn = tn * p.bn + row0 / (bw_ * bh_);
+                const int cw = tw * bw_ + row0 % bw_;
+                const int chh = th * bh_ + (p.hnw ? row0 / (bw_ * p.bn) : (row0 / bw_) % bh_);
+                const int cn = tn * p.bn + (p.hnw ? (row0 / bw_) % p.bn : row0 / (bw_ * bh_));
+                const int c3 = p.hnw ? cn : chh, c4 = p.hnw ? chh : cn;       // tensor-map coordinates 3 and 4
                 const int cbase = (p.os == 2 ? ph.opw * (int)p.out_ld : 0);
                 const int cph = (p.os == 2 ? ph.oph : 0);
                 const uint32_t stg0 = sbase + (uint32_t)stages * stage_bytes + (uint32_t)((grp * 4 + q) * p.nbuf) * 4096u;
@@ -468,8 +475,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         }
                     }
                     if (lane == 0) {
-                        if (p.accumulate) tma_reduce_add_5d(&tmO, buf, cbase + ncol0 + cc * CH, cw, cph, chh, cn);
-                        else tma_store_5d(&tmO, buf, cbase + ncol0 + cc * CH, cw, cph, chh, cn);
+                        if (p.accumulate) tma_reduce_add_5d(&tmO, buf, cbase + ncol0 + cc * CH, cw, cph, c3, c4);
+                        else tma_store_5d(&tmO, buf, cbase + ncol0 + cc * CH, cw, cph, c3, c4);
                         bulk_commit_group();
                     }
                 }
@@ -666,16 +673,16 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                     const uint32_t x_s = g_s + 2 * kBox;
                     if (!PAIR) {
                         mbar_expect_tx(fb, stage_bytes);
-                        tma_load_5d(g_s, &tmG, fb, gc0, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
-                        tma_load_5d(g_s + kBox, &tmG, fb, gc0 + 64, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
+                        tma_load_5d(g_s, &tmG, fb, gc0, w0 + tp.g_dw, tp.g_dhp, p.hnw ? n0 : h0 + tp.g_dh, p.hnw ? h0 + tp.g_dh : n0);
+                        tma_load_5d(g_s + kBox, &tmG, fb, gc0 + 64, w0 + tp.g_dw, tp.g_dhp, p.hnw ? n0 : h0 + tp.g_dh, p.hnw ? h0 + tp.g_dh : n0);
                         for (int b = 0; b < nxb; ++b)
-                            tma_load_5d(x_s + b * xbb, &tmX, fb, xc0 + b * 64, w0 + tp.x_dw, tp.x_dhp, h0 + tp.x_dh, n0);
+                            tma_load_5d(x_s + b * xbb, &tmX, fb, xc0 + b * 64, w0 + tp.x_dw, tp.x_dhp, p.hnw ? n0 : h0 + tp.x_dh, p.hnw ? h0 + tp.x_dh : n0);
                     } else {
                         if (rank == 0) mbar_expect_tx(fb, 2u * stage_bytes);
-                        tma_load_5d_pair(g_s, &tmG, fb, gc0, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
-                        tma_load_5d_pair(g_s + kBox, &tmG, fb, gc0 + 64, w0 + tp.g_dw, tp.g_dhp, h0 + tp.g_dh, n0);
+                        tma_load_5d_pair(g_s, &tmG, fb, gc0, w0 + tp.g_dw, tp.g_dhp, p.hnw ? n0 : h0 + tp.g_dh, p.hnw ? h0 + tp.g_dh : n0);
+                        tma_load_5d_pair(g_s + kBox, &tmG, fb, gc0 + 64, w0 + tp.g_dw, tp.g_dhp, p.hnw ? n0 : h0 + tp.g_dh, p.hnw ? h0 + tp.g_dh : n0);
                         for (int b = 0; b < nxb; ++b)
-                            tma_load_5d_pair(x_s + b * xbb, &tmX, fb, xc0 + b * 64, w0 + tp.x_dw, tp.x_dhp, h0 + tp.x_dh, n0);
+                            tma_load_5d_pair(x_s + b * xbb, &tmX, fb, xc0 + b * 64, w0 + tp.x_dw, tp.x_dhp, p.hnw ? n0 : h0 + tp.x_dh, p.hnw ? h0 + tp.x_dh : n0);
                     }
                 }
                 g_s += stage_bytes;
@@ -881,18 +888,26 @@ static int get_encode() {
 // NHWC bf16 activation view -> 5-D map (c, w, row-phase, h, n).
 //   plain : tensor (NB, H, W, C) with pixel stride ld           -> dims (C, W, 1, H, NB)
 //   phase : same memory seen as (NB, H/2, 2, W/2, [2 pixels])   -> dims (ld + C, W/2, 2, H/2, NB)
+//   hnw   : (plain only) dimensions 3 and 4 swapped -> (C, W, 1, NB, H): a box lands in shared memory ordered (h, n, w)
 static int make_act_map(CUtensorMap* m, const void* ptr, int NB, int H, int W, int C, long long ld, int phase_view,
-                        int box_n, int box_h, int box_w) {
+                        int box_n, int box_h, int box_w, int hnw = 0) {
     if (get_encode()) return 2;
     SNN_REQUIRE(((uintptr_t)ptr & 15) == 0, "activation pointer must be 16-byte aligned");
     SNN_REQUIRE(ld % 8 == 0 && C % 8 == 0, "activation channels/stride must be multiples of 8 (C=%d ld=%lld)", C, ld);
     cuuint64_t dims[5], strides[4];
     cuuint32_t box[5] = {64, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, (cuuint32_t)box_n}, es[5] = {1, 1, 1, 1, 1};
-    if (!phase_view) {
+    if (!phase_view && hnw) {
+        // strides[i] = byte stride of dimension i + 1: row-phase (size 1), then n, then h
+        dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = NB; dims[4] = H;
+        strides[0] = ld * 2; strides[1] = (cuuint64_t)W * ld * 2; strides[2] = (cuuint64_t)H * W * ld * 2;
+        strides[3] = (cuuint64_t)W * ld * 2;
+        box[3] = (cuuint32_t)box_n; box[4] = (cuuint32_t)box_h;
+    } else if (!phase_view) {
         dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = NB;
         strides[0] = ld * 2; strides[1] = (cuuint64_t)W * ld * 2; strides[2] = (cuuint64_t)W * ld * 2;
         strides[3] = (cuuint64_t)H * W * ld * 2;
     } else {
+        SNN_REQUIRE(!hnw, "make_act_map: (h, n, w) order is for plain views only");
         SNN_REQUIRE(H % 2 == 0 && W % 2 == 0, "stride-2 / transposed conv needs even H, W (got %dx%d)", H, W);
         SNN_REQUIRE(C % 64 == 0, "stride-2 / transposed conv needs C %% 64 == 0 (got %d)", C);
         dims[0] = ld + C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = NB;
@@ -926,12 +941,17 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int wN, int wT, int wK, i
 // 32 rows x 128 bytes.  os == 2 (transposed conv / stride-2 dgrad): the phase view of make_act_map, the store's channel
 // coordinate selects the column phase.
 static int make_out_map(CUtensorMap* m, void* ptr, int f32, int NB, int Ho, int Wo, int n_store, long long ld, int os,
-                        int sbw, int sbh, int sbn) {
+                        int sbw, int sbh, int sbn, int hnw = 0) {
     if (get_encode()) return 2;
     const cuuint64_t es = f32 ? 4 : 2;
     cuuint64_t dims[5], strides[4];
     cuuint32_t box[5] = {(cuuint32_t)(f32 ? 32 : 64), (cuuint32_t)sbw, 1, (cuuint32_t)sbh, (cuuint32_t)sbn}, est[5] = {1, 1, 1, 1, 1};
-    if (os == 1) {
+    if (os == 1 && hnw) {
+        dims[0] = n_store; dims[1] = Wo; dims[2] = 1; dims[3] = NB; dims[4] = Ho;
+        strides[0] = ld * es; strides[1] = (cuuint64_t)Wo * ld * es; strides[2] = (cuuint64_t)Ho * Wo * ld * es;
+        strides[3] = (cuuint64_t)Wo * ld * es;
+        box[3] = (cuuint32_t)sbn; box[4] = (cuuint32_t)sbh;
+    } else if (os == 1) {
         dims[0] = n_store; dims[1] = Wo; dims[2] = 1; dims[3] = Ho; dims[4] = NB;
         strides[0] = ld * es; strides[1] = (cuuint64_t)Wo * ld * es; strides[2] = (cuuint64_t)Wo * ld * es;
         strides[3] = (cuuint64_t)Ho * Wo * ld * es;
@@ -1023,17 +1043,19 @@ static bool pair_possible(const ConvGemmParams& p) {
     return p.b_mn ? (p.BN % 128 == 0) : (p.BN % 16 == 0);
 }
 
-// Row-strip mode for a 3x3 stride-1 conv (see ConvGemmParams::ntap)?  Needs the 128-pixel box inside ONE image (bn == 1; the
-// three row-shifted views of a [bh + 2][bw] box are then contiguous 128-row ranges), bw a multiple of 8 (view shift = whole
-// 1024-byte swizzle atoms) and room for >= 2 of the deeper stages (knob 12 == 2: >= 3, which leaves the 256-column tiles
+// Row-strip mode for a 3x3 stride-1 conv (see ConvGemmParams::ntap)?  The box is staged with its rows ordered (h, n, w)
+// (ConvGemmParams::hnw), so the three views of a [bh + 2][bn][bw] box shifted by one image row are contiguous 128-row
+// ranges bn * bw rows apart also when a box spans several images (8x8 and 4x4 maps); needs bn * bw to be a multiple of 8
+// (view shift = whole 1024-byte swizzle atoms) and room for >= 2 of the deeper stages (knob 12 == 2: >= 3, which leaves the 256-column tiles
 // tap-by-tap; measured 0.8 % slower per step, profiles/README.md); knob 12 == 1 turns the mode off.  Set domain, BN and b_mn
 // before calling.
 static bool strip_mode_ok(const ConvGemmParams& p) {
     if (g_debug_flags[12] == 1) return false;
-    if (p.bn != 1 || p.bw % 8 != 0 || p.Hd * p.Wd < 128) return false;
+    if ((p.bn * p.bw) % 8 != 0) return false;
+    if (g_debug_flags[12] == 3 && p.bn != 1) return false;          // A/B timing: only boxes inside one image
     const int bn_cta = pair_possible(p) ? p.BN / 2 : p.BN;
     const int b_bytes = p.b_mn ? ((bn_cta + 63) / 64) * 8192 : bn_cta * 128;
-    const int chunk = (p.bh + 2) * p.bw * 128 + 3 * b_bytes;
+    const int chunk = (p.bh + 2) * p.bn * p.bw * 128 + 3 * b_bytes;
     const int stages = (220 * 1024 - 4 * 2 * 4096) / chunk;          // epilogue staging of the TMA-store path taken out
     return stages >= (g_debug_flags[12] == 2 ? 3 : 2);
 }
@@ -1061,8 +1083,9 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     const int bn_cta = pair ? p.BN / 2 : p.BN;
     p.b_boxes = (bn_cta + 63) / 64;
     p.b_bytes = p.b_mn ? p.b_boxes * 8192 : bn_cta * 128;
-    p.a_bytes = strip ? (p.bh + 2) * p.bw * 128 : 16384;
-    p.a_tap_off = strip ? p.bw * 128 : 0;
+    p.a_bytes = strip ? (p.bh + 2) * p.bn * p.bw * 128 : 16384;
+    p.a_tap_off = strip ? p.bn * p.bw * 128 : 0;
+    p.hnw = strip ? 1 : 0;
     p.chunk_bytes = p.a_bytes + p.ntap * p.b_bytes;
     // chunks per stage: keep >= ~512 MMA cycles behind every mbarrier round trip (N = 256: 1 chunk, 128: 2, <= 64: 4)
     p.cps = (small_k || strip) ? 1 : (p.BN > 128 ? 1 : (p.BN > 64 ? 2 : 4));
@@ -1098,8 +1121,12 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
     CUtensorMap b, o;
     if (make_w_map(&b, wd.ptr, wd.wN, wd.wT, wd.wK, p.b_mn ? 64 : bn_cta)) return 2;
     if (p.tma_out) {
-        const int sbw = p.bw >= 32 ? 32 : p.bw, sbh = (32 / sbw) < p.bh ? (32 / sbw) : p.bh, sbn = 32 / (sbw * sbh);
-        if (make_out_map(&o, obase, p.out_f32, p.NB, p.Ho, p.Wo, p.n_store, p.out_ld, p.os, sbw, sbh, sbn)) return 2;
+        // one epilogue warp's 32 rows as a box: (n, h, w) order fills w, then h, then n; (h, n, w) order w, then n, then h
+        const int sbw = p.bw >= 32 ? 32 : p.bw;
+        int sbh, sbn;
+        if (p.hnw) { sbn = (32 / sbw) < p.bn ? (32 / sbw) : p.bn; sbh = 32 / (sbw * sbn); }
+        else { sbh = (32 / sbw) < p.bh ? (32 / sbw) : p.bh; sbn = 32 / (sbw * sbh); }
+        if (make_out_map(&o, obase, p.out_f32, p.NB, p.Ho, p.Wo, p.n_store, p.out_ld, p.os, sbw, sbh, sbn, p.hnw)) return 2;
     } else {
         o = b;
     }
@@ -1202,8 +1229,8 @@ int conv_fprop(int geom, int NB, int H, int W, const void* x0, int C0, long long
     const bool strip = geom == GEOM_3x3_S1 && strip_mode_ok(p);
     const int box_h = strip ? p.bh + 2 : p.bh;
     CUtensorMap a0, a1;
-    if (make_act_map(&a0, x0, NB, H, W, C0, ld0, phase_view, p.bn, box_h, p.bw)) return 2;
-    if (x1) { if (make_act_map(&a1, x1, NB, H, W, C1, ld1, phase_view, p.bn, box_h, p.bw)) return 2; } else a1 = a0;
+    if (make_act_map(&a0, x0, NB, H, W, C0, ld0, phase_view, p.bn, box_h, p.bw, strip)) return 2;
+    if (x1) { if (make_act_map(&a1, x1, NB, H, W, C1, ld1, phase_view, p.bn, box_h, p.bw, strip)) return 2; } else a1 = a0;
     const WDesc wd = {w, w_rows, taps, w_K};
     if (stats) {
         int gpt = 0;
@@ -1267,7 +1294,7 @@ int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long lo
     p.out = dx; p.bias = nullptr; p.out_f32 = dx_f32; p.accumulate = accumulate; p.out_ld = dx_ld; p.out_coff = dx_coff;
     const bool strip = geom == GEOM_3x3_S1 && strip_mode_ok(p);
     CUtensorMap a0;
-    if (make_act_map(&a0, dy, NB, Hy, Wy, Cout, ld_dy, phase_view, p.bn, strip ? p.bh + 2 : p.bh, p.bw)) return 2;
+    if (make_act_map(&a0, dy, NB, Hy, Wy, Cout, ld_dy, phase_view, p.bn, strip ? p.bh + 2 : p.bh, p.bw, strip)) return 2;
     const WDesc wd = {wt, Cout, taps, w_K};                  // box = 64 input channels x 1 tap x 64 output-channel rows
     if (strip) {
         // dx[h, w] = sum dy[h + 1 - kh, w + 1 - kw] * W[kh, kw]: column offset d = 1 - kw; box row r = 0..2 reads dy row
@@ -1356,15 +1383,17 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
         p.n_ci_tiles = (Ci + p.NT - 1) / p.NT;
     }
     p.Cout = Cout; p.Ci = Ci; p.dw = dw; p.dw_ld = (long long)taps * w_K; p.wK = w_K; p.w_coff = w_coff;
-    // Row-strip mode (WgradParams::strip): 3x3 stride-1, the 64-pixel box inside one image, rows of >= 8 pixels, cin in tiles of
+    // Row-strip mode (WgradParams::strip): 3x3 stride-1, bn * bw a multiple of 8 (boxes ordered (h, n, w)), cin in tiles of
     // 128 without padding (64 for a 64-channel input): dY is read once per stencil column instead of once per tap and X once
     // per three taps -- 32 KB instead of 72 KB of operands per CTA and three taps of a 128-wide cin tile.  Knob 13 = 1: off.
-    p.strip = geom == GEOM_3x3_S1 && p.bn == 1 && p.bw % 8 == 0 && Hd * Wd >= 64 && (Ci % 128 == 0 || Ci == 64) && g_debug_flags[13] != 1;
+    p.strip = geom == GEOM_3x3_S1 && (p.bn * p.bw) % 8 == 0 && (Ci % 128 == 0 || Ci == 64) && g_debug_flags[13] != 1 &&
+              !(g_debug_flags[13] == 2 && p.bn != 1);                 // knob 13 == 2 (A/B timing): only boxes inside one image
     if (p.strip) {
         p.NT = Ci == 64 ? 64 : 128;
         p.n_ci_tiles = (Ci + p.NT - 1) / p.NT;
-        p.x_box_bytes = (p.bh + 2) * p.bw * 128;
-        p.x_tap_off = p.bw * 128;
+        p.x_box_bytes = (p.bh + 2) * p.bn * p.bw * 128;
+        p.x_tap_off = p.bn * p.bw * 128;
+        p.hnw = 1;            // both pixel boxes ordered (h, n, w): the K (pixel) index of dY and X must agree
     }
     const bool pair = Cout > 128 && p.NT % 128 == 0 && g_debug_flags[6] != 1;
     p.stage_bytes = p.strip ? 2 * 8192 + ((pair ? p.NT / 2 : p.NT) / 64) * p.x_box_bytes : (2 + (pair ? p.NT / 2 : p.NT) / 64) * 8192;
@@ -1411,8 +1440,8 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
     p.tiles_per_split = (p.total_tiles + ksplit - 1) / ksplit;
     p.ksplit = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
     CUtensorMap mg, mx, mw;
-    if (make_act_map(&mg, dy, NB, Hy, Wy, Cout, ld_dy, g_phase, p.bn, p.bh, p.bw)) return 2;
-    if (make_act_map(&mx, x, NB, H, W, Ci, ld_x, x_phase, p.bn, p.strip ? p.bh + 2 : p.bh, p.bw)) return 2;
+    if (make_act_map(&mg, dy, NB, Hy, Wy, Cout, ld_dy, g_phase, p.bn, p.bh, p.bw, p.hnw)) return 2;
+    if (make_act_map(&mx, x, NB, H, W, Ci, ld_x, x_phase, p.bn, p.strip ? p.bh + 2 : p.bh, p.bw, p.hnw)) return 2;
     {   // dW fp32 [Cout][taps][w_K] -> 3-D reduce-add map (k, tap, n), box 32 x 1 x 32
         if (get_encode()) return 2;
         SNN_REQUIRE(((uintptr_t)dw & 15) == 0, "conv_wgrad: dw must be 16-byte aligned");

@@ -47,6 +47,11 @@ CASES = [
     (3, 12, 20, 128, 0, 128),      # non power-of-two map: partly out-of-bounds boxes
     (1, 16, 8, 64, 0, 64),         # exactly one tile per image
     (7, 16, 16, 128, 0, 8),        # N = 8
+    (8, 8, 8, 512, 0, 512),        # 8x8 maps: a box spans 2 images, rows ordered (h, n, w)
+    (5, 8, 8, 256, 144, 256),      # ... odd image count (the second image of the last box is out of range), two sources
+    (16, 4, 4, 1024, 0, 512),      # 4x4 maps: 8 images per box
+    (3, 4, 4, 128, 0, 128),        # ... mostly out-of-range box
+    (40, 2, 2, 64, 0, 64),         # 2x2 maps: 32 images per box
 ]
 
 
@@ -71,7 +76,8 @@ def test_fprop_strip_mode(knobs, nb, h, w, c0, c1, cout, single, cap):
     assert rel_err(outs[0], outs[1]) < 1e-5 and rel_err(outs[2], outs[1]) < 1e-5
 
 
-@pytest.mark.parametrize("T,B,h,w,cin,cout", [(4, 2, 32, 32, 144, 128), (2, 3, 16, 16, 128, 64), (3, 2, 12, 20, 64, 144)])
+@pytest.mark.parametrize("T,B,h,w,cin,cout", [(4, 2, 32, 32, 144, 128), (2, 3, 16, 16, 128, 64), (3, 2, 12, 20, 64, 144),
+                                              (2, 4, 8, 8, 256, 512), (3, 8, 4, 4, 512, 256)])
 def test_fprop_strip_mode_fused_statistics(knobs, T, B, h, w, cin, cout):
     """The BN partial sums come out of the epilogue, which the strip mode does not touch: sums == a pass over the same y."""
     setup_exact()
@@ -90,7 +96,8 @@ def test_fprop_strip_mode_fused_statistics(knobs, T, B, h, w, cin, cout):
 
 
 @pytest.mark.parametrize("nb,h,w,cin,cout", [(6, 32, 32, 128, 128), (3, 16, 16, 256, 256), (4, 16, 16, 144, 64), (3, 12, 20, 128, 128),
-                                             (2, 64, 64, 64, 128), (5, 16, 16, 128, 144)])
+                                             (2, 64, 64, 64, 128), (5, 16, 16, 128, 144), (8, 8, 8, 512, 512), (5, 8, 8, 256, 128),
+                                             (16, 4, 4, 1024, 1024), (3, 4, 4, 128, 256)])
 @pytest.mark.parametrize("single,cap", [(0, 0), (1, 0), (0, 2)])
 def test_dgrad_strip_mode(knobs, nb, h, w, cin, cout, single, cap):
     setup_exact()
@@ -123,6 +130,8 @@ WGRAD_CASES = [
     (2, 64, 64, 128, 256),     # bw = 64, bh = 1
     (5, 12, 20, 128, 128),     # non power-of-two map
     (4, 16, 16, 144, 128),     # cin not a multiple of 128: stays tap-by-tap (same result either way)
+    (16, 4, 4, 1024, 1024),    # 4x4 maps: the 64-pixel box spans 4 images, rows ordered (h, n, w) in both operands
+    (7, 4, 4, 256, 512),       # ... image count not a multiple of the box
 ]
 
 
