@@ -1052,6 +1052,9 @@ static bool pair_possible(const ConvGemmParams& p) {
 static bool strip_mode_ok(const ConvGemmParams& p) {
     if (g_debug_flags[12] == 1) return false;
     if ((p.bn * p.bw) % 8 != 0) return false;
+    // 4x4 maps: the box covers the whole height, 2 of its 6 rows are always padding, and the 2-stage pipeline costs more than
+    // the saved bytes (measured: 1024->4096@4x4 1488 -> 1360 TF/s); 8x8 maps gain (512<-512 dgrad 1198 -> 1362)
+    if (p.bh < 8 && p.tiles_h == 1) return false;
     if (g_debug_flags[12] == 3 && p.bn != 1) return false;          // A/B timing: only boxes inside one image
     const int bn_cta = pair_possible(p) ? p.BN / 2 : p.BN;
     const int b_bytes = p.b_mn ? ((bn_cta + 63) / 64) * 8192 : bn_cta * 128;
@@ -1292,7 +1295,18 @@ int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long lo
     p.BN = pick_bn(Ci);
     p.n_store = Ci; p.wn_off = ci_off; p.b_mn = 1;
     p.out = dx; p.bias = nullptr; p.out_f32 = dx_f32; p.accumulate = accumulate; p.out_ld = dx_ld; p.out_coff = dx_coff;
-    const bool strip = geom == GEOM_3x3_S1 && strip_mode_ok(p);
+    // Small-M convs (ConvLSTM recurrent dgrad: 8 pixel tiles x 4 column blocks = 16 work items for 74 CTA pairs) split K
+    // over the taps; the partial products meet in the fp32 output through TMA reduce-add (zero-filled first).
+    int ks = 1;
+    if (dx_f32 && !accumulate && geom != GEOM_3x3_S2 && dx_coff == 0 && dx_ld == Ci && g_debug_flags[0] != 1) {
+        const int m_work = (p.tiles_w * p.tiles_h * p.tiles_n + 1) / 2;
+        const int items = m_work * ((Ci + p.BN - 1) / p.BN);
+        const int nseg = taps, pairs = num_sms() / 2;           // one K segment per tap in these geometries
+        for (int cand = 1; cand <= nseg; ++cand)
+            if (nseg % cand == 0 && items * cand <= 2 * pairs) ks = cand;
+        if (!(ks > 1 && items <= pairs / 2)) ks = 1;
+    }
+    const bool strip = ks == 1 && geom == GEOM_3x3_S1 && strip_mode_ok(p);
     CUtensorMap a0;
     if (make_act_map(&a0, dy, NB, Hy, Wy, Cout, ld_dy, phase_view, p.bn, strip ? p.bh + 2 : p.bh, p.bw, strip)) return 2;
     const WDesc wd = {wt, Cout, taps, w_K};                  // box = 64 input channels x 1 tap x 64 output-channel rows
@@ -1332,20 +1346,10 @@ int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long lo
         for (int a = 0; a < 2; ++a)
             for (int bb = 0; bb < 2; ++bb) ph.seg[ph.nseg++] = mkseg(0, (int)(bb * ld_dy), 0, a, 0, a * 2 + bb, 0, Cout);
     }
-    // Small-M convs (ConvLSTM recurrent dgrad: 8 pixel tiles x 4 column blocks = 16 work items for 74 CTA pairs) split K
-    // over the taps; the partial products meet in the fp32 output through TMA reduce-add (zero-filled first).
-    if (dx_f32 && !accumulate && p.nphase == 1 && p.ntap <= 1 && dx_coff == 0 && dx_ld == Ci && g_debug_flags[0] != 1) {
-        const int m_work = (p.tiles_w * p.tiles_h * p.tiles_n + 1) / 2;
-        const int items = m_work * ((Ci + p.BN - 1) / p.BN);
-        const int nseg = p.phase[0].nseg, pairs = num_sms() / 2;
-        int ks = 1;
-        for (int cand = 1; cand <= nseg; ++cand)
-            if (nseg % cand == 0 && items * cand <= 2 * pairs) ks = cand;
-        if (ks > 1 && items <= pairs / 2) {
-            SNN_CUDA_OK(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)NB * H * W * Ci, st));
-            p.ksplit = ks;
-            p.accumulate = 1;
-        }
+    if (ks > 1) {
+        SNN_CUDA_OK(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)NB * H * W * Ci, st));
+        p.ksplit = ks;
+        p.accumulate = 1;
     }
     return launch_conv_gemm(a0, a0, wd, p, st);
 }
@@ -1387,6 +1391,7 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
     // 128 without padding (64 for a 64-channel input): dY is read once per stencil column instead of once per tap and X once
     // per three taps -- 32 KB instead of 72 KB of operands per CTA and three taps of a 128-wide cin tile.  Knob 13 = 1: off.
     p.strip = geom == GEOM_3x3_S1 && (p.bn * p.bw) % 8 == 0 && (Ci % 128 == 0 || Ci == 64) && g_debug_flags[13] != 1 &&
+              (p.bh >= 8 || p.tiles_h > 1) &&                         // not on 4x4 maps (a third of the strip box would be padding)
               !(g_debug_flags[13] == 2 && p.bn != 1);                 // knob 13 == 2 (A/B timing): only boxes inside one image
     if (p.strip) {
         p.NT = Ci == 64 ? 64 : 128;
