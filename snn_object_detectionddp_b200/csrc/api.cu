@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <mutex>
 #include <stdio.h>
 
 #include "../../include/snn_b200.h"
@@ -42,6 +43,34 @@ int num_sms() {
 static std::atomic<int> g_pdl{0};
 bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 void set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
+
+static std::atomic<int> g_det{0};
+bool deterministic() { return g_det.load(std::memory_order_relaxed) != 0; }
+void set_deterministic(int on) { g_det.store(on ? 1 : 0, std::memory_order_relaxed); }
+
+static void* g_det_ws[64];
+static size_t g_det_ws_bytes[64];
+static std::mutex g_det_mutex;
+void* det_scratch(size_t bytes, cudaStream_t st) {
+    const int dev = current_device();
+    if (dev < 0 || dev >= 64) { set_error("deterministic mode: bad CUDA device %d", dev); return nullptr; }
+    std::lock_guard<std::mutex> g(g_det_mutex);
+    if (g_det_ws_bytes[dev] >= bytes) return g_det_ws[dev];
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+        set_error("deterministic mode: the scratch buffer (%zu bytes) must be allocated outside CUDA-graph capture: run the step once eagerly first", bytes);
+        return nullptr;
+    }
+    size_t want = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes;
+    void* q = nullptr;
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMalloc(&q, want) != cudaSuccess) {
+        set_error("deterministic mode: cudaMalloc(%zu) failed", want);
+        return nullptr;
+    }
+    if (g_det_ws[dev]) cudaFree(g_det_ws[dev]);
+    g_det_ws[dev] = q; g_det_ws_bytes[dev] = want;
+    return q;
+}
 
 // launchers defined in the other translation units
 void debug_set(int k, int v);
@@ -114,6 +143,8 @@ const char* snn_last_error(void) { return g_err; }
 int snn_version(void) { return 100; }
 void snn_debug_set(int key, int value) { debug_set(key, value); }
 void snn_set_tile_scheduling(int dynamic) { set_dynamic_tiles(dynamic); }
+void snn_set_deterministic(int on) { set_deterministic(on); }
+int snn_get_deterministic(void) { return deterministic() ? 1 : 0; }
 void snn_set_dependent_launch(int on) { set_pdl(on); }
 int snn_get_dependent_launch(void) { return pdl_enabled() ? 1 : 0; }
 void snn_tensor_map_cache_stats(unsigned long long* hits, unsigned long long* misses) { tmap_cache_stats(hits, misses); }

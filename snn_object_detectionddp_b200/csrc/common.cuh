@@ -63,6 +63,24 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+// ------------------------------------------------------------------------------------------
+// Deterministic mode (set_deterministic / snn_set_deterministic): every sum whose order is otherwise decided by atomics or by
+// the arrival order of TMA reduce-adds is taken in a FIXED order, so two runs from the same state give bit-identical gradients:
+//   * wgrad and the small-M dgrad run without split-K (one contribution per output element and launch);
+//   * block-level reductions (BatchNorm backward sums, bias column sums, depthwise wgrad, gradient norm, loss sums) write one
+//     partial per block into a library-owned scratch buffer (det_scratch) and a second tiny kernel adds them in block order;
+//     inside a block, per-row partials go through shared-memory slots and are summed in row order.
+// Slower (the 128-channel wgrads lose their K split) -- a reproducibility / debugging mode, off by default.  The scratch is
+// allocated per device at the first deterministic launch on that device: make it outside CUDA-graph capture.
+// ------------------------------------------------------------------------------------------
+bool deterministic();
+void set_deterministic(int on);
+// >= bytes of device scratch on the current device (stream-ordered reuse: all users run on the caller's stream); nullptr + error set on failure
+void* det_scratch(size_t bytes, cudaStream_t st);
+// out[i] += sum over b = 0 .. nblocks-1 (in this order) of part[b * n + i]
+int launch_ordered_combine_f32(const float* part, int nblocks, long long n, float* out, cudaStream_t st);
+int launch_ordered_combine_f64(const double* part, int nblocks, long long n, double* out, cudaStream_t st);
+
 // One-time initialisation PER DEVICE (function attributes such as the dynamic shared-memory limit live in the device's
 // context: a process that touches cuda:3 after cuda:0 must set them again).  Thread-safe; remembers the first error.
 struct PerDeviceOnce {

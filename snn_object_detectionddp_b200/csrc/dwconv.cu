@@ -146,7 +146,7 @@ dw3x3_col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
 // wgrad: grid (blocks); a block walks columns blockIdx.x, blockIdx.x + gridDim.x, ... (slots columns at a time)
 __global__ void __launch_bounds__(256)
 dw3x3_wgrad_col_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, int NB, int H,
-                       int W, int C) {
+                       int W, int C, float* __restrict__ part /* deterministic mode: [gridDim.x][9][C] block partials, else null */) {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ float sh[];                 // [slots][3][C] (one tap row at a time)
@@ -201,7 +201,8 @@ dw3x3_wgrad_col_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
         for (int i = threadIdx.x; i < 3 * C; i += 256) {
             float a = 0.f;
             for (int sidx = 0; sidx < slots; ++sidx) a += sh[(size_t)sidx * 3 * C + i];
-            atomicAdd(&dw[(size_t)kh * 3 * C + i], a);
+            if (part) part[((size_t)blockIdx.x * 3 + kh) * 3 * C + i] = a;
+            else atomicAdd(&dw[(size_t)kh * 3 * C + i], a);
         }
     }
 }
@@ -263,7 +264,14 @@ int launch_dw3x3_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* d
     const size_t smem = sizeof(float) * (size_t)slots * 3 * C;
     static PerDeviceOnce once;
     SNN_CUDA_OK(once.run([] { return cudaFuncSetAttribute(dw3x3_wgrad_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
-    launch_pdl(dw3x3_wgrad_col_kernel, dim3((unsigned)blocks), dim3(256), smem, st, x, dy, dw, NB, H, W, C);
+    if (deterministic()) {
+        float* part = static_cast<float*>(det_scratch(sizeof(float) * (size_t)blocks * 9 * C, st));
+        if (!part) return 2;
+        launch_pdl(dw3x3_wgrad_col_kernel, dim3((unsigned)blocks), dim3(256), smem, st, x, dy, dw, NB, H, W, C, part);
+        SNN_CUDA_OK(cudaGetLastError());
+        return launch_ordered_combine_f32(part, (int)blocks, 9LL * C, dw, st);
+    }
+    launch_pdl(dw3x3_wgrad_col_kernel, dim3((unsigned)blocks), dim3(256), smem, st, x, dy, dw, NB, H, W, C, (float*)nullptr);
     return check_cuda(cudaGetLastError(), "dw3x3_wgrad_col_kernel");
 }
 // uint8 frames (what the dataset decodes, dataset.py:139-152) -> /255 on the device (the reference divides on the host and

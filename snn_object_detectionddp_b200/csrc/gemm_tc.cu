@@ -1306,6 +1306,7 @@ int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long lo
             if (nseg % cand == 0 && items * cand <= 2 * pairs) ks = cand;
         if (!(ks > 1 && items <= pairs / 2)) ks = 1;
     }
+    if (deterministic()) ks = 1;
     const bool strip = ks == 1 && geom == GEOM_3x3_S1 && strip_mode_ok(p);
     CUtensorMap a0;
     if (make_act_map(&a0, dy, NB, Hy, Wy, Cout, ld_dy, phase_view, p.bn, strip ? p.bh + 2 : p.bh, p.bw, strip)) return 2;
@@ -1442,6 +1443,7 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
     if (ksplit > max_split) ksplit = max_split;
     if (ksplit < 1) ksplit = 1;
     if (g_debug_flags[4] > 0) ksplit = g_debug_flags[4];
+    if (deterministic()) ksplit = 1;       // one reduce-add per dW element and launch: the order of additions is the stream order
     p.tiles_per_split = (p.total_tiles + ksplit - 1) / ksplit;
     p.ksplit = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
     CUtensorMap mg, mx, mw;

@@ -165,6 +165,7 @@ struct LossFinal {
     float* out6;               // loss*B [3], loss [3]
     float* coef3;
     float batch;
+    double* part;              // deterministic mode: [gridDim.x][3] block sums, added in block order (else null: fp64 atomics)
 };
 
 __global__ void __launch_bounds__(128)
@@ -192,9 +193,15 @@ detect_loss_fwd_kernel(const float* __restrict__ distri, const float* __restrict
     cls = block_sum(cls, sh);
     dfl = block_sum(dfl, sh);
     if (threadIdx.x == 0) {
-        atomicAdd(&sums[0], (double)box);
-        atomicAdd(&sums[1], (double)cls);
-        atomicAdd(&sums[2], (double)dfl);
+        if (fin.part) {
+            fin.part[(size_t)blockIdx.x * 3 + 0] = (double)box;
+            fin.part[(size_t)blockIdx.x * 3 + 1] = (double)cls;
+            fin.part[(size_t)blockIdx.x * 3 + 2] = (double)dfl;
+        } else {
+            atomicAdd(&sums[0], (double)box);
+            atomicAdd(&sums[1], (double)cls);
+            atomicAdd(&sums[2], (double)dfl);
+        }
     }
     if (fin.tss_part == nullptr) return;
     if (threadIdx.x == 0) {
@@ -208,7 +215,14 @@ detect_loss_fwd_kernel(const float* __restrict__ distri, const float* __restrict
     for (int i = 0; i < fin.n_parts; ++i) tss += (double)fin.tss_part[i];
     if (tss < 1.0) tss = 1.0;
     for (int k = 0; k < 3; ++k) {
-        const double s = __ldcg(&sums[k]);
+        double s;
+        if (fin.part) {
+            s = 0.0;
+            for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&fin.part[(size_t)b * 3 + k]);
+            sums[k] = s;
+        } else {
+            s = __ldcg(&sums[k]);
+        }
         const float l = (float)(s / tss) * fin.gains[k];
         fin.out6[k] = l * fin.batch;
         fin.out6[3 + k] = l;
@@ -333,11 +347,18 @@ int launch_detect_loss_fwd(const float* distri, const float* scores, const float
     if (N == 0) return 0;
     RowMap rm;
     if (make_rowmap(&rm, nl, a_off, B, A)) return 2;
-    LossFinal fin = {tss_part, n_parts, gains, counter, out6, coef3, (float)B};
+    LossFinal fin = {tss_part, n_parts, gains, counter, out6, coef3, (float)B, nullptr};
     if (tss_part) SNN_REQUIRE(gains && counter && out6 && coef3 && n_parts >= 1, "detect_loss_fwd: fused finalisation needs gains/counter/out6/coef3");
-    launch_pdl(detect_loss_fwd_kernel, dim3((unsigned)((N + 127) / 128)), dim3(128), 0, st, distri, scores, anchors, stride, tbox_px, tscores, fg,
+    const unsigned int blocks = (unsigned)((N + 127) / 128);
+    if (deterministic()) {
+        fin.part = static_cast<double*>(det_scratch(sizeof(double) * 3 * (size_t)blocks, st));
+        if (!fin.part) return 2;
+    }
+    launch_pdl(detect_loss_fwd_kernel, dim3(blocks), dim3(128), 0, st, distri, scores, anchors, stride, tbox_px, tscores, fg,
                                                                         N, A, nc, sums, rm, fin);
-    return check_cuda(cudaGetLastError(), "detect_loss_fwd_kernel");
+    SNN_CUDA_OK(cudaGetLastError());
+    if (fin.part && !tss_part) return launch_ordered_combine_f64(fin.part, (int)blocks, 3, sums, st);    // raw sums only: no finalising block
+    return 0;
 }
 
 int launch_detect_loss_bwd(const float* distri, const float* scores, const float* anchors, const float* stride,

@@ -208,14 +208,36 @@ int launch_lstm_gates_bwd(const float* gates, const float* c_prev, const float* 
 }
 
 // ------------------------------------------------------------------------------------------
+// deterministic mode: out[i] += part[0][i] + part[1][i] + ... in block order (see common.cuh)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) ordered_combine_kernel(const T* __restrict__ part, int nblocks, long long n, T* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    T a = part[i];
+    for (int b = 1; b < nblocks; ++b) a += part[(long long)b * n + i];
+    out[i] += a;
+}
+int launch_ordered_combine_f32(const float* part, int nblocks, long long n, float* out, cudaStream_t st) {
+    launch_pdl(ordered_combine_kernel<float>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, part, nblocks, n, out);
+    return check_cuda(cudaGetLastError(), "ordered_combine_kernel<float>");
+}
+int launch_ordered_combine_f64(const double* part, int nblocks, long long n, double* out, cudaStream_t st) {
+    launch_pdl(ordered_combine_kernel<double>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, part, nblocks, n, out);
+    return check_cuda(cudaGetLastError(), "ordered_combine_kernel<double>");
+}
+
+// ------------------------------------------------------------------------------------------
 // bias gradient: acc[c] += sum_p dy[p][c]  (dy bf16 [P][C]); grid.y walks column blocks of <= 1024
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ acc, long long P, int C, int cblk,
-                   int pix_per_block) {
+                   int pix_per_block, float* __restrict__ part /* deterministic mode: [gridDim.x][C] block partials, else null */) {
     pdl_launch_dependents();
     pdl_wait();
-    extern __shared__ float shc[];  // [cblk]
+    extern __shared__ float shc[];  // [cblk] (+ deterministic mode: [rows][cblk] slots behind it)
     const int c_base = blockIdx.y * cblk;
     const int cw = min(cblk, C - c_base);
     const int tpp = cw >> 2;  // threads per pixel, 4 channels each
@@ -231,10 +253,23 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ acc
             const uint2 v = __ldg(reinterpret_cast<const uint2*>(dy + p * C + c_base) + cg);
             s[0] += bf16_lo(v.x); s[1] += bf16_hi(v.x); s[2] += bf16_lo(v.y); s[3] += bf16_hi(v.y);
         }
+        if (part) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) atomicAdd(&shc[cg * 4 + i], s[i]);
+            for (int i = 0; i < 4; ++i) shc[cblk + row * cw + cg * 4 + i] = s[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) atomicAdd(&shc[cg * 4 + i], s[i]);
+        }
     }
     __syncthreads();
+    if (part) {     // rows summed in row order, one partial per block and column
+        for (int i = threadIdx.x; i < cw; i += 256) {
+            float a = 0.f;
+            for (int r = 0; r < rows; ++r) a += shc[cblk + r * cw + i];
+            part[(size_t)blockIdx.x * C + c_base + i] = a;
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < cw; i += 256) atomicAdd(&acc[c_base + i], shc[i]);
 }
 
@@ -248,7 +283,14 @@ int launch_colsum_bf16(const __nv_bfloat16* dy, float* acc, long long P, int C, 
     if (ppb < rows * 4) ppb = rows * 4;
     ppb = (ppb + rows - 1) / rows * rows;
     dim3 grid((unsigned)((P + ppb - 1) / ppb), (C + cblk - 1) / cblk);
-    launch_pdl(colsum_bf16_kernel, grid, dim3(256), sizeof(float) * cblk, st, dy, acc, P, C, cblk, (int)ppb);
+    if (deterministic()) {
+        float* part = static_cast<float*>(det_scratch(sizeof(float) * (size_t)grid.x * C, st));
+        if (!part) return 2;
+        launch_pdl(colsum_bf16_kernel, grid, dim3(256), sizeof(float) * (cblk + 1024), st, dy, acc, P, C, cblk, (int)ppb, part);
+        SNN_CUDA_OK(cudaGetLastError());
+        return launch_ordered_combine_f32(part, (int)grid.x, C, acc, st);
+    }
+    launch_pdl(colsum_bf16_kernel, grid, dim3(256), sizeof(float) * cblk, st, dy, acc, P, C, cblk, (int)ppb, (float*)nullptr);
     return check_cuda(cudaGetLastError(), "colsum_bf16_kernel");
 }
 
@@ -259,7 +301,8 @@ int launch_colsum_bf16(const __nv_bfloat16* dy, float* acc, long long P, int C, 
 // hyper-parameters (lr, beta1, step-dependent bias corrections) are read from a device array so the
 // OneCycle schedule never forces a host sync:  hp = {lr, beta1, beta2, eps, wd, bc1, bc2, max_norm}
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n4, double* __restrict__ acc) {
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n4, double* __restrict__ acc,
+                                                    double* __restrict__ part /* deterministic mode: [gridDim.x], else null */) {
     pdl_launch_dependents();
     pdl_wait();
     float s = 0.f;
@@ -274,7 +317,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
     if (threadIdx.x == 0) {
         double t = 0;
         for (int i = 0; i < 8; ++i) t += ws[i];
-        atomicAdd(acc, t);
+        if (part) part[blockIdx.x] = t;
+        else atomicAdd(acc, t);
     }
 }
 
@@ -328,7 +372,14 @@ int launch_sumsq(const float* g, long long n, double* acc, int zero_first, cudaS
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    launch_pdl(sumsq_kernel, dim3((unsigned)blocks), dim3(256), 0, st, g, n4, acc);
+    if (deterministic()) {
+        double* part = static_cast<double*>(det_scratch(sizeof(double) * (size_t)blocks, st));
+        if (!part) return 2;
+        launch_pdl(sumsq_kernel, dim3((unsigned)blocks), dim3(256), 0, st, g, n4, acc, part);
+        SNN_CUDA_OK(cudaGetLastError());
+        return launch_ordered_combine_f64(part, (int)blocks, 1, acc, st);
+    }
+    launch_pdl(sumsq_kernel, dim3((unsigned)blocks), dim3(256), 0, st, g, n4, acc, (double*)nullptr);
     return check_cuda(cudaGetLastError(), "sumsq_kernel");
 }
 
