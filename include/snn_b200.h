@@ -45,6 +45,14 @@ void snn_debug_set(int key, int value);
  * static walk every launch waits for them.  Dynamic mode uses a library-owned 32 KB counter pool per device (allocated at
  * the first launch in that mode; launch once eagerly before capturing a CUDA graph). */
 void snn_set_tile_scheduling(int dynamic);
+/* Deterministic mode (process-wide, read at launch; default 0).  1 = every sum whose order is otherwise decided by atomics or
+ * by the arrival order of TMA reduce-adds is taken in a fixed order: wgrad and the small-M dgrad run without split-K;
+ * BatchNorm-backward sums, bias column sums, depthwise wgrad, the gradient norm and the loss sums go through per-block
+ * partials in a library-owned scratch buffer (>= 64 MB per device, allocated at the first such launch -- run one step
+ * eagerly before capturing a CUDA graph) and are added in block order.  Two runs from the same state then produce
+ * bit-identical gradients on one GPU.  Slower: a reproducibility / debugging mode. */
+void snn_set_deterministic(int on);
+int snn_get_deterministic(void);
 /* Programmatic dependent launch (process-wide, read at launch; default 0): 1 = every kernel of the library is launched with
  * cudaLaunchAttributeProgrammaticStreamSerialization, so it may become resident -- and run its barrier / TMEM / table
  * set-up -- while its predecessor on the stream drains; each kernel executes griddepcontrol.wait before its first global

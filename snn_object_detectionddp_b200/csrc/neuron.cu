@@ -530,7 +530,8 @@ bn_act_bwd2_kernel(const float* __restrict__ y, const float* __restrict__ scale,
                    const float* __restrict__ red_in, const float* __restrict__ v_init, const __nv_bfloat16* __restrict__ gs,
                    const float* __restrict__ gv_final, __nv_bfloat16* __restrict__ dy_out, float* __restrict__ gv_init,
                    float* __restrict__ red_out, float* dgamma, float* dbeta, int T_rt, int P, int C, int Cb, int pix_per_block,
-                   float beta, float theta, float alpha, float invP) {
+                   float beta, float theta, float alpha, float invP,
+                   float* __restrict__ part /* REDUCE, deterministic mode: [gridDim.x][T*2*C] block partials, else null */) {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ float4 shc4[];
@@ -671,22 +672,42 @@ bn_act_bwd2_kernel(const float* __restrict__ y, const float* __restrict__ scale,
         }
         if (REDUCE) {
             const int cl = cg * 2;
+            float* slot = accum + (size_t)(1 + row) * T * 2 * Cb;       // deterministic mode: this row's own copy of accum[]
 #pragma unroll
             for (int t = 0; t < TMAX; ++t) {
                 if (EXACT || t < T) {
-                    atomicAdd(&accum[(t * 2 + 0) * Cb + cl], acc_s[t].x); atomicAdd(&accum[(t * 2 + 0) * Cb + cl + 1], acc_s[t].y);
-                    atomicAdd(&accum[(t * 2 + 1) * Cb + cl], acc_d[t].x); atomicAdd(&accum[(t * 2 + 1) * Cb + cl + 1], acc_d[t].y);
+                    if (part) {
+                        slot[(t * 2 + 0) * Cb + cl] = acc_s[t].x; slot[(t * 2 + 0) * Cb + cl + 1] = acc_s[t].y;
+                        slot[(t * 2 + 1) * Cb + cl] = acc_d[t].x; slot[(t * 2 + 1) * Cb + cl + 1] = acc_d[t].y;
+                    } else {
+                        atomicAdd(&accum[(t * 2 + 0) * Cb + cl], acc_s[t].x); atomicAdd(&accum[(t * 2 + 0) * Cb + cl + 1], acc_s[t].y);
+                        atomicAdd(&accum[(t * 2 + 1) * Cb + cl], acc_d[t].x); atomicAdd(&accum[(t * 2 + 1) * Cb + cl + 1], acc_d[t].y);
+                    }
                 }
             }
         }
     }
     if (REDUCE) {
         __syncthreads();
+        if (part) {          // rows in row order -> block partial -> this block's row of the scratch buffer
+            for (int i = threadIdx.x; i < T * 2 * Cb; i += 256) {
+                float a = 0.f;
+                for (int r = 0; r < rows; ++r) a += accum[(size_t)(1 + r) * T * 2 * Cb + i];
+                accum[i] = a;
+            }
+            __syncthreads();
+        }
         for (int i = threadIdx.x; i < T * Cb; i += 256) {
             const int t = i / Cb, c = i % Cb;
-            atomicAdd(&red_out[(t * 2 + 0) * C + c_base + c], accum[(t * 2 + 0) * Cb + c]);
-            // sum gx*(y - mean) -> sum gx*xhat
-            atomicAdd(&red_out[(t * 2 + 1) * C + c_base + c], accum[(t * 2 + 1) * Cb + c] * invstd[t * C + c_base + c]);
+            const float v0 = accum[(t * 2 + 0) * Cb + c];
+            const float v1 = accum[(t * 2 + 1) * Cb + c] * invstd[t * C + c_base + c];      // sum gx*(y - mean) -> sum gx*xhat
+            if (part) {
+                part[(size_t)blockIdx.x * T * 2 * C + (t * 2 + 0) * C + c_base + c] = v0;
+                part[(size_t)blockIdx.x * T * 2 * C + (t * 2 + 1) * C + c_base + c] = v1;
+            } else {
+                atomicAdd(&red_out[(t * 2 + 0) * C + c_base + c], v0);
+                atomicAdd(&red_out[(t * 2 + 1) * C + c_base + c], v1);
+            }
         }
     }
 }
@@ -780,7 +801,7 @@ bn_act_bwd2_t16_kernel(const float* __restrict__ y, const float* __restrict__ sc
                        const float* __restrict__ red_in, const float* __restrict__ v_init, const __nv_bfloat16* __restrict__ gs,
                        const float* __restrict__ gv_final, __nv_bfloat16* __restrict__ dy_out, float* __restrict__ gv_init,
                        float* __restrict__ red_out, float* dgamma, float* dbeta, int T_rt, int P, int C, int Cb, int pix_per_block,
-                       float beta, float theta, float alpha, float invP) {
+                       float beta, float theta, float alpha, float invP, float* __restrict__ part /* as in bn_act_bwd2_kernel */) {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ float4 shc4[];
@@ -871,7 +892,7 @@ bn_act_bwd2_t16_kernel(const float* __restrict__ y, const float* __restrict__ sc
             bwd2_chunk8<ACT, REDUCE, 0>(yp, gp, dp, nt2, tA, tB, v0, gv, nbb, k, acc);
             if (!REDUCE && ACT == ACT_LIF && gv_init) *(reinterpret_cast<float2*>(gv_init) + e2) = gv;
         }
-        if (REDUCE) {
+        if (REDUCE && !part) {
             const int cl = cg * 2;
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
@@ -883,10 +904,27 @@ bn_act_bwd2_t16_kernel(const float* __restrict__ y, const float* __restrict__ sc
     }
     if (REDUCE) {
         __syncthreads();
+        if (part) {          // deterministic mode: the per-thread slots summed in row order
+            const float* slots = accum + (size_t)T * 2 * Cb;           // float4 [16][256] = {s.x, s.y, d.x, d.y} of thread (row, cg)
+            for (int i = threadIdx.x; i < T * 2 * Cb; i += 256) {
+                const int t = i / (2 * Cb), h = (i / Cb) & 1, c = i % Cb;
+                float a = 0.f;
+                for (int r = 0; r < rows; ++r) a += slots[((size_t)t * 256 + r * tpp + (c >> 1)) * 4 + h * 2 + (c & 1)];
+                accum[i] = a;
+            }
+            __syncthreads();
+        }
         for (int i = threadIdx.x; i < T * Cb; i += 256) {
             const int t = i / Cb, c = i % Cb;
-            atomicAdd(&red_out[(t * 2 + 0) * C + c_base + c], accum[(t * 2 + 0) * Cb + c]);
-            atomicAdd(&red_out[(t * 2 + 1) * C + c_base + c], accum[(t * 2 + 1) * Cb + c] * invstd[t * C + c_base + c]);
+            const float v0 = accum[(t * 2 + 0) * Cb + c];
+            const float v1 = accum[(t * 2 + 1) * Cb + c] * invstd[t * C + c_base + c];
+            if (part) {
+                part[(size_t)blockIdx.x * T * 2 * C + (t * 2 + 0) * C + c_base + c] = v0;
+                part[(size_t)blockIdx.x * T * 2 * C + (t * 2 + 1) * C + c_base + c] = v1;
+            } else {
+                atomicAdd(&red_out[(t * 2 + 0) * C + c_base + c], v0);
+                atomicAdd(&red_out[(t * 2 + 1) * C + c_base + c], v1);
+            }
         }
     }
 }
@@ -901,7 +939,8 @@ __global__ void __launch_bounds__(256, 4)
 silu_t1_bwd2_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ beta_bn,
                     const float* __restrict__ red_in, const __nv_bfloat16* __restrict__ gs, __nv_bfloat16* __restrict__ dy_out,
-                    float* __restrict__ red_out, float* dgamma, float* dbeta, int P, int C, int Cb, int pix_per_block, float invP) {
+                    float* __restrict__ red_out, float* dgamma, float* dbeta, int P, int C, int Cb, int pix_per_block, float invP,
+                    float* __restrict__ part /* REDUCE, deterministic mode: [gridDim.x][2*C] block partials, else null */) {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ float4 sht[];
@@ -983,15 +1022,34 @@ silu_t1_bwd2_kernel(const float* __restrict__ y, const float* __restrict__ scale
         }
         if (REDUCE) {
             const int cl = cg * 2;
-            atomicAdd(&accum[cl], acc_s.x); atomicAdd(&accum[cl + 1], acc_s.y);
-            atomicAdd(&accum[Cb + cl], acc_d.x); atomicAdd(&accum[Cb + cl + 1], acc_d.y);
+            if (part) {
+                float* slot = accum + (size_t)(1 + row) * 2 * Cb;
+                slot[cl] = acc_s.x; slot[cl + 1] = acc_s.y; slot[Cb + cl] = acc_d.x; slot[Cb + cl + 1] = acc_d.y;
+            } else {
+                atomicAdd(&accum[cl], acc_s.x); atomicAdd(&accum[cl + 1], acc_s.y);
+                atomicAdd(&accum[Cb + cl], acc_d.x); atomicAdd(&accum[Cb + cl + 1], acc_d.y);
+            }
         }
     }
     if (REDUCE) {
         __syncthreads();
+        if (part) {
+            for (int i = threadIdx.x; i < 2 * Cb; i += 256) {
+                float a = 0.f;
+                for (int r = 0; r < rows; ++r) a += accum[(size_t)(1 + r) * 2 * Cb + i];
+                accum[i] = a;
+            }
+            __syncthreads();
+        }
         for (int c = threadIdx.x; c < Cb; c += 256) {
-            atomicAdd(&red_out[c_base + c], accum[c]);
-            atomicAdd(&red_out[C + c_base + c], accum[Cb + c] * invstd[c_base + c]);
+            const float v0 = accum[c], v1 = accum[Cb + c] * invstd[c_base + c];
+            if (part) {
+                part[(size_t)blockIdx.x * 2 * C + c_base + c] = v0;
+                part[(size_t)blockIdx.x * 2 * C + C + c_base + c] = v1;
+            } else {
+                atomicAdd(&red_out[c_base + c], v0);
+                atomicAdd(&red_out[C + c_base + c], v1);
+            }
         }
     }
 }
@@ -1137,23 +1195,35 @@ static int launch_bwd2_t(const float* y, const float* scale, const float* shift,
     const int min_ppb = rows * (REDUCE ? 8 : 2);
     if (ppb < min_ppb) ppb = min_ppb;
     ppb = ((ppb + rows - 1) / rows) * rows;
-    const size_t smem = (size_t)Cb * per_c + acc_slots;
     dim3 grid((P + ppb - 1) / ppb, nyb);
+    // deterministic mode (REDUCE pass): per-row copies of the block accumulators in shared memory (the t16 kernel has its
+    // per-thread slots anyway) and one partial row per block in the scratch buffer, combined in block order afterwards
+    float* part = nullptr;
+    size_t det_slots = 0;
+    if (REDUCE && deterministic()) {
+        part = static_cast<float*>(det_scratch(sizeof(float) * (size_t)grid.x * T * 2 * C, st));
+        if (!part) return 2;
+        if (!acc_slots) det_slots = sizeof(float) * (size_t)rows * T * 2 * Cb;
+    }
+    const size_t smem = (size_t)Cb * per_c + acc_slots + det_slots;
+    SNN_REQUIRE(smem <= 200 * 1024, "bn_act_bwd2: %zu bytes of shared memory (C=%d T=%d)", smem, C, T);
 #define SNN_GO(EX)                                                                                                         \
     do {                                                                                                                   \
         auto kern = bn_act_bwd2_kernel<ACT, TMAX, REDUCE, EX>;                                                             \
         if (smem > 48 * 1024) SNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         launch_pdl(kern, grid, dim3(256), smem, st, y, scale, shift, mean, invstd, beta_bn, red_in, v_init, gs, gv_final, dy, gv_init,   \
-                                      red_out, dgamma, dbeta, T, P, C, Cb, ppb, beta, theta, alpha, 1.0f / (float)P);      \
+                                      red_out, dgamma, dbeta, T, P, C, Cb, ppb, beta, theta, alpha, 1.0f / (float)P, part); \
     } while (0)
     if (chunked) {
         auto kern = bn_act_bwd2_t16_kernel<ACT, REDUCE>;
         if (smem > 48 * 1024) SNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         launch_pdl(kern, grid, dim3(256), smem, st, y, scale, shift, mean, invstd, beta_bn, red_in, v_init, gs, gv_final, dy, gv_init,
-                   red_out, dgamma, dbeta, T, P, C, Cb, ppb, beta, theta, alpha, 1.0f / (float)P);
+                   red_out, dgamma, dbeta, T, P, C, Cb, ppb, beta, theta, alpha, 1.0f / (float)P, part);
     } else if (T == TMAX) SNN_GO(true); else SNN_GO(false);
 #undef SNN_GO
-    return check_cuda(cudaGetLastError(), REDUCE ? "bn_act_bwd2_kernel<reduce>" : "bn_act_bwd2_kernel<dx>");
+    SNN_CUDA_OK(cudaGetLastError());
+    if (part) return launch_ordered_combine_f32(part, (int)grid.x, (long long)T * 2 * C, red_out, st);
+    return 0;
 }
 
 static int g_t1_fast = 1;     // 0: T == 1 SiLU layers go through the generic kernel (A/B timing)
@@ -1181,15 +1251,22 @@ int launch_bn_act_bwd2(int pass, int act, const float* y, const float* scale, co
         const int unit = rows * 4;
         if (ppb < unit * (pass == 0 ? 2 : 1)) ppb = unit * (pass == 0 ? 2 : 1);
         ppb = ((ppb + unit - 1) / unit) * unit;
-        const size_t smem = (size_t)(Cb / 2) * 32 + (pass == 0 ? (size_t)2 * Cb * 4 : 0);
         dim3 grid((P + ppb - 1) / ppb, nyb);
+        float* part = nullptr;
+        if (pass == 0 && deterministic()) {
+            part = static_cast<float*>(det_scratch(sizeof(float) * (size_t)grid.x * 2 * C, st));
+            if (!part) return 2;
+        }
+        const size_t smem = (size_t)(Cb / 2) * 32 + (pass == 0 ? (size_t)2 * Cb * 4 * (part ? 1 + rows : 1) : 0);
         if (pass == 0)
             launch_pdl(silu_t1_bwd2_kernel<true>, grid, dim3(256), smem, st, y, scale, shift, mean, invstd, beta_bn, nullptr, gs, nullptr, red, nullptr,
-                                                               nullptr, P, C, Cb, ppb, 1.0f / (float)P);
+                                                               nullptr, P, C, Cb, ppb, 1.0f / (float)P, part);
         else
             launch_pdl(silu_t1_bwd2_kernel<false>, grid, dim3(256), smem, st, y, scale, shift, mean, invstd, beta_bn, red, gs, dy, nullptr, dgamma, dbeta,
-                                                                P, C, Cb, ppb, 1.0f / (float)P);
-        return check_cuda(cudaGetLastError(), "silu_t1_bwd2_kernel");
+                                                                P, C, Cb, ppb, 1.0f / (float)P, (float*)nullptr);
+        SNN_CUDA_OK(cudaGetLastError());
+        if (part) return launch_ordered_combine_f32(part, (int)grid.x, 2LL * C, red, st);
+        return 0;
     }
 #define SNN_BWD2(ACT, TM)                                                                                                   \
     return pass == 0 ? launch_bwd2_t<ACT, TM, true>(y, scale, shift, mean, invstd, beta_bn, nullptr, v_init, gs, gv_final,   \
