@@ -152,6 +152,39 @@ def test_ddp_same_batch_equals_single_process():
 
 
 @needs2
+def test_ddp_same_batch_is_bit_exact_in_deterministic_mode():
+    """Deterministic mode (snn_set_deterministic: fixed-order reductions, no split-K): the single-process gradient is
+    bit-reproducible, the all-reduce averages two identical fp32 gradients ((g + g) / 2 == g exactly), so the DDP gradient
+    must EQUAL the single-process one bit for bit -- any lost, doubled or reordered contribution in the bucketed exchange
+    shows.  (Workers inherit SNN_DETERMINISTIC from the environment.)"""
+    from snn_object_detectionddp_b200 import _lib
+    from snn_object_detectionddp_b200.data import synthetic_batch
+    from snn_object_detectionddp_b200.trainer import Trainer
+    L = _lib.lib()
+    before, env_before = L.snn_get_deterministic(), os.environ.get("SNN_DETERMINISTIC")
+    os.environ["SNN_DETERMINISTIC"] = "1"
+    L.snn_set_deterministic(1)
+    try:
+        _, g_ddp, losses, launched, _, nb = _run("grad")
+        ref = []
+        for _ in range(2):
+            net = _build("cuda:0")
+            tr = Trainer(net, total_steps=20, device="cuda:0")
+            frames, labels = synthetic_batch(2, 2, 128, 128, seed=100)
+            ref.append(_backward_only(tr, frames.cuda(), tr.prepare_batch(labels, 2, max_boxes=8)))
+    finally:
+        L.snn_set_deterministic(before)
+        if env_before is None:
+            os.environ.pop("SNN_DETERMINISTIC", None)
+        else:
+            os.environ["SNN_DETERMINISTIC"] = env_before
+    (g1, it1), (g2, it2) = ref
+    assert torch.equal(it1, it2) and torch.equal(it1.cpu(), losses[0])
+    assert float(g1.abs().max()) > 0 and torch.equal(g1, g2)
+    assert torch.equal(g_ddp.cuda(), g1), float((g_ddp.cuda() - g1).abs().max())
+
+
+@needs2
 def test_ddp_different_batches_keep_ranks_in_lockstep():
     same, _, losses, _, _, _ = _run("diff")
     assert same and all(torch.isfinite(l).all() for l in losses)

@@ -424,3 +424,42 @@ def test_fused_head_loss_path_equals_list_of_maps_path():
     assert rel_err(g_f, g_m) < 1e-2
     head = [w for w in worst if w[1].startswith("detection_head.") and (".cv2.0.2." in w[1] or ".cv3.0.2." in w[1])]
     assert head and max(head)[0] < 1e-2, head
+
+
+def test_dead_frame_shortcut_in_deterministic_mode():
+    """Same comparison as test_skipping_dead_frame_backward_changes_nothing with snn_set_deterministic(1): the two full-backward
+    runs are now BIT-IDENTICAL (no noise term), and the shortcut differs from them only through the launch shapes of the head /
+    output-conv backward (NB = B instead of T*B moves tile and reduction-group boundaries, i.e. fp32 summation order),
+    measured 1e-9 relative -- so the percent-level noise band of the default-mode test above is all reordering noise of the
+    atomics, not a property of the shortcut.  Bound: 1e-6."""
+    setup_exact()
+    from snn_object_detectionddp_b200 import _lib
+    from snn_object_detectionddp_b200.params import store_for
+    from snn_object_detectionddp_b200.loss import v8DetectionLoss
+    L = _lib.lib()
+    before = L.snn_get_deterministic()
+    L.snn_set_deterministic(1)
+    try:
+        res = []
+        for skip in (True, False, False):
+            _, net = _models("lif", seed=7)
+            net.skip_dead_backward = skip
+            net.train()
+            B, T, HW = 2, 3, 128
+            frames, labels = MO.synthetic_batch(B, T, HW, HW, seed=13)
+            frames, labels = frames.to(DEV), labels.to(DEV)
+            st = store_for(net, DEV)
+            st.zero_grad()
+            det, _ = net.forward_sequence(frames)
+            loss, items = v8DetectionLoss(net)(det, {"batch_idx": labels[:, 0], "cls": labels[:, 1], "bboxes": labels[:, 2:]})
+            loss.sum().backward()
+            torch.cuda.synchronize()
+            res.append((items.clone(), st.flat_g.clone()))
+    finally:
+        L.snn_set_deterministic(before)
+    (it_a, g_a), (it_b, g_b), (it_c, g_c) = res
+    assert torch.equal(it_a, it_b) and torch.equal(it_b, it_c)
+    assert float(g_b.abs().max()) > 0 and torch.equal(g_b, g_c)
+    e = float(rel_err(g_a, g_b))
+    print(f"dead-frame shortcut vs full backward, deterministic mode: rel {e:.2e}")
+    assert e < 1e-6, e
