@@ -35,8 +35,10 @@ int snn_version(void);
  *   8: 1 = T == 1 SiLU layers use the generic two-pass BN backward kernel
  *   9: 1 = T == 16 uses the one-chunk two-pass BN backward kernel instead of the two-chunk one
  *  12: row-strip mode of the 3x3 stride-1 convs (one [bh+2] x bw activation box feeds the three taps of a stencil column):
- *      0 = wherever >= 2 pipeline stages fit, 1 = off, 2 = only where >= 3 stages fit (tiles of <= 144 columns)
- *  13: 1 = wgrad of the 3x3 stride-1 convs tap by tap (default: one stencil column = three taps per work item, row-strip X box)
+ *      0 = wherever >= 2 pipeline stages fit (maps >= 8x8), 1 = off, 2 = only where >= 3 stages fit (tiles of <= 144 columns),
+ *      3 = only pixel boxes inside one image (maps >= 16x8)
+ *  13: 1 = wgrad of the 3x3 stride-1 convs tap by tap (default: one stencil column = three taps per work item, row-strip X box),
+ *      2 = row-strip wgrad only for pixel boxes inside one image
  *  14: 1 = row-strip wgrad keeps the two-round K split of the tap-by-tap kernel */
 void snn_debug_set(int key, int value);
 /* Tile scheduling of the persistent tensor-core kernels (process-wide, read at launch): 0 (default) = static walk
