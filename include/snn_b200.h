@@ -47,6 +47,14 @@ void snn_debug_set(int key, int value);
  * static walk every launch waits for them.  Dynamic mode uses a library-owned 32 KB counter pool per device (allocated at
  * the first launch in that mode; launch once eagerly before capturing a CUDA graph). */
 void snn_set_tile_scheduling(int dynamic);
+/* Launch plan of a conv call WITHOUT launching it: the host-side planning (pixel box, N tile, CTA pairs, row-strip mode,
+ * pipeline stages, K split, work items) runs exactly as for a launch, no CUDA call is made -- usable without a GPU (the SM
+ * count then defaults to 148).  kind: 0 = fprop, 1 = dgrad, 2 = wgrad; frames_per_step > 0 = fprop with fused statistics.
+ * out20 = {bn, bh, bw, N tile, CTA pair, row-strip, (h,n,w) row order, stages, stage bytes, K chunks per stage, K split,
+ * work items, N blocks (wgrad: cin tiles), CTAs or CTA pairs launched, epilogue warp groups, small-K, TMA-store epilogue,
+ * dynamic shared memory bytes, activation bytes per stage (wgrad: X box bytes), weight-slice bytes per tap (wgrad: dY bytes)}. */
+int snn_conv_plan(int kind, int geom, int NB, int H, int W, int Cin, int Cout, int out_f32, int frames_per_step, int accumulate,
+                  int* out20);
 /* Deterministic mode (process-wide, read at launch; default 0).  1 = every sum whose order is otherwise decided by atomics or
  * by the arrival order of TMA reduce-adds is taken in a fixed order: wgrad and the small-M dgrad run without split-K;
  * BatchNorm-backward sums, bias column sums, depthwise wgrad, the gradient norm and the loss sums go through per-block

@@ -65,7 +65,7 @@ class SnnKernelError(RuntimeError):
 
 
 def exported_symbols():
-    return sorted(list(_SIGNATURES) + ["snn_last_error", "snn_version", "snn_debug_set", "snn_set_tile_scheduling", "snn_set_dependent_launch", "snn_get_dependent_launch", "snn_set_deterministic", "snn_get_deterministic", "snn_tensor_map_cache_stats", "snn_conv_stats_groups", "snn_bn_stats_workspace_floats", "snn_nms_workspace_keys",
+    return sorted(list(_SIGNATURES) + ["snn_last_error", "snn_version", "snn_debug_set", "snn_set_tile_scheduling", "snn_set_dependent_launch", "snn_get_dependent_launch", "snn_set_deterministic", "snn_get_deterministic", "snn_conv_plan", "snn_tensor_map_cache_stats", "snn_conv_stats_groups", "snn_bn_stats_workspace_floats", "snn_nms_workspace_keys",
                                              "snn_tal_workspace_bytes", "snn_dw3x3_stats_blocks", "snn_bn_finalize_workspace_doubles"])
 
 
@@ -111,6 +111,8 @@ def lib():
         L.snn_get_dependent_launch.argtypes = []
         L.snn_get_dependent_launch.restype = _I
         L.snn_set_dependent_launch(int(os.environ.get("SNN_DEPENDENT_LAUNCH", "0")))
+        L.snn_conv_plan.argtypes = [_I] * 10 + [ctypes.POINTER(_I)]
+        L.snn_conv_plan.restype = _I
         L.snn_set_deterministic.argtypes = [_I]
         L.snn_set_deterministic.restype = None
         L.snn_get_deterministic.argtypes = []

@@ -76,6 +76,7 @@ void* det_scratch(size_t bytes, cudaStream_t st) {
 void debug_set(int k, int v);
 void set_dynamic_tiles(int on);
 void tmap_cache_stats(unsigned long long*, unsigned long long*);
+int conv_plan(int, int, int, int, int, int, int, int, int, int, int*);
 int conv_fprop(int, int, int, int, const void*, int, long long, const void*, int, long long, const void*, int, int, int, int,
                int, const float*, void*, int, long long, int, int, cudaStream_t, float*, int);
 long long conv_stats_groups(int, int, int, int, int, int*);
@@ -143,6 +144,9 @@ const char* snn_last_error(void) { return g_err; }
 int snn_version(void) { return 100; }
 void snn_debug_set(int key, int value) { debug_set(key, value); }
 void snn_set_tile_scheduling(int dynamic) { set_dynamic_tiles(dynamic); }
+int snn_conv_plan(int kind, int geom, int NB, int H, int W, int Cin, int Cout, int out_f32, int frames_per_step, int accumulate, int* out20) {
+    return conv_plan(kind, geom, NB, H, W, Cin, Cout, out_f32, frames_per_step, accumulate, out20);
+}
 void snn_set_deterministic(int on) { set_deterministic(on); }
 int snn_get_deterministic(void) { return deterministic() ? 1 : 0; }
 void snn_set_dependent_launch(int on) { set_pdl(on); }

@@ -874,6 +874,12 @@ static CUresult g_encode(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank
     return r;
 }
 
+// Plan-only mode (snn_conv_plan): the host-side launch planning below runs exactly as for a launch, but tensor maps are not
+// encoded, no CUDA call is made and nothing is launched; the chosen configuration lands in t_plan.v.  Usable without a GPU
+// (the SM count then defaults to 148), which is how the CPU test suite covers this logic.
+struct PlanSink { bool active = false; int v[24]; };
+static thread_local PlanSink t_plan;
+
 static int get_encode() {
     std::call_once(g_encode_once, [] {
         void* fn = nullptr;
@@ -891,6 +897,7 @@ static int get_encode() {
 //   hnw   : (plain only) dimensions 3 and 4 swapped -> (C, W, 1, NB, H): a box lands in shared memory ordered (h, n, w)
 static int make_act_map(CUtensorMap* m, const void* ptr, int NB, int H, int W, int C, long long ld, int phase_view,
                         int box_n, int box_h, int box_w, int hnw = 0) {
+    if (t_plan.active) return 0;
     if (get_encode()) return 2;
     SNN_REQUIRE(((uintptr_t)ptr & 15) == 0, "activation pointer must be 16-byte aligned");
     SNN_REQUIRE(ld % 8 == 0 && C % 8 == 0, "activation channels/stride must be multiples of 8 (C=%d ld=%lld)", C, ld);
@@ -924,6 +931,7 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int NB, int H, int W, i
 
 // weights bf16 [wN][wT][wK] -> 3-D map (k, tap, n), box (64, 1, box_n)
 static int make_w_map(CUtensorMap* m, const void* ptr, int wN, int wT, int wK, int box_n) {
+    if (t_plan.active) return 0;
     if (get_encode()) return 2;
     SNN_REQUIRE(((uintptr_t)ptr & 15) == 0, "weight pointer must be 16-byte aligned");
     SNN_REQUIRE(wK % 8 == 0, "weight K extent must be a multiple of 8 (got %d)", wK);
@@ -942,6 +950,7 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int wN, int wT, int wK, i
 // coordinate selects the column phase.
 static int make_out_map(CUtensorMap* m, void* ptr, int f32, int NB, int Ho, int Wo, int n_store, long long ld, int os,
                         int sbw, int sbh, int sbn, int hnw = 0) {
+    if (t_plan.active) return 0;
     if (get_encode()) return 2;
     const cuuint64_t es = f32 ? 4 : 2;
     cuuint64_t dims[5], strides[4];
@@ -1065,11 +1074,13 @@ static bool strip_mode_ok(const ConvGemmParams& p) {
 
 static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const WDesc& wd, ConvGemmParams& p, cudaStream_t st) {
     static PerDeviceOnce once;
-    SNN_CUDA_OK(once.run([] {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        return e;
-    }));
+    if (!t_plan.active) {
+        SNN_CUDA_OK(once.run([] {
+            cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+            return e;
+        }));
+    }
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     bool pair = pair_possible(p);
     // K chunks per work item: small-K convs (1x1, transposed) are bound by per-tile latencies, not by operand traffic:
@@ -1121,6 +1132,15 @@ static int launch_conv_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const 
 #else
     p.dbg = 0;
 #endif
+    if (t_plan.active) {
+        const int tiles = (pair ? (m_tiles + 1) / 2 : m_tiles) * p.n_blocks * p.nphase * p.ksplit;
+        const int workers = pair ? num_sms() / 2 : num_sms();
+        const int v[20] = {p.bn, p.bh, p.bw, p.BN, pair ? 1 : 0, p.ntap > 1 ? 1 : 0, p.hnw, p.stages, p.stage_bytes, p.cps, p.ksplit,
+                           tiles, p.n_blocks, workers < tiles ? workers : tiles, p.epi_groups, small_k ? 1 : 0, p.tma_out, (int)smem,
+                           p.a_bytes, p.b_bytes};
+        for (int i = 0; i < 20; ++i) t_plan.v[i] = v[i];
+        return 0;
+    }
     CUtensorMap b, o;
     if (make_w_map(&b, wd.ptr, wd.wN, wd.wT, wd.wK, p.b_mn ? 64 : bn_cta)) return 2;
     if (p.tma_out) {
@@ -1348,7 +1368,7 @@ int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long lo
             for (int bb = 0; bb < 2; ++bb) ph.seg[ph.nseg++] = mkseg(0, (int)(bb * ld_dy), 0, a, 0, a * 2 + bb, 0, Cout);
     }
     if (ks > 1) {
-        SNN_CUDA_OK(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)NB * H * W * Ci, st));
+        if (!t_plan.active) SNN_CUDA_OK(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)NB * H * W * Ci, st));
         p.ksplit = ks;
         p.accumulate = 1;
     }
@@ -1361,11 +1381,13 @@ int conv_dgrad(int geom, int NB, int H, int W, const void* dy, int Cout, long lo
 int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long ld_x, const void* dy, int Cout,
                long long ld_dy, float* dw, int w_K, int w_coff, cudaStream_t st) {
     static PerDeviceOnce once;
-    SNN_CUDA_OK(once.run([] {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        return e;
-    }));
+    if (!t_plan.active) {
+        SNN_CUDA_OK(once.run([] {
+            cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+            return e;
+        }));
+    }
     SNN_REQUIRE(Ci % 8 == 0 && Cout % 8 == 0 && w_K % 4 == 0 && w_coff % 4 == 0, "conv_wgrad: channel counts must be multiples of 8");
     WgradParams p;
     memset(&p, 0, sizeof(p));
@@ -1449,7 +1471,7 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
     CUtensorMap mg, mx, mw;
     if (make_act_map(&mg, dy, NB, Hy, Wy, Cout, ld_dy, g_phase, p.bn, p.bh, p.bw, p.hnw)) return 2;
     if (make_act_map(&mx, x, NB, H, W, Ci, ld_x, x_phase, p.bn, p.strip ? p.bh + 2 : p.bh, p.bw, p.hnw)) return 2;
-    {   // dW fp32 [Cout][taps][w_K] -> 3-D reduce-add map (k, tap, n), box 32 x 1 x 32
+    if (!t_plan.active) {   // dW fp32 [Cout][taps][w_K] -> 3-D reduce-add map (k, tap, n), box 32 x 1 x 32
         if (get_encode()) return 2;
         SNN_REQUIRE(((uintptr_t)dw & 15) == 0, "conv_wgrad: dw must be 16-byte aligned");
         cuuint64_t dims[3] = {(cuuint64_t)w_K, (cuuint64_t)taps, (cuuint64_t)Cout};
@@ -1464,6 +1486,12 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
     const int items = base * p.ksplit;
     int nw = workers < items ? workers : items;
     if (g_debug_flags[5] > 0 && nw > g_debug_flags[5]) nw = g_debug_flags[5];
+    if (t_plan.active) {
+        const int v[20] = {p.bn, p.bh, p.bw, p.NT, pair ? 1 : 0, p.strip, p.hnw, p.stages, p.stage_bytes, 1, p.ksplit, items, p.n_ci_tiles, nw, 1, 0, 1,
+                           (int)smem, p.strip ? p.x_box_bytes : 8192, 2 * 8192};
+        for (int i = 0; i < 20; ++i) t_plan.v[i] = v[i];
+        return 0;
+    }
     if (!pair) {
         return check_cuda(launch_pdl(wgrad_gemm_kernel<false>, dim3(nw), dim3(192), smem, st, mg, mx, mw, p), "wgrad_gemm_kernel launch");
     }
@@ -1481,6 +1509,26 @@ int conv_wgrad(int geom, int NB, int H, int W, const void* x, int Ci, long long 
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
     return check_cuda(cudaLaunchKernelEx(&cfg, wgrad_gemm_kernel<true>, mg, mx, mw, p), "wgrad_gemm_kernel<pair> launch");
+}
+
+// kind: 0 fprop, 1 dgrad, 2 wgrad.  out[20] = {bn, bh, bw, N tile (BN | NT), CTA pair, row-strip mode, (h,n,w) row order, stages,
+// stage bytes, K chunks per stage, K split, work items, N blocks (| cin tiles), CTAs (pairs) launched, epilogue warp groups, small-K,
+// TMA-store epilogue, dynamic shared memory bytes, A (| X box) bytes per stage and tap group, B (| dY) bytes per tap}
+int conv_plan(int kind, int geom, int NB, int H, int W, int Cin, int Cout, int out_f32, int frames_per_step, int accumulate, int* out) {
+    void* const dummy = reinterpret_cast<void*>((uintptr_t)1 << 20);      // aligned, never dereferenced
+    t_plan.active = true;
+    for (int i = 0; i < 24; ++i) t_plan.v[i] = 0;
+    int rc;
+    if (kind == 0)
+        rc = conv_fprop(geom, NB, H, W, dummy, Cin, Cin, nullptr, 0, 0, dummy, Cout, Cin, 0, Cout, 0, nullptr, dummy, out_f32, Cout, 0, accumulate,
+                        nullptr, frames_per_step > 0 ? static_cast<float*>(dummy) : nullptr, frames_per_step);
+    else if (kind == 1)
+        rc = conv_dgrad(geom, NB, H, W, dummy, Cout, Cout, dummy, Cin, 0, Cin, dummy, out_f32, Cin, 0, accumulate, nullptr);
+    else
+        rc = conv_wgrad(geom, NB, H, W, dummy, Cin, Cin, dummy, Cout, Cout, static_cast<float*>(dummy), Cin, 0, nullptr);
+    t_plan.active = false;
+    if (rc == 0) for (int i = 0; i < 20; ++i) out[i] = t_plan.v[i];
+    return rc;
 }
 
 }  // namespace snn

@@ -148,6 +148,22 @@ def conv_wgrad(geom, x, dy, dw, w_coff=0):
     return dw
 
 
+PLAN_FIELDS = ("bn", "bh", "bw", "n_tile", "pair", "strip", "hnw", "stages", "stage_bytes", "chunks_per_stage", "ksplit", "items",
+               "n_blocks", "ctas", "epi_groups", "small_k", "tma_out", "smem_bytes", "a_bytes", "b_bytes")
+
+
+def conv_plan(kind, geom, nb, h, w, cin, cout, out_f32=True, frames_per_step=0, accumulate=False):
+    """Launch plan of conv_fprop ('fprop') / conv_dgrad ('dgrad') / conv_wgrad ('wgrad') for these shapes, without launching
+    (host logic only: works without a GPU).  Returns a dict over PLAN_FIELDS (see snn_conv_plan in include/snn_b200.h)."""
+    import ctypes
+    out = (ctypes.c_int * 20)()
+    rc = _lib.lib().snn_conv_plan({"fprop": 0, "dgrad": 1, "wgrad": 2}[kind], geom, nb, h, w, cin, cout, int(out_f32), frames_per_step,
+                             int(accumulate), out)
+    if rc:
+        raise _lib.SnnKernelError(f"snn_conv_plan failed (rc={rc}): {_lib.lib().snn_last_error().decode()}")
+    return dict(zip(PLAN_FIELDS, list(out)))
+
+
 def weight_prep(w_master, want_fprop=True, want_dgrad=True, wf=None, wt=None):
     """fp32 [N][T][K] -> (bf16 [N][T][K], bf16 [K][T][N])."""
     require_cuda(w_master)
